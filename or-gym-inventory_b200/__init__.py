@@ -1,0 +1,19 @@
+"""B200-native batched simulator for the step dynamics of jacklu2016/or-gym-inventory.
+
+Drop-in (vectorised) replacements for the reference's three env families, same class names and
+constructor keywords, each running `num_envs` instances on one GPU behind a C-ABI CUDA library:
+
+    from or_gym_inventory_b200 import InvManagementBacklogEnv
+    env = InvManagementBacklogEnv(num_envs=1 << 20, device="cuda:0")
+    obs, info = env.reset(seed=0)
+    obs, reward, terminated, truncated, info = env.step(actions)      # torch CUDA tensors, zero-copy
+    out = env.rollout("base_stock")                                   # fused 30-period rollout
+
+Importing the package does not load the CUDA library; constructing an env does, and raises if the
+library has not been built (there is no CPU fallback).
+"""
+from . import _capi  # noqa: F401
+from .inventory_management import (InvManagementBacklogEnv, InvManagementLostSalesEnv,  # noqa: F401
+                                   InvManagementMasterEnv, InvManagementParams)
+
+__version__ = "0.1.0"
