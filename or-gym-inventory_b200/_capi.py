@@ -164,8 +164,11 @@ def lib():
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a).  or-gym-inventory_b200 has no CPU fallback.")
         L = C.CDLL(LIB_PATH)
+        missing = [name for name in SYMBOLS if not hasattr(L, name)]
+        if missing:  # the header and the library disagree: refuse to run on a partial build
+            raise ImportError(f"{LIB_PATH} does not export {missing}; rebuild it")
         for name, (res, args) in SYMBOLS.items():
-            f = getattr(L, name)  # AttributeError if the header and the library disagree
+            f = getattr(L, name)
             f.restype = res
             f.argtypes = args
         _lib = L

@@ -1,0 +1,272 @@
+// common.cuh -- shared host/device utilities of liborgym_b200.so (sm_100a only).
+//
+//  * error plumbing for the C ABI (thread-local last error, CUDA checks)
+//  * Philox4x32-10 counter-based generator and the stream/counter conventions
+//  * alias-table sampling for the fixed demand distributions, PTRS/inversion for per-env Poisson means
+//  * 1-D bulk async copies (TMA engine: cp.async.bulk, SASS UBLKCP) used to move the row-major
+//    [env][obs_dim] / [env][act_dim] tiles of the Gymnasium-facing tensors between HBM and shared memory
+//  * numpy-order summation helpers
+//
+// The whole library is compiled with --fmad=false: the reference (numpy / CPython) never contracts a*b+c,
+// and rewards are checked bit-for-bit against it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/orgym_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// host: errors
+// ------------------------------------------------------------------------------------------------
+void orgym_set_error(const char* fmt, ...);
+
+#define ORGYM_CUDA(call)                                                                      \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            orgym_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return ORGYM_E_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define ORGYM_REQUIRE(cond, ...)        \
+    do {                                \
+        if (!(cond)) {                  \
+            orgym_set_error(__VA_ARGS__); \
+            return ORGYM_E_INVALID;     \
+        }                               \
+    } while (0)
+
+enum { FAM_INVMGMT = 1, FAM_NEWSVENDOR = 2, FAM_NETINV = 3 };
+
+// every family handle starts with this header (orgym_errors / destroy dispatch on it)
+struct HandleBase {
+    uint32_t magic;  // 'ORGY'
+    int family;
+    int device;
+    int64_t num_envs;
+    uint32_t* err_dev;  // sticky device error bits
+};
+#define ORGYM_MAGIC 0x4F524759u
+
+int orgym_handle_base_init(HandleBase* b, int family, int device, int64_t num_envs);
+void orgym_handle_base_free(HandleBase* b);
+int orgym_check_handle(const void* h, int family);
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// alias tables (host builder in dist.cu)
+// ------------------------------------------------------------------------------------------------
+struct AliasDev {
+    const uint2* table;  // [1 << log2k] {threshold (u32, accept if u < thr), alias index}
+    int32_t log2k;
+    int32_t base;        // sample = base + index
+    int32_t kind;        // ORGYM_DIST_*; ORGYM_DIST_USER -> trace lookup
+    const int64_t* user_D;
+    int32_t user_D_len;
+    int32_t user_clamp;  // 1: index min(t, len-1) (network env), 0: 0 beyond the end (serial env)
+};
+
+// builds the table on the host and uploads it; *out_dev_alloc receives the cudaMalloc'd pointer to free later
+int orgym_build_alias(const orgym_dist_t* d, int user_clamp, AliasDev* out, std::vector<void*>* allocs);
+// host pmf used by the builder and exposed for tests
+int orgym_dist_pmf(const orgym_dist_t* d, std::vector<double>* pmf, int64_t* base);
+
+// ------------------------------------------------------------------------------------------------
+// device: Philox4x32-10
+// ------------------------------------------------------------------------------------------------
+#define PHILOX_M0 0xD2511F53u
+#define PHILOX_M1 0xCD9E8D57u
+#define PHILOX_W0 0x9E3779B9u
+#define PHILOX_W1 0xBB67AE85u
+
+// counter word 2 = stream id
+enum {
+    STREAM_DEMAND = 0,    // c0 = period >> 1 (two alias samples per block), c3 = demand source (retail link) index
+    STREAM_ACTION = 1,    // random-action policy: c0 = period, c3 = stage group (4 stages per block)
+    STREAM_PARAMS = 2,    // newsvendor reset uniforms: c0 = 0..2
+    STREAM_POISSON_MU = 3 // per-env-mean Poisson: c0 = period, c3 = attempt
+};
+
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = mulhi32(PHILOX_M0, c.x), lo0 = PHILOX_M0 * c.x;
+        uint32_t hi1 = mulhi32(PHILOX_M1, c.z), lo1 = PHILOX_M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += PHILOX_W0;
+        k1 += PHILOX_W1;
+    }
+    return c;
+}
+
+__host__ __device__ __forceinline__ uint4 philox_block(uint64_t key, uint32_t c0, uint32_t episode, uint32_t stream,
+                                                       uint32_t c3) {
+    return philox4x32_10(make_uint4(c0, episode, stream, c3), (uint32_t)key, (uint32_t)(key >> 32));
+}
+
+// 53-bit uniform in [0,1) from two 32-bit words (same construction as numpy's next_double)
+__host__ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+    uint64_t x = ((uint64_t)hi << 32) | lo;
+    return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// one alias-table draw from two random words; the table may live in shared or global memory
+__device__ __forceinline__ int32_t alias_draw(const uint2* __restrict__ table, int log2k, int base, uint32_t u1,
+                                               uint32_t u2) {
+    uint32_t idx = log2k ? (u1 >> (32 - log2k)) : 0u;
+    uint2 e = table[idx];
+    return base + (int32_t)(u2 < e.x ? idx : e.y);
+}
+
+// demand for (key, episode, period t, source r) from a fixed distribution
+__device__ __forceinline__ int64_t sample_fixed(const AliasDev& A, const uint2* table, uint64_t key, uint32_t episode,
+                                                int t, uint32_t source) {
+    if (A.kind == ORGYM_DIST_USER) {
+        int idx = t;
+        if (A.user_clamp) idx = t < A.user_D_len - 1 ? t : A.user_D_len - 1;
+        return (idx >= 0 && idx < A.user_D_len) ? A.user_D[idx] : 0;
+    }
+    uint4 w = philox_block(key, (uint32_t)t >> 1, episode, STREAM_DEMAND, source);
+    return (t & 1) ? alias_draw(table, A.log2k, A.base, w.z, w.w) : alias_draw(table, A.log2k, A.base, w.x, w.y);
+}
+
+// Poisson with a per-call mean (Newsvendor: mu differs per env).  mu >= 10: Hoermann's PTRS transformed
+// rejection in float64 (the algorithm numpy uses); mu < 10: CDF inversion by sequential search from one
+// 53-bit uniform.  Keyed by (key, episode, t); rejection attempts advance counter word 3.
+__device__ __forceinline__ int64_t poisson_mu(double mu, uint64_t key, uint32_t episode, int t) {
+    if (!(mu > 0.0)) return 0;
+    if (mu < 10.0) {
+        uint4 w = philox_block(key, (uint32_t)t, episode, STREAM_POISSON_MU, 0);
+        double u = u53(w.x, w.y), p = exp(-mu), s = p;
+        int64_t x = 0;
+        while (u > s && x < 200) {
+            x += 1;
+            p *= mu / (double)x;
+            s += p;
+        }
+        return x;
+    }
+    double slam = sqrt(mu), loglam = log(mu), b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (uint32_t attempt = 0;; attempt++) {
+        uint4 w = philox_block(key, (uint32_t)t, episode, STREAM_POISSON_MU, attempt);
+        double U = u53(w.x, w.y) - 0.5, V = u53(w.z, w.w), us = 0.5 - fabs(U);
+        double kf = floor((2.0 * a / us + b) * U + mu + 0.43);
+        if (us >= 0.07 && V <= vr) return (int64_t)kf;
+        if (kf < 0.0 || (us < 0.013 && V > us)) continue;
+        if ((log(V) + log(invalpha) - log(a / (us * us) + b)) <= (-mu + kf * loglam - lgamma(kf + 1.0)))
+            return (int64_t)kf;
+        if (attempt > 1000u) return (int64_t)kf;  // unreachable in practice; bounds the loop
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// device: numpy summation order (np.add.reduce pairwise: sequential below 8, 8 partial sums up to 128)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CAP>
+__device__ __forceinline__ T np_sum_reg(const T (&a)[CAP], int n) {
+    if (n < 8) {
+        T res = (T)0;
+#pragma unroll
+        for (int i = 0; i < CAP; i++)
+            if (i < n && i < 7) res = res + a[i];
+        return res;
+    }
+    T r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = a[i < CAP ? i : 0];
+    int full = n - (n % 8);
+#pragma unroll
+    for (int i = 8; i < CAP; i++)
+        if (i < full) r[i % 8] = r[i % 8] + a[i];
+    T res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll
+    for (int i = 8; i < CAP; i++)
+        if (i >= full && i < n) res = res + a[i];
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device: 1-D bulk async copies through the TMA engine (cp.async.bulk; SASS UBLKCP) + mbarrier
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a lost transaction traps (error return) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!done && spin > (1u << 24)) __trap();
+    }
+}
+// global -> shared, completion signalled on an mbarrier.  dst/src 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global (bulk group)
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy before a bulk store reads them
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// streaming (evict-first) scalar accesses for state that is touched once per launch
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T* p) {
+    return __ldcs(p);
+}
+template <typename T>
+__device__ __forceinline__ void st_stream(T* p, T v) {
+    __stcs(p, v);
+}
+
+#define ORGYM_TILE 128  // env instances per CTA in the step kernels
+
+static inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }

@@ -1,0 +1,900 @@
+// invmgmt.cu -- serial multi-echelon env (reference: inventory_management.py).
+//
+// Kernels (one env instance per thread, all instances independent):
+//   inv_reset_kernel    reset (inventory_management.py:186-222) + first observation (:354-391)
+//   inv_step_kernel     one period (:224-352) + observation; HBM-bound: struct-of-arrays state is read and
+//                       written coalesced, the row-major [env][obs_dim] observation tile and the [env][n] action
+//                       tile go through shared memory and the TMA engine (cp.async.bulk)
+//   inv_rollout_kernel  fused reset + `periods` steps with on-device policy and Philox demand; on-hand
+//                       inventory / backlog in registers, lead-time rings in shared memory; issue-bound
+//   inv_reduce_kernel   deterministic reduction of the per-CTA episode statistics
+//
+// Integer state is exact (int64, or int32 with a range guard); rewards are float64 evaluated in the reference's
+// operation order (no FMA contraction: the library is built with --fmad=false).
+#include "common.cuh"
+
+#define MAXN ORGYM_INV_MAX_STAGES
+
+struct InvDev {
+    int n, m, T, backlog, lt_max, obs_dim, sumL;
+    int L[MAXN], roff[MAXN];
+    long long c[MAXN], I0[MAXN];
+    double up[MAXN + 1], uc[MAXN + 1], kc[MAXN + 1], hc[MAXN + 1];
+    const double* disc;  // [T] alpha**t, computed on the host with libm pow like CPython's float.__pow__
+    AliasDev dem;
+};
+
+struct InvHandle {
+    HandleBase base;
+    InvDev dev;
+    int wide;
+    int64_t npad;
+    std::vector<void*> allocs;
+    double* partials;  // [max_blocks][8] rollout block partial sums
+    int max_blocks;
+};
+
+// ---- state layout: field[slot][env], env stride npad -------------------------------------------------------
+// [key u64][S slots: I n | B m | Rring sumL | Aring lt_max*n][period i32][episode u32]
+template <typename S>
+struct InvState {
+    uint64_t* key;
+    S* f;
+    int32_t* period;
+    uint32_t* episode;
+    int64_t npad;
+    int oI, oB, oR, oA;
+    __host__ __device__ InvState(void* base, int64_t npad_, const InvDev& P) : npad(npad_) {
+        char* p = (char*)base;
+        key = (uint64_t*)p;
+        p += 8 * npad;
+        f = (S*)p;
+        oI = 0;
+        oB = P.n;
+        oR = P.n + P.m;
+        oA = P.n + P.m + P.sumL;
+        p += sizeof(S) * npad * (size_t)(oA + P.lt_max * P.n);
+        period = (int32_t*)p;
+        p += 4 * npad;
+        episode = (uint32_t*)p;
+    }
+    __device__ __forceinline__ S& at(int slot, int64_t e) const { return f[(size_t)slot * npad + e]; }
+};
+static int64_t inv_state_bytes(const InvDev& P, int64_t npad, int wide) {
+    int64_t slots = P.n + P.m + P.sumL + (int64_t)P.lt_max * P.n;
+    return npad * (8 + (wide ? 8 : 4) * slots + 8);
+}
+
+#define INT32_GUARD (1 << 29)
+
+struct InvStepArgs {
+    int64_t N, npad;
+    void* state;
+    const void* actions;
+    int act_f64;
+    const int64_t* demand;
+    int autoreset;
+    int64_t* obs;
+    double* reward;
+    uint8_t* terminated;
+    uint8_t* truncated;
+    int64_t* info_demand;
+    int64_t* info_sales;
+    int64_t* info_unf;
+    double* info_profit;
+    int64_t* final_obs;
+    uint32_t* err;
+    int use_bulk;
+};
+
+// ---- one period of one env: shared by the step and rollout kernels --------------------------------------------
+// in:  t, req[i] (requested order, already max(a,0) truncated), arr[i] = R[t-L_i] for L_i > 0 (0 before t = L_i),
+//      d = demand sample.   state: I[], B[] (B[] all-zero in lost-sales mode).
+// out: Rf[] fulfilled orders, s0 retail sales, U0 unfulfilled retail demand, profit (undiscounted).
+template <int NS, bool EXACT, typename S>
+__device__ __forceinline__ double inv_period(const InvDev& P, const S (&req)[NS], const S (&arr)[NS], S d, S (&I)[NS],
+                                             S (&B)[NS + 1], S (&Rf)[NS], S& s0_out, S (&U)[NS + 1]) {
+    const int n = EXACT ? NS : P.n;
+    S cur[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+        if (EXACT || i < n) {
+            cur[i] = req[i] + B[i + 1];                   // :253-255 (B is zero at t = 0)
+            S r = cur[i] < (S)P.c[i] ? cur[i] : (S)P.c[i];  // :263
+            if (i + 1 < n) r = I[i + 1] < r ? I[i + 1] : r; // :265 supplier's start-of-period on-hand (may be < 0)
+            Rf[i] = r;
+        }
+    }
+    S Ic[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++)
+        if (EXACT || i < n) Ic[i] = I[i] + (P.L[i] == 0 ? Rf[i] : arr[i]);  // :271-277
+    d = d > 0 ? d : 0;                                                      // :280
+    S fill = d + B[0];                                                      // :284-286
+    S s0 = Ic[0] < fill ? Ic[0] : fill;                                     // :288
+    Ic[0] -= s0;
+#pragma unroll
+    for (int i = 1; i < NS; i++)
+        if (EXACT || i < n) Ic[i] -= Rf[i];  // :300 (the stage's own inbound order -- reference quirk)
+    U[0] = fill - s0;                        // :303
+#pragma unroll
+    for (int i = 0; i < NS; i++)
+        if (EXACT || i < n) U[i + 1] = cur[i] - Rf[i];  // :304
+    // profit :315-321: elementwise float64, then np.sum over the m stages
+    double term[NS + 1];
+#pragma unroll
+    for (int j = 0; j <= NS; j++) {
+        if (EXACT || j <= n) {
+            S sj = j == 0 ? s0 : Rf[j - 1];
+            S inv = 0;
+            if (j < n) inv = Ic[j] > 0 ? Ic[j] : 0;
+            double s = (double)sj;
+            double rev = P.up[j] * s, pc = P.uc[j] * s;
+            double hold = P.hc[j] * (double)inv, pen = P.kc[j] * (double)U[j];
+            term[j] = ((rev - pc) - hold) - pen;
+        } else
+            term[j] = 0.0;
+    }
+    double profit = np_sum_reg<double, NS + 1>(term, n + 1);
+#pragma unroll
+    for (int i = 0; i < NS; i++)
+        if (EXACT || i < n) I[i] = Ic[i];  // :326
+#pragma unroll
+    for (int j = 0; j <= NS; j++)
+        if (EXACT || j <= n) B[j] = P.backlog ? U[j] : (S)0;  // :307-312
+    s0_out = s0;
+    return profit;
+}
+
+// ---- tile movers: row-major [TILE][width] tiles of the API tensors <-> shared memory --------------------------
+// dense tile (stride == width) + full tile + 16-byte multiples -> one bulk async copy; else cooperative loop.
+template <typename T>
+__device__ __forceinline__ void tile_store(T* __restrict__ g, const T* s, int width, int stride, int nvalid, bool bulk) {
+    if (bulk) {
+        fence_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_s2g(g, s, (uint32_t)(nvalid * width * sizeof(T)));
+            bulk_commit();
+            bulk_wait_read0();
+        }
+    } else {
+        __syncthreads();
+        int total = nvalid * width;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            int r = i / width, c = i - r * width;
+            g[i] = s[r * stride + c];
+        }
+    }
+}
+
+// ---- reset ------------------------------------------------------------------------------------------------------
+template <typename S>
+__device__ __forceinline__ void inv_reset_env(const InvDev& P, const InvState<S>& st, int64_t e) {
+    for (int i = 0; i < P.n; i++) st.at(st.oI + i, e) = (S)P.I0[i];
+    for (int j = 0; j < P.m; j++) st.at(st.oB + j, e) = 0;
+    for (int k = 0; k < P.sumL; k++) st.at(st.oR + k, e) = 0;
+    for (int k = 0; k < P.lt_max * P.n; k++) st.at(st.oA + k, e) = 0;
+    st.period[e] = 0;
+}
+
+template <typename S>
+__global__ void inv_reset_kernel(const __grid_constant__ InvDev P, int64_t N, int64_t npad, void* state, int reseed,
+                                 uint64_t seed, int64_t env_offset, const uint8_t* __restrict__ mask,
+                                 int64_t* __restrict__ obs) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    if (mask && !mask[e]) return;
+    InvState<S> st(state, npad, P);
+    inv_reset_env(P, st, e);
+    if (reseed) {
+        st.key[e] = seed + (uint64_t)(env_offset + e);  // gymnasium vector convention: env i <- seed + i
+        st.episode[e] = 0;
+    } else
+        st.episode[e] += 1;
+    int64_t* o = obs + e * P.obs_dim;
+    for (int k = 0; k < P.obs_dim; k++) o[k] = k < P.n ? P.I0[k] : 0;
+}
+
+// ---- step ------------------------------------------------------------------------------------------------------
+template <int NS, bool EXACT, typename S>
+__global__ void __launch_bounds__(ORGYM_TILE) inv_step_kernel(const __grid_constant__ InvDev P, const InvStepArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int n = EXACT ? NS : P.n, m = n + 1;
+    const int tid = threadIdx.x;
+    const int64_t e0 = (int64_t)blockIdx.x * ORGYM_TILE, e = e0 + tid;
+    const int nvalid = (int)((A.N - e0) < ORGYM_TILE ? (A.N - e0) : ORGYM_TILE);
+    const bool valid = tid < nvalid;
+    const bool full = nvalid == ORGYM_TILE;
+    const bool obs_dense = (P.obs_dim & 1) != 0;  // odd row length: conflict-free dense tile
+    const int ostride = obs_dense ? P.obs_dim : P.obs_dim + 1;
+    const bool bulk_out = A.use_bulk && full && obs_dense;
+    const bool bulk_in = A.use_bulk && full;
+    // shared: obs tile | action tile | mbarrier | alias table
+    int64_t* obs_tile = (int64_t*)smem;
+    size_t off = (size_t)ORGYM_TILE * ostride * 8;
+    unsigned char* act_tile = smem + off;
+    off += (size_t)ORGYM_TILE * n * 8;
+    uint64_t* bar = (uint64_t*)(smem + off);
+    off += 16;
+    uint2* tab = (uint2*)(smem + off);
+
+    if (bulk_in && tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (bulk_in) {
+        if (tid == 0) {
+            uint32_t bytes = (uint32_t)(ORGYM_TILE * n * 8);
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(act_tile, (const char*)A.actions + (size_t)e0 * n * 8, bytes, bar);
+        }
+    } else {
+        const int64_t* src = (const int64_t*)A.actions + (size_t)e0 * n;
+        for (int i = tid; i < nvalid * n; i += ORGYM_TILE) ((int64_t*)act_tile)[i] = src[i];
+    }
+    const bool sample = A.demand == nullptr && P.dem.kind != ORGYM_DIST_USER;
+    if (sample)
+        for (int i = tid; i < (1 << P.dem.log2k); i += ORGYM_TILE) tab[i] = P.dem.table[i];
+
+    InvState<S> st(A.state, A.npad, P);
+    S I[NS], B[NS + 1];
+    int t = 0;
+    uint32_t episode = 0;
+    uint64_t key = 0;
+    bool do_step = valid;
+    if (valid) {
+        t = st.period[e];
+        episode = st.episode[e];
+        key = st.key[e];
+        if (t >= P.T) {  // episode already over
+            do_step = false;
+            if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {
+                inv_reset_env(P, st, e);
+                st.episode[e] = episode + 1;
+                for (int k = 0; k < P.obs_dim; k++) obs_tile[tid * ostride + k] = k < n ? P.I0[k] : 0;
+                A.reward[e] = 0.0;
+                A.terminated[e] = 0;
+                A.truncated[e] = 0;
+            } else {  // reference: IndexError on R[t] (inventory_management.py:267)
+                atomicOr(A.err, ORGYM_ERR_STEP_PAST_END);
+                const int64_t* old = A.obs + e * P.obs_dim;
+                for (int k = 0; k < P.obs_dim; k++) obs_tile[tid * ostride + k] = old[k];
+                A.reward[e] = 0.0;
+                A.terminated[e] = 0;
+                A.truncated[e] = 1;
+            }
+        }
+    }
+    if (do_step) {
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+            if (EXACT || i < n) I[i] = st.at(st.oI + i, e);
+#pragma unroll
+        for (int j = 0; j <= NS; j++)
+            if (EXACT || j <= n) B[j] = st.at(st.oB + j, e);
+    }
+    if (bulk_in)
+        mbar_wait(bar, 0);
+    __syncthreads();  // action tile (cooperative path) and alias table visible
+
+    if (do_step) {
+        S req[NS], arr[NS], Rf[NS], U[NS + 1];
+        bool range_bad = false;
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            if (EXACT || i < n) {
+                long long a;
+                if (A.act_f64) {
+                    double x = ((const double*)act_tile)[tid * n + i];
+                    x = x > 0.0 ? x : 0.0;  // np.maximum(action, 0) :250
+                    a = (long long)x;       // astype(int64): truncation
+                } else {
+                    a = ((const long long*)act_tile)[tid * n + i];
+                    a = a > 0 ? a : 0;
+                }
+                if (sizeof(S) == 4 && a > INT32_GUARD) {
+                    range_bad = true;
+                    a = INT32_GUARD;
+                }
+                req[i] = (S)a;
+                arr[i] = 0;
+                if (P.L[i] > 0) arr[i] = st.at(st.oR + P.roff[i] + (t % P.L[i]), e);  // ring slot holds R[t-L_i]
+            }
+        }
+        long long dl;
+        if (A.demand)
+            dl = A.demand[e];
+        else
+            dl = sample_fixed(P.dem, tab, key, episode, t, 0u);
+        if (sizeof(S) == 4) {
+            if (dl > INT32_GUARD) { range_bad = true; dl = INT32_GUARD; }
+        }
+        S d = (S)dl, s0;
+        double profit = inv_period<NS, EXACT, S>(P, req, arr, d, I, B, Rf, s0, U);
+        double reward = P.disc[t] * profit;  // :322
+        // ---- write back state
+        if (sizeof(S) == 4) {
+#pragma unroll
+            for (int i = 0; i < NS; i++)
+                if (EXACT || i < n) range_bad |= (I[i] > INT32_GUARD) | (I[i] < -INT32_GUARD);
+#pragma unroll
+            for (int j = 0; j <= NS; j++)
+                if (EXACT || j <= n) range_bad |= (U[j] > INT32_GUARD) | (U[j] < -INT32_GUARD);
+            if (range_bad) atomicOr(A.err, ORGYM_ERR_INT32_RANGE);
+        }
+        const int tn = t + 1;
+        const bool trunc = tn >= P.T;  // :350
+        const bool reset_now = trunc && A.autoreset == ORGYM_AUTORESET_SAME_STEP;
+        int64_t* orow = obs_tile + tid * ostride;
+        // observation :354-391: on-hand, then the last min(t', lt_max) requested orders, oldest first, left aligned
+        const int Lm = P.lt_max;
+        const int k = tn < Lm ? tn : Lm;
+        if (!reset_now) {
+#pragma unroll
+            for (int i = 0; i < NS; i++)
+                if (EXACT || i < n) {
+                    st.at(st.oI + i, e) = I[i];
+                    orow[i] = (int64_t)I[i];
+                    if (P.L[i] > 0) st.at(st.oR + P.roff[i] + (t % P.L[i]), e) = Rf[i];
+                    if (Lm > 0) st.at(st.oA + (t % Lm) * n + i, e) = req[i];
+                }
+#pragma unroll
+            for (int j = 0; j <= NS; j++)
+                if (EXACT || j <= n) st.at(st.oB + j, e) = B[j];
+            st.period[e] = tn;
+            for (int q = 0; q < Lm; q++) {
+                int p = tn - k + q;  // period whose action sits at window position q
+                bool in = q < k;
+                int slot = in ? (p % Lm) : 0;
+                for (int i = 0; i < n; i++) {
+                    int64_t v = 0;
+                    if (in) v = (p == t) ? (int64_t)req[i] : (int64_t)st.at(st.oA + slot * n + i, e);
+                    orow[n + q * n + i] = v;
+                }
+            }
+        } else {
+            // SAME_STEP autoreset: the terminal observation goes to final_obs, the env restarts immediately
+            if (A.final_obs) {
+                int64_t* fo = A.final_obs + e * P.obs_dim;
+                for (int i = 0; i < n; i++) fo[i] = (int64_t)I[i];
+                for (int q = 0; q < Lm; q++) {
+                    int p = tn - k + q;
+                    bool in = q < k;
+                    int slot = in ? (p % Lm) : 0;
+                    for (int i = 0; i < n; i++) {
+                        int64_t v = 0;
+                        if (in) v = (p == t) ? (int64_t)req[i] : (int64_t)st.at(st.oA + slot * n + i, e);
+                        fo[n + q * n + i] = v;
+                    }
+                }
+            }
+            inv_reset_env(P, st, e);
+            st.episode[e] = episode + 1;
+            for (int q = 0; q < P.obs_dim; q++) orow[q] = q < n ? P.I0[q] : 0;
+        }
+        A.reward[e] = reward;
+        A.terminated[e] = 0;  // :349
+        A.truncated[e] = trunc ? 1 : 0;
+        if (A.info_demand) A.info_demand[e] = (int64_t)(d > 0 ? d : 0);
+        if (A.info_profit) A.info_profit[e] = profit;
+        if (A.info_sales) {
+            A.info_sales[e * m] = (int64_t)s0;
+            for (int i = 0; i < n; i++) A.info_sales[e * m + 1 + i] = (int64_t)Rf[i];
+        }
+        if (A.info_unf)
+            for (int j = 0; j < m; j++) A.info_unf[e * m + j] = (int64_t)U[j];
+    }
+    tile_store<int64_t>(A.obs + (size_t)e0 * P.obs_dim, obs_tile, P.obs_dim, ostride, nvalid, bulk_out);
+}
+
+// ---- export -----------------------------------------------------------------------------------------------------
+template <typename S>
+__global__ void inv_export_kernel(const __grid_constant__ InvDev P, int64_t N, int64_t npad, const void* state,
+                                  int64_t* __restrict__ I, int64_t* __restrict__ B, int32_t* __restrict__ period) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    InvState<S> st((void*)state, npad, P);
+    if (I)
+        for (int i = 0; i < P.n; i++) I[e * P.n + i] = (int64_t)st.at(st.oI + i, e);
+    if (B)
+        for (int j = 0; j < P.m; j++) B[e * P.m + j] = (int64_t)st.at(st.oB + j, e);
+    if (period) period[e] = st.period[e];
+}
+
+// ---- fused rollout ----------------------------------------------------------------------------------------------
+struct InvRolloutArgs {
+    int64_t N, env_offset;
+    uint64_t seed;
+    uint32_t episode;
+    int policy;
+    double target[MAXN];  // base-stock levels (L_i+1)*mu*sf as float64
+    const int64_t* actions;
+    int64_t a_se, a_st;
+    const int64_t* demand;
+    int64_t d_se, d_st;
+    double* ep_return;
+    int64_t* stats;
+    double* reward_traj;
+    int64_t* final_I;
+    int64_t* final_B;
+    double* partials;  // [gridDim.x][8]
+};
+
+#define ROLL_THREADS 128
+
+template <int NS, bool EXACT, typename S>
+__global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_constant__ InvDev P,
+                                                                   const __grid_constant__ InvRolloutArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int n = EXACT ? NS : P.n;
+    const int tid = threadIdx.x;
+    const int64_t e = (int64_t)blockIdx.x * ROLL_THREADS + tid;
+    const bool valid = e < A.N;
+    const bool need_aring = A.policy == ORGYM_POLICY_BASE_STOCK;
+    // shared: alias table | R rings [sumL][threads] | request rings [sumL][threads] (base-stock only)
+    uint2* tab = (uint2*)smem;
+    const int K = (P.dem.kind == ORGYM_DIST_USER) ? 0 : (1 << P.dem.log2k);
+    S* rring = (S*)(smem + (size_t)K * 8);
+    S* aring = rring + (size_t)P.sumL * ROLL_THREADS;
+    for (int i = tid; i < K; i += ROLL_THREADS) tab[i] = P.dem.table[i];
+    for (int k = 0; k < P.sumL; k++) {
+        rring[k * ROLL_THREADS + tid] = 0;
+        if (need_aring) aring[k * ROLL_THREADS + tid] = 0;
+    }
+    __syncthreads();
+
+    const uint64_t key = A.seed + (uint64_t)(A.env_offset + e);
+    S I[NS], B[NS + 1], psum[NS];
+    int rpos[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+        I[i] = (EXACT || i < n) ? (S)P.I0[i] : (S)0;
+        psum[i] = 0;
+        rpos[i] = 0;
+    }
+#pragma unroll
+    for (int j = 0; j <= NS; j++) B[j] = 0;
+    double ret = 0.0;
+    long long s_sales = 0, s_dem = 0, s_stock = 0, s_inv = 0;
+    uint4 w = make_uint4(0, 0, 0, 0);
+
+    for (int t = 0; t < P.T; t++) {
+        S req[NS], arr[NS], Rf[NS], U[NS + 1];
+        // ---- policy ---------------------------------------------------------------------------------------
+        if (A.policy == ORGYM_POLICY_BASE_STOCK) {
+            // benchmark_InvManagementBacklogEnv.py:152-198: position = on-hand + requested orders of the last L_i
+            // periods; q = clip(max(0, target - position), 0, c) in float64, truncated to int64
+#pragma unroll
+            for (int i = 0; i < NS; i++)
+                if (EXACT || i < n) {
+                    double q = A.target[i] - (double)(I[i] + psum[i]);
+                    q = q > 0.0 ? q : 0.0;
+                    double cap = (double)P.c[i];
+                    q = q < cap ? q : cap;
+                    req[i] = (S)(long long)q;
+                }
+        } else if (A.policy == ORGYM_POLICY_RANDOM) {
+            uint4 a4 = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int i = 0; i < NS; i++)
+                if (EXACT || i < n) {
+                    if ((i & 3) == 0) a4 = philox_block(key, (uint32_t)t, A.episode, STREAM_ACTION, (uint32_t)(i >> 2));
+                    uint32_t u = (i & 3) == 0 ? a4.x : (i & 3) == 1 ? a4.y : (i & 3) == 2 ? a4.z : a4.w;
+                    req[i] = (S)mulhi32(u, (uint32_t)P.c[i] + 1u);  // uniform on {0..c_i}
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NS; i++)
+                if (EXACT || i < n) {
+                    long long a = valid ? A.actions[e * A.a_se + (int64_t)t * A.a_st + i] : 0;
+                    a = a > 0 ? a : 0;
+                    req[i] = (S)a;
+                }
+        }
+        // ---- lead-time rings --------------------------------------------------------------------------------
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+            if (EXACT || i < n) {
+                arr[i] = 0;
+                if (P.L[i] > 0) arr[i] = rring[(P.roff[i] + rpos[i]) * ROLL_THREADS + tid];
+            }
+        // ---- demand -----------------------------------------------------------------------------------------
+        long long dl;
+        if (A.demand)
+            dl = valid ? A.demand[e * A.d_se + (int64_t)t * A.d_st] : 0;
+        else if (P.dem.kind == ORGYM_DIST_USER)
+            dl = t < P.dem.user_D_len ? P.dem.user_D[t] : 0;
+        else {
+            // one Philox block serves two periods: (x,y) at even t, (z,w) at odd t
+            if ((t & 1) == 0) w = philox_block(key, (uint32_t)t >> 1, A.episode, STREAM_DEMAND, 0u);
+            dl = (t & 1) ? alias_draw(tab, P.dem.log2k, P.dem.base, w.z, w.w)
+                         : alias_draw(tab, P.dem.log2k, P.dem.base, w.x, w.y);
+        }
+        S s0;
+        double profit = inv_period<NS, EXACT, S>(P, req, arr, (S)dl, I, B, Rf, s0, U);
+        double reward = P.disc[t] * profit;
+        ret += reward;  // Python: total += reward, in period order
+        if (A.reward_traj && valid) A.reward_traj[e * P.T + t] = reward;
+        s_sales += (long long)s0;
+        s_dem += dl > 0 ? dl : 0;
+        s_stock += (long long)U[0];
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+            if (EXACT || i < n) s_inv += I[i] > 0 ? (long long)I[i] : 0;
+        // ---- ring updates -----------------------------------------------------------------------------------
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+            if (EXACT || i < n) {
+                if (P.L[i] > 0) {
+                    int slot = (P.roff[i] + rpos[i]) * ROLL_THREADS + tid;
+                    rring[slot] = Rf[i];
+                    if (need_aring) {
+                        psum[i] += req[i] - aring[slot];
+                        aring[slot] = req[i];
+                    }
+                    rpos[i] = rpos[i] + 1 == P.L[i] ? 0 : rpos[i] + 1;
+                }
+            }
+    }
+    // ---- per-episode outputs --------------------------------------------------------------------------------------
+    if (valid) {
+        if (A.ep_return) A.ep_return[e] = ret;
+        if (A.stats) {
+            longlong4 v = make_longlong4(s_sales, s_dem, s_stock, s_inv);
+            *reinterpret_cast<longlong4*>(A.stats + e * 4) = v;
+        }
+        if (A.final_I)
+            for (int i = 0; i < n; i++) A.final_I[e * n + i] = (int64_t)I[i];
+        if (A.final_B)
+            for (int j = 0; j <= n; j++) A.final_B[e * (n + 1) + j] = (int64_t)B[j];
+    }
+    // ---- batch summary: warp shuffles -> one row of partials per CTA (summed in fixed order afterwards) -------
+    if (A.partials) {
+        double v[7];
+        v[0] = valid ? 1.0 : 0.0;
+        v[1] = valid ? ret : 0.0;
+        v[2] = valid ? ret * ret : 0.0;
+        v[3] = valid ? (double)s_sales : 0.0;
+        v[4] = valid ? (double)s_dem : 0.0;
+        v[5] = valid ? (double)s_stock : 0.0;
+        v[6] = valid ? (double)s_inv : 0.0;
+        __shared__ double red[ROLL_THREADS / 32][7];
+#pragma unroll
+        for (int q = 0; q < 7; q++) {
+            double x = v[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if ((tid & 31) == 0) red[tid >> 5][q] = x;
+        }
+        __syncthreads();
+        if (tid < 7) {
+            double x = 0.0;
+            for (int wv = 0; wv < ROLL_THREADS / 32; wv++) x += red[wv][tid];
+            A.partials[(size_t)blockIdx.x * 8 + tid] = x;
+        }
+    }
+}
+
+__global__ void orgym_reduce_partials_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out) {
+    // one warp per column; fixed summation order -> run-to-run deterministic
+    int col = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (col >= 8) return;
+    double x = 0.0;
+    for (int b = lane; b < nblocks; b += 32) x += col < 7 ? partials[(size_t)b * 8 + col] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) out[col] = x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side of the C ABI
+// ------------------------------------------------------------------------------------------------
+template <typename S>
+static void launch_step(const InvHandle* H, const InvStepArgs& A, size_t smem, cudaStream_t s) {
+    const InvDev& P = H->dev;
+    unsigned grid = (unsigned)((A.N + ORGYM_TILE - 1) / ORGYM_TILE);
+#define STEP_CASE(NSV)                                                                                              \
+    case NSV:                                                                                                       \
+        cudaFuncSetAttribute(inv_step_kernel<NSV, true, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        inv_step_kernel<NSV, true, S><<<grid, ORGYM_TILE, smem, s>>>(P, A);                                          \
+        break;
+    switch (P.n) {
+        STEP_CASE(1) STEP_CASE(2) STEP_CASE(3) STEP_CASE(4) STEP_CASE(5) STEP_CASE(6) STEP_CASE(7) STEP_CASE(8)
+        default:
+            cudaFuncSetAttribute(inv_step_kernel<MAXN, false, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            inv_step_kernel<MAXN, false, S><<<grid, ORGYM_TILE, smem, s>>>(P, A);
+    }
+#undef STEP_CASE
+}
+
+template <typename S>
+static void launch_rollout(const InvHandle* H, const InvRolloutArgs& A, size_t smem, cudaStream_t s) {
+    const InvDev& P = H->dev;
+    unsigned grid = (unsigned)((A.N + ROLL_THREADS - 1) / ROLL_THREADS);
+#define ROLL_CASE(NSV)                                                                                                 \
+    case NSV:                                                                                                          \
+        cudaFuncSetAttribute(inv_rollout_kernel<NSV, true, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        inv_rollout_kernel<NSV, true, S><<<grid, ROLL_THREADS, smem, s>>>(P, A);                                        \
+        break;
+    switch (P.n) {
+        ROLL_CASE(1) ROLL_CASE(2) ROLL_CASE(3) ROLL_CASE(4) ROLL_CASE(5) ROLL_CASE(6) ROLL_CASE(7) ROLL_CASE(8)
+        default:
+            cudaFuncSetAttribute(inv_rollout_kernel<MAXN, false, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem);
+            inv_rollout_kernel<MAXN, false, S><<<grid, ROLL_THREADS, smem, s>>>(P, A);
+    }
+#undef ROLL_CASE
+}
+
+extern "C" int orgym_invmgmt_create(const orgym_invmgmt_config_t* cfg, int64_t num_envs, int device,
+                                    orgym_handle_t* out) {
+    ORGYM_REQUIRE(cfg && out, "null argument");
+    const int m = cfg->num_stages, n = m - 1;
+    // the reference's input validation (inventory_management.py:144-167)
+    ORGYM_REQUIRE(m >= 2, "Minimum number of stages is 2");
+    ORGYM_REQUIRE(cfg->periods > 0, "Number of periods must be positive");
+    ORGYM_REQUIRE(cfg->alpha > 0 && cfg->alpha <= 1, "alpha must be in the range (0, 1]");
+    ORGYM_REQUIRE(cfg->init_inv && cfg->capacity && cfg->lead_time && cfg->unit_price && cfg->unit_cost &&
+                      cfg->demand_cost && cfg->holding_cost,
+                  "null config array");
+    if (n > MAXN) {
+        orgym_set_error("%d inventory stages exceed this build's limit of %d", n, MAXN);
+        return ORGYM_E_UNSUPPORTED;
+    }
+    InvHandle* H = new InvHandle();
+    InvDev& P = H->dev;
+    memset(&P, 0, sizeof(P));
+    P.n = n;
+    P.m = m;
+    P.T = cfg->periods;
+    P.backlog = cfg->backlog ? 1 : 0;
+    int rc = ORGYM_OK;
+    long long cmax = 0;
+    for (int i = 0; i < n && rc == ORGYM_OK; i++) {
+        if (cfg->init_inv[i] < 0) { orgym_set_error("Initial inventory cannot be negative"); rc = ORGYM_E_INVALID; }
+        if (cfg->capacity[i] <= 0) { orgym_set_error("Supply capacities must be positive"); rc = ORGYM_E_INVALID; }
+        if (cfg->lead_time[i] < 0) { orgym_set_error("Lead times cannot be negative"); rc = ORGYM_E_INVALID; }
+        if (cfg->lead_time[i] > ORGYM_INV_MAX_LEAD) {
+            orgym_set_error("lead time %lld exceeds this build's limit of %d", (long long)cfg->lead_time[i], ORGYM_INV_MAX_LEAD);
+            rc = ORGYM_E_UNSUPPORTED;
+        }
+        P.I0[i] = cfg->init_inv[i];
+        P.c[i] = cfg->capacity[i];
+        P.L[i] = (int)cfg->lead_time[i];
+        P.roff[i] = P.sumL;
+        P.sumL += P.L[i];
+        if (P.L[i] > P.lt_max) P.lt_max = P.L[i];
+        if (P.c[i] > cmax) cmax = P.c[i];
+        if (P.I0[i] > cmax) cmax = P.I0[i];
+    }
+    for (int j = 0; j < m && rc == ORGYM_OK; j++) {
+        P.up[j] = cfg->unit_price[j];
+        P.uc[j] = cfg->unit_cost[j];
+        P.kc[j] = cfg->demand_cost[j];
+        P.hc[j] = cfg->holding_cost[j];
+        if (P.up[j] < 0 || P.uc[j] < 0 || P.kc[j] < 0 || P.hc[j] < 0) {
+            orgym_set_error("prices and costs cannot be negative");
+            rc = ORGYM_E_INVALID;
+        }
+    }
+    if (rc == ORGYM_OK && !(cfg->dist.kind >= 1 && cfg->dist.kind <= 5)) {
+        orgym_set_error("dist must be one of 1, 2, 3, 4, 5");
+        rc = ORGYM_E_INVALID;
+    }
+    if (rc == ORGYM_OK && cfg->dist.kind == ORGYM_DIST_USER && cfg->dist.user_D_len != cfg->periods) {
+        orgym_set_error("User specified demand length != num periods");
+        rc = ORGYM_E_INVALID;
+    }
+    P.obs_dim = n * (P.lt_max + 1);
+    H->wide = cfg->wide_state ? 1 : 0;
+    if (rc == ORGYM_OK && !H->wide && cmax > (INT32_GUARD >> 8)) H->wide = 1;  // compact int32 state cannot hold it
+    if (rc == ORGYM_OK) rc = orgym_handle_base_init(&H->base, FAM_INVMGMT, device, num_envs);
+    if (rc != ORGYM_OK) {
+        delete H;
+        return rc;
+    }
+    DeviceGuard g(device);
+    H->npad = round_up(num_envs, 32);
+    std::vector<double> disc((size_t)P.T);
+    for (int t = 0; t < P.T; t++) disc[(size_t)t] = std::pow(cfg->alpha, (double)t);  // CPython float ** int == libm pow
+    double* disc_dev = nullptr;
+    cudaError_t ce = cudaMalloc(&disc_dev, sizeof(double) * (size_t)P.T);
+    if (ce == cudaSuccess) {
+        H->allocs.push_back(disc_dev);
+        ce = cudaMemcpy(disc_dev, disc.data(), sizeof(double) * (size_t)P.T, cudaMemcpyHostToDevice);
+    }
+    P.disc = disc_dev;
+    H->max_blocks = (int)((num_envs + ROLL_THREADS - 1) / ROLL_THREADS);
+    H->partials = nullptr;
+    if (ce == cudaSuccess) {
+        ce = cudaMalloc(&H->partials, sizeof(double) * 8 * (size_t)H->max_blocks);
+        if (ce == cudaSuccess) H->allocs.push_back(H->partials);
+    }
+    if (ce != cudaSuccess) {
+        orgym_set_error("device allocation failed: %s", cudaGetErrorString(ce));
+        rc = ORGYM_E_CUDA;
+    }
+    if (rc == ORGYM_OK) rc = orgym_build_alias(&cfg->dist, 0, &P.dem, &H->allocs);
+    if (rc != ORGYM_OK) {
+        for (void* p : H->allocs) cudaFree(p);
+        orgym_handle_base_free(&H->base);
+        delete H;
+        return rc;
+    }
+    *out = (orgym_handle_t)H;
+    return ORGYM_OK;
+}
+
+extern "C" int orgym_invmgmt_destroy(orgym_handle_t h) {
+    if (orgym_check_handle(h, FAM_INVMGMT)) return ORGYM_E_INVALID;
+    InvHandle* H = (InvHandle*)h;
+    {
+        DeviceGuard g(H->base.device);
+        for (void* p : H->allocs) cudaFree(p);
+    }
+    orgym_handle_base_free(&H->base);
+    delete H;
+    return ORGYM_OK;
+}
+
+extern "C" int64_t orgym_invmgmt_state_bytes(orgym_handle_t h) {
+    if (orgym_check_handle(h, FAM_INVMGMT)) return -1;
+    InvHandle* H = (InvHandle*)h;
+    return inv_state_bytes(H->dev, H->npad, H->wide);
+}
+extern "C" int32_t orgym_invmgmt_obs_dim(orgym_handle_t h) {
+    if (orgym_check_handle(h, FAM_INVMGMT)) return -1;
+    return ((InvHandle*)h)->dev.obs_dim;
+}
+extern "C" int32_t orgym_invmgmt_act_dim(orgym_handle_t h) {
+    if (orgym_check_handle(h, FAM_INVMGMT)) return -1;
+    return ((InvHandle*)h)->dev.n;
+}
+
+extern "C" int orgym_invmgmt_reset(orgym_handle_t h, void* state_dev, int reseed, uint64_t seed, int64_t env_offset,
+                                   const uint8_t* mask_dev, int64_t* obs_dev, void* stream) {
+    if (orgym_check_handle(h, FAM_INVMGMT)) return ORGYM_E_INVALID;
+    InvHandle* H = (InvHandle*)h;
+    ORGYM_REQUIRE(state_dev && obs_dev, "state_dev and obs_dev are required");
+    DeviceGuard g(H->base.device);
+    int64_t N = H->base.num_envs;
+    unsigned grid = (unsigned)((N + 255) / 256);
+    if (H->wide)
+        inv_reset_kernel<long long><<<grid, 256, 0, (cudaStream_t)stream>>>(H->dev, N, H->npad, state_dev, reseed, seed,
+                                                                           env_offset, mask_dev, obs_dev);
+    else
+        inv_reset_kernel<int><<<grid, 256, 0, (cudaStream_t)stream>>>(H->dev, N, H->npad, state_dev, reseed, seed,
+                                                                     env_offset, mask_dev, obs_dev);
+    ORGYM_CUDA(cudaGetLastError());
+    return ORGYM_OK;
+}
+
+static int g_use_bulk = -1;
+static int use_bulk() {
+    if (g_use_bulk < 0) {
+        const char* v = getenv("ORGYM_NO_BULK");
+        g_use_bulk = (v && v[0] == '1') ? 0 : 1;
+    }
+    return g_use_bulk;
+}
+
+extern "C" int orgym_invmgmt_step(orgym_handle_t h, void* state_dev, const void* actions_dev, int action_is_f64,
+                                  const int64_t* demand_override_dev, int autoreset_mode, int64_t* obs_dev,
+                                  double* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
+                                  const orgym_invmgmt_info_t* info, void* stream) {
+    if (orgym_check_handle(h, FAM_INVMGMT)) return ORGYM_E_INVALID;
+    InvHandle* H = (InvHandle*)h;
+    ORGYM_REQUIRE(state_dev && actions_dev && obs_dev && reward_dev && terminated_dev && truncated_dev,
+                  "state, actions, obs, reward, terminated and truncated pointers are required");
+    ORGYM_REQUIRE(autoreset_mode >= 0 && autoreset_mode <= 2, "bad autoreset mode");
+    DeviceGuard g(H->base.device);
+    const InvDev& P = H->dev;
+    InvStepArgs A;
+    memset(&A, 0, sizeof(A));
+    A.N = H->base.num_envs;
+    A.npad = H->npad;
+    A.state = state_dev;
+    A.actions = actions_dev;
+    A.act_f64 = action_is_f64;
+    A.demand = demand_override_dev;
+    A.autoreset = autoreset_mode;
+    A.obs = obs_dev;
+    A.reward = reward_dev;
+    A.terminated = terminated_dev;
+    A.truncated = truncated_dev;
+    if (info) {
+        A.info_demand = info->demand_dev;
+        A.info_sales = info->sales_dev;
+        A.info_unf = info->unfulfilled_dev;
+        A.info_profit = info->profit_dev;
+        A.final_obs = info->final_obs_dev;
+    }
+    A.err = H->base.err_dev;
+    A.use_bulk = use_bulk() && ((uintptr_t)actions_dev % 16 == 0) && ((uintptr_t)obs_dev % 16 == 0);
+    int ostride = (P.obs_dim & 1) ? P.obs_dim : P.obs_dim + 1;
+    size_t smem = (size_t)ORGYM_TILE * ostride * 8 + (size_t)ORGYM_TILE * P.n * 8 + 16 +
+                  (P.dem.kind == ORGYM_DIST_USER ? 0 : (size_t(8) << P.dem.log2k));
+    if (smem > 220 * 1024) {
+        orgym_set_error("observation tile of %zu bytes does not fit in shared memory (obs_dim=%d)", smem, P.obs_dim);
+        return ORGYM_E_UNSUPPORTED;
+    }
+    if (H->wide)
+        launch_step<long long>(H, A, smem, (cudaStream_t)stream);
+    else
+        launch_step<int>(H, A, smem, (cudaStream_t)stream);
+    ORGYM_CUDA(cudaGetLastError());
+    return ORGYM_OK;
+}
+
+extern "C" int orgym_invmgmt_export_state(orgym_handle_t h, const void* state_dev, int64_t* I_dev, int64_t* B_dev,
+                                          int32_t* period_dev, void* stream) {
+    if (orgym_check_handle(h, FAM_INVMGMT)) return ORGYM_E_INVALID;
+    InvHandle* H = (InvHandle*)h;
+    ORGYM_REQUIRE(state_dev, "state_dev is required");
+    DeviceGuard g(H->base.device);
+    int64_t N = H->base.num_envs;
+    unsigned grid = (unsigned)((N + 255) / 256);
+    if (H->wide)
+        inv_export_kernel<long long><<<grid, 256, 0, (cudaStream_t)stream>>>(H->dev, N, H->npad, state_dev, I_dev, B_dev,
+                                                                            period_dev);
+    else
+        inv_export_kernel<int><<<grid, 256, 0, (cudaStream_t)stream>>>(H->dev, N, H->npad, state_dev, I_dev, B_dev,
+                                                                      period_dev);
+    ORGYM_CUDA(cudaGetLastError());
+    return ORGYM_OK;
+}
+
+extern "C" int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t env_offset, uint32_t episode,
+                                     const orgym_invmgmt_rollout_in_t* in, const orgym_invmgmt_rollout_out_t* out,
+                                     void* stream) {
+    if (orgym_check_handle(h, FAM_INVMGMT)) return ORGYM_E_INVALID;
+    InvHandle* H = (InvHandle*)h;
+    ORGYM_REQUIRE(in && out, "null argument");
+    ORGYM_REQUIRE(in->policy >= 0 && in->policy <= 2, "unknown policy %d", in->policy);
+    ORGYM_REQUIRE(in->policy != ORGYM_POLICY_ACTIONS || in->actions_dev, "policy ACTIONS needs actions_dev");
+    if (in->policy == ORGYM_POLICY_RANDOM)
+        for (int i = 0; i < ((InvHandle*)h)->dev.n; i++)
+            ORGYM_REQUIRE(((InvHandle*)h)->dev.c[i] < 0x7fffffffLL, "random policy needs capacities below 2^31");
+    DeviceGuard g(H->base.device);
+    const InvDev& P = H->dev;
+    InvRolloutArgs A;
+    memset(&A, 0, sizeof(A));
+    A.N = H->base.num_envs;
+    A.env_offset = env_offset;
+    A.seed = seed;
+    A.episode = episode;
+    A.policy = in->policy;
+    if (in->policy == ORGYM_POLICY_BASE_STOCK)
+        for (int i = 0; i < P.n; i++) A.target[i] = ((double)(P.L[i] + 1) * in->param[1]) * in->param[0];
+    A.actions = in->actions_dev;
+    A.a_se = in->act_stride_env;
+    A.a_st = in->act_stride_t;
+    A.demand = in->demand_dev;
+    A.d_se = in->dem_stride_env;
+    A.d_st = in->dem_stride_t;
+    A.ep_return = out->ep_return_dev;
+    A.stats = out->stats_dev;
+    A.reward_traj = out->reward_traj_dev;
+    A.final_I = out->final_I_dev;
+    A.final_B = out->final_B_dev;
+    A.partials = out->summary_dev ? H->partials : nullptr;
+    // pre-staged actions may be arbitrary int64 -> exact wide arithmetic; on-device policies stay inside [0, c]
+    const bool wide = H->wide || in->policy == ORGYM_POLICY_ACTIONS;
+    size_t ring = (size_t)P.sumL * ROLL_THREADS * (wide ? 8 : 4);
+    size_t smem = (P.dem.kind == ORGYM_DIST_USER ? 0 : (size_t(8) << P.dem.log2k)) +
+                  ring * (in->policy == ORGYM_POLICY_BASE_STOCK ? 2 : 1);
+    if (smem > 220 * 1024) {
+        orgym_set_error("lead-time rings of %zu bytes do not fit in shared memory (sum of lead times = %d)", smem, P.sumL);
+        return ORGYM_E_UNSUPPORTED;
+    }
+    if (wide)
+        launch_rollout<long long>(H, A, smem, (cudaStream_t)stream);
+    else
+        launch_rollout<int>(H, A, smem, (cudaStream_t)stream);
+    ORGYM_CUDA(cudaGetLastError());
+    if (out->summary_dev) {
+        int nblocks = (int)((A.N + ROLL_THREADS - 1) / ROLL_THREADS);
+        orgym_reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(H->partials, nblocks, out->summary_dev);
+        ORGYM_CUDA(cudaGetLastError());
+    }
+    return ORGYM_OK;
+}

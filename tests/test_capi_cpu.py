@@ -1,0 +1,70 @@
+"""CPU suite: the C-ABI library loads and exports every symbol the header declares; host-side config logic
+mirrors the reference's constructors; no compute call is made without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import or_gym_inventory_b200 as pkg
+from or_gym_inventory_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_capi.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return _capi.lib()
+
+
+def test_header_symbols_are_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "orgym_b200.h")).read()
+    names = set(re.findall(r"\b(orgym_[a-z0-9_]+)\s*\(", hdr))
+    assert names, "no prototypes found"
+    assert names == set(_capi.SYMBOLS), names ^ set(_capi.SYMBOLS)
+    for n in names:
+        assert hasattr(lib, n)
+    assert lib.orgym_version() == 100
+
+
+def test_no_gpu_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert lib.orgym_device_count() == 0
+    keep = []
+    cfg = pkg.InvManagementParams().to_c(keep)
+    h = C.c_void_p()
+    rc = lib.orgym_invmgmt_create(C.byref(cfg), 16, 0, C.byref(h))
+    assert rc == _capi.E_CUDA and b"no CUDA device" in lib.orgym_last_error()
+    with pytest.raises(RuntimeError):
+        pkg.InvManagementBacklogEnv(num_envs=4, device="cpu")
+
+
+def test_invmgmt_params_mirror_reference_defaults():
+    P = pkg.InvManagementParams()
+    assert P.num_stages == 4 and P.lt_max == 10 and P.pipeline_length == 33
+    assert P.unit_price.dtype == np.float32 and P.unit_price.tolist() == [20, 15, 10, 7]
+    assert P.holding_cost.tolist() == [np.float32(0.15), np.float32(0.10), np.float32(0.05), 0]
+    obs_space, act_space = P.spaces()
+    assert obs_space.shape == (33,) and obs_space.dtype == np.int64
+    assert act_space.high.tolist() == [100, 200, 230] and act_space.low.tolist() == [0, 0, 0]
+    cap = (100 + 200 + 230) * 30 * 2
+    assert obs_space.high[0] == cap and obs_space.low[0] == -cap
+    # env_config overrides are applied after the keyword arguments (inventory_management.py:83-84)
+    P2 = pkg.InvManagementParams(periods=10, env_config={"periods": 12, "L": [0, 0, 0]})
+    assert P2.num_periods == 12 and P2.lt_max == 0 and P2.pipeline_length == 3
+
+
+@pytest.mark.parametrize("bad, msg", [
+    (dict(I0=[-1, 5, 5]), "Initial inventory"), (dict(periods=0), "periods"), (dict(c=[0, 1, 1]), "capacities"),
+    (dict(L=[1, -2, 3]), "Lead times"), (dict(backlog=1), "boolean"), (dict(r=[1, 2, 3]), "Length of r"),
+    (dict(dist=7), "dist must be"), (dict(alpha=0.0), "alpha"), (dict(dist=5, user_D=[1, 2]), "User specified"),
+])
+def test_invmgmt_validation_matches_reference(bad, msg):
+    with pytest.raises(AssertionError, match=msg):
+        pkg.InvManagementParams(**bad)

@@ -1,0 +1,249 @@
+"""GPU parity tests of the serial multi-echelon env (csrc/invmgmt.cu) through the C ABI:
+CUDA step / fused rollout vs the golden vectors of the reference and vs the C oracle."""
+import numpy as np
+import pytest
+
+import or_gym_inventory_b200 as pkg
+from helpers import golden_files, ids, load_golden, seq_sum
+
+pytestmark = pytest.mark.gpu
+INV = golden_files("invmgmt_")
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _mk(meta, n, **kw):
+    cls = pkg.InvManagementBacklogEnv if meta["backlog"] else pkg.InvManagementLostSalesEnv
+    return cls(num_envs=n, device="cuda:0", **meta["cfg"], **kw)
+
+
+@pytest.mark.parametrize("wide", [False, True], ids=["int32state", "int64state"])
+@pytest.mark.parametrize("path", INV, ids=ids(INV))
+def test_step_matches_reference(path, wide):
+    torch = _torch()
+    g, meta = load_golden(path)
+    E = len(g["seeds"])
+    env = _mk(meta, E, wide_state=wide, autoreset_mode="disabled")
+    T = env.num_periods
+    obs, _ = env.reset(seed=0)
+    assert np.array_equal(obs.cpu().numpy(), g["obs"][:, 0])
+    float_actions = meta["policy"] == "wild"
+    for t in range(T):
+        a = g["actions"][:, t]
+        a = torch.from_numpy(a if float_actions else a.astype(np.int64)).cuda()
+        obs, r, term, trunc, info = env.step(a, demand=torch.from_numpy(g["D"][:, t]).cuda())
+        assert np.array_equal(obs.cpu().numpy(), g["obs"][:, t + 1]), t
+        assert np.array_equal(r.cpu().numpy(), g["reward"][:, t]), t      # bit-exact float64
+        assert np.array_equal(trunc.cpu().numpy(), g["truncated"][:, t])
+        assert not term.any()
+        assert np.array_equal(info["sales"].cpu().numpy(), g["S"][:, t])
+        unf = g["B"][:, t + 1] if meta["backlog"] else g["LS"][:, t]
+        assert np.array_equal(info["unfulfilled"].cpu().numpy(), unf)
+        assert np.array_equal(info["period_profit"].cpu().numpy(), g["profit"][:, t])
+        assert np.array_equal(info["demand_realized"].cpu().numpy(), g["D"][:, t])
+        I, B, per = env.export_state()
+        assert np.array_equal(I.cpu().numpy(), g["I"][:, t + 1])
+        assert np.array_equal(B.cpu().numpy(), g["B"][:, t + 1])
+        assert (per.cpu().numpy() == t + 1).all()
+    assert env.errors() == 0
+    env.close()
+
+
+@pytest.mark.parametrize("path", INV, ids=ids(INV))
+def test_rollout_replay_matches_reference(path):
+    g, meta = load_golden(path)
+    E = len(g["seeds"])
+    env = _mk(meta, E)
+    acts = np.trunc(np.maximum(g["actions"], 0)).astype(np.int64)  # rollout takes int64 actions
+    out = env.rollout("actions", actions=acts, demand=g["D"],
+                      want=("ep_return", "stats", "reward_traj", "final_I", "final_B", "summary"))
+    _torch().cuda.synchronize()
+    assert np.array_equal(out["reward_traj"].cpu().numpy(), g["reward"])
+    ret = out["ep_return"].cpu().numpy()
+    for e in range(E):
+        assert ret[e] == seq_sum(g["reward"][e])
+    assert np.array_equal(out["final_I"].cpu().numpy(), g["I"][:, -1])
+    assert np.array_equal(out["final_B"].cpu().numpy(), g["B"][:, -1])
+    st = out["stats"].cpu().numpy()
+    assert np.array_equal(st[:, 0], g["S"][:, :, 0].sum(axis=1))
+    assert np.array_equal(st[:, 1], g["D"].sum(axis=1))
+    unf0 = (g["B"][:, 1:, 0] if meta["backlog"] else g["LS"][:, :, 0]).sum(axis=1)
+    assert np.array_equal(st[:, 2], unf0)
+    assert np.array_equal(st[:, 3], np.maximum(g["I"][:, 1:], 0).sum(axis=(1, 2)))
+    summ = out["summary"].cpu().numpy()
+    assert summ[0] == E and np.isclose(summ[1], ret.sum(), rtol=1e-12)
+    # time-major layouts give the same result
+    out2 = env.rollout("actions", actions=np.ascontiguousarray(acts.transpose(1, 0, 2)),
+                       demand=np.ascontiguousarray(g["D"].T), time_major=True, want=("ep_return",))
+    assert np.array_equal(out2["ep_return"].cpu().numpy(), ret)
+    if meta["policy"] == "base_stock":
+        out3 = env.rollout("base_stock", demand=g["D"], want=("ep_return", "reward_traj", "final_I"))
+        assert np.array_equal(out3["reward_traj"].cpu().numpy(), g["reward"])
+        assert np.array_equal(out3["final_I"].cpu().numpy(), g["I"][:, -1])
+    env.close()
+
+
+@pytest.mark.parametrize("backlog", [True, False])
+def test_large_batch_vs_oracle(backlog):
+    """Default config, 20k instances (tail tile included), random actions / demand: step API and fused rollout
+    against the C oracle on a sample of instances, and against each other on all of them."""
+    from oracle import oracle
+    torch = _torch()
+    N = 20011
+    cls = pkg.InvManagementBacklogEnv if backlog else pkg.InvManagementLostSalesEnv
+    env = cls(num_envs=N, device="cuda:0")
+    T, n = env.num_periods, env.num_stages - 1
+    rng = np.random.default_rng(3)
+    acts = rng.integers(0, env.supply_capacity + 1, size=(N, T, n)).astype(np.int64)
+    dem = rng.poisson(20, size=(N, T)).astype(np.int64)
+    a_d, d_d = torch.from_numpy(acts).cuda(), torch.from_numpy(dem).cuda()
+    obs, _ = env.reset(seed=3)
+    rew = torch.zeros((N, T), dtype=torch.float64, device="cuda")
+    obs_hist = []
+    for t in range(T):
+        obs, r, term, trunc, info = env.step(a_d[:, t], demand=d_d[:, t])
+        rew[:, t] = r
+        if t in (0, 9, T - 1):
+            obs_hist.append((t, obs.clone()))
+    out = env.rollout("actions", actions=a_d, demand=d_d, want=("ep_return", "reward_traj", "final_I", "final_B"))
+    assert torch.equal(out["reward_traj"], rew)
+    I, B, per = env.export_state()
+    assert torch.equal(I, out["final_I"]) and torch.equal(B, out["final_B"])
+    rew = rew.cpu().numpy()
+    for e in list(range(0, N, 997)) + [N - 1]:
+        o = oracle.invmgmt_episode(env.params, actions=acts[e], demand=dem[e])
+        assert np.array_equal(o["reward"], rew[e])
+        for t, ob in obs_hist:
+            assert np.array_equal(o["obs"][t + 1], ob[e].cpu().numpy())
+    env.close()
+
+
+def test_sampled_demand_consistent_between_step_and_rollout():
+    """On-device Philox demand: the step API and the fused rollout draw the same stream for (seed, env, period),
+    and the stream does not depend on batch size or env_offset sharding."""
+    torch = _torch()
+    N = 3000
+    env = pkg.InvManagementLostSalesEnv(num_envs=N, device="cuda:0")
+    T, n = env.num_periods, env.num_stages - 1
+    acts = torch.zeros((N, n), dtype=torch.int64, device="cuda") + 20
+    env.reset(seed=5000)
+    dem = torch.zeros((N, T), dtype=torch.int64, device="cuda")
+    rew = torch.zeros((N, T), dtype=torch.float64, device="cuda")
+    for t in range(T):
+        _, r, _, _, info = env.step(acts)
+        dem[:, t] = info["demand_realized"]
+        rew[:, t] = r
+    out = env.rollout("actions", actions=acts[:, None, :].expand(N, T, n).contiguous(), seed=5000,
+                      want=("ep_return", "stats", "reward_traj"))
+    assert torch.equal(out["stats"][:, 1], dem.sum(dim=1))
+    assert torch.equal(out["reward_traj"], rew)
+    # sharding invariance: instances [1000, 1500) simulated alone reproduce the same numbers
+    sub = pkg.InvManagementLostSalesEnv(num_envs=500, device="cuda:0", env_offset=1000)
+    o2 = sub.rollout("actions", actions=acts[:500, None, :].expand(500, T, n).contiguous(), seed=5000,
+                     want=("ep_return", "stats"))
+    assert torch.equal(o2["ep_return"], out["ep_return"][1000:1500])
+    assert torch.equal(o2["stats"], out["stats"][1000:1500])
+    # a different episode index gives a different demand path
+    o3 = env.rollout("actions", actions=acts[:, None, :].expand(N, T, n).contiguous(), seed=5000, episode=1,
+                     want=("stats",))
+    assert not torch.equal(o3["stats"][:, 1], dem.sum(dim=1))
+    env.close(); sub.close()
+
+
+def test_on_device_policies():
+    """base-stock and random-action rollouts: sane statistics and agreement with the oracle's base-stock driver
+    when it is fed the demand the device sampled."""
+    from oracle import oracle
+    torch = _torch()
+    N = 4096
+    env = pkg.InvManagementBacklogEnv(num_envs=N, device="cuda:0", autoreset_mode="disabled")
+    T, n = env.num_periods, env.num_stages - 1
+    # recover the device's demand stream through the step API (actions are irrelevant to the demand draw)
+    env.reset(seed=4000)
+    dem = torch.zeros((N, T), dtype=torch.int64, device="cuda")
+    for t in range(T):
+        _, _, _, _, info = env.step(torch.zeros((N, n), dtype=torch.int64, device="cuda"))
+        dem[:, t] = info["demand_realized"]
+    out = env.rollout("base_stock", seed=4000, want=("ep_return", "stats", "final_I", "final_B", "summary"))
+    dem_h = dem.cpu().numpy()
+    ret = out["ep_return"].cpu().numpy()
+    for e in range(0, N, 211):
+        o = oracle.invmgmt_episode(env.params, policy="base_stock", demand=dem_h[e])
+        assert ret[e] == seq_sum(o["reward"])
+        assert np.array_equal(out["final_I"][e].cpu().numpy(), o["I"][-1])
+        assert np.array_equal(out["final_B"][e].cpu().numpy(), o["B"][-1])
+    summ = out["summary"].cpu().numpy()
+    assert summ[0] == N and np.isclose(summ[1], ret.sum(), rtol=1e-12) and summ[4] == dem_h.sum()
+    assert 15 < dem_h.mean() < 25
+    r = env.rollout("random", seed=1, want=("ep_return", "stats", "summary"))
+    assert np.isfinite(r["ep_return"].cpu().numpy()).all()
+    env.close()
+
+
+def test_autoreset_modes():
+    torch = _torch()
+    N, cfg = 300, dict(periods=4, I0=[10, 10], p=5, r=[3, 2, 1], k=[1, 1, 1], h=[0.5, 0.2], c=[15, 20], L=[1, 2],
+                       dist_param={"mu": 8})
+    a = torch.full((N, 2), 7, dtype=torch.int64, device="cuda")
+    # next_step: the call after truncation returns the reset observation, reward 0, flags False
+    env = pkg.InvManagementBacklogEnv(num_envs=N, device="cuda:0", autoreset_mode="next_step", **cfg)
+    obs0 = env.reset(seed=9)[0].clone()
+    for t in range(4):
+        obs, r, term, trunc, _ = env.step(a)
+    assert trunc.all()
+    last = obs.clone()
+    obs, r, term, trunc, _ = env.step(a)
+    assert torch.equal(obs, obs0) and (r == 0).all() and not trunc.any()
+    assert not torch.equal(last, obs0)
+    obs, r, term, trunc, _ = env.step(a)
+    assert (env.period == 1).all()
+    # same_step: reset inside the truncating step, terminal observation in info['final_obs']
+    env2 = pkg.InvManagementBacklogEnv(num_envs=N, device="cuda:0", autoreset_mode="same_step", **cfg)
+    env2.reset(seed=9)
+    for t in range(4):
+        obs2, r2, term2, trunc2, info2 = env2.step(a)
+    assert trunc2.all() and torch.equal(obs2, obs0) and torch.equal(info2["final_obs"], last)
+    assert (env2.period == 0).all()
+    # disabled: stepping past the end raises like the reference
+    env3 = pkg.InvManagementBacklogEnv(num_envs=N, device="cuda:0", autoreset_mode="disabled", **cfg)
+    env3.reset(seed=9)
+    for t in range(5):
+        env3.step(a)
+    with pytest.raises(IndexError):
+        env3.check_errors()
+    # partial reset through a mask
+    env3.reset(options={"reset_mask": (torch.arange(N) % 2 == 0)})
+    per = env3.period.cpu().numpy()
+    assert (per[::2] == 0).all() and (per[1::2] == 4).all()
+    for e in (env, env2, env3):
+        e.close()
+
+
+def test_int32_range_guard():
+    torch = _torch()
+    env = pkg.InvManagementBacklogEnv(num_envs=64, device="cuda:0")
+    env.reset(seed=0)
+    env.step(torch.full((64, 3), 2**40, dtype=torch.int64, device="cuda"))
+    with pytest.raises(OverflowError):
+        env.check_errors()
+    env.close()
+
+
+def test_no_bulk_path_matches(monkeypatch):
+    """The cooperative (non-TMA) tile path is used for tail tiles; make sure a ragged batch is exact."""
+    torch = _torch()
+    g, meta = load_golden(INV[1])
+    env = _mk(meta, 131)  # one full 128-tile + a 3-env tail
+    T = env.num_periods
+    reps = 131 // len(g["seeds"]) + 1
+    acts = np.tile(g["actions"], (reps, 1, 1))[:131].astype(np.int64)
+    dem = np.tile(g["D"], (reps, 1))[:131]
+    ref_obs = np.tile(g["obs"], (reps, 1, 1))[:131]
+    env.reset(seed=0)
+    for t in range(T):
+        obs, *_ = env.step(torch.from_numpy(acts[:, t]).cuda(), demand=torch.from_numpy(dem[:, t]).cuda())
+        assert np.array_equal(obs.cpu().numpy(), ref_obs[:, t + 1])
+    env.close()
