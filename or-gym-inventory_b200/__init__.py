@@ -16,4 +16,9 @@ from . import _capi  # noqa: F401
 from .inventory_management import (InvManagementBacklogEnv, InvManagementLostSalesEnv,  # noqa: F401
                                    InvManagementMasterEnv, InvManagementParams)
 
+from .newsvendor import NewsvendorEnv, NewsvendorParams  # noqa: F401
+from .network_management import (NetInvMgmtBacklogEnv, NetInvMgmtLostSalesEnv, NetInvMgmtMasterEnv,  # noqa: F401
+                                 NetInvMgmtParams, default_graph, graph_from_spec, synthetic_graph)
+from . import network_management_custom  # noqa: F401
+
 __version__ = "0.1.0"

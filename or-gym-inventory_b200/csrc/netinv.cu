@@ -1,0 +1,683 @@
+// netinv.cu -- graph-structured network inventory env (reference: network_management.py).
+//
+// One env instance per thread.  The topology (flattened from networkx on the host: sorted reorder links,
+// per-node predecessor / successor lists in adjacency order) travels as a __grid_constant__ kernel parameter,
+// i.e. it lives in the constant bank; every loop over links / nodes is uniform across the warp, so the
+// sequential per-supplier allocation of the reference runs divergence-free with one instance per lane.
+// Per-instance float64 work vectors (X, consumed, R_t, Y, U, S_retail) sit in shared memory as [slot][thread]
+// (conflict-free); the lead-time rings (last L_e fulfilled orders per link) stay in HBM as ring[slot][env] and are
+// touched twice per link per period.
+//
+//   net_reset_kernel   reset (network_management.py:301-332) + first observation (:334-413)
+//   net_sim_kernel     STEP mode: one period (:436-635) + observation;  ROLLOUT mode: fused reset + T periods
+//
+// float64 throughout, evaluated in the reference's operation order (Python sum order = adjacency order).
+#include "common.cuh"
+
+#define NJ ORGYM_NET_MAX_NODES
+#define NE ORGYM_NET_MAX_REORDER
+#define NM ORGYM_NET_MAX_RETAIL
+#define NSUCC (NE + NM)
+
+struct NetDev {
+    int T, backlog, J, E, M, obs_dim, sumL;
+    const double* disc;  // [T] alpha**t
+    double I0[NJ], h[NJ], C[NJ], v[NJ], o[NJ];
+    uint8_t is_factory[NJ], is_retail[NJ];
+    int16_t sup[NE], pur[NE], L[NE];
+    int32_t roff[NE];
+    double p[NE], g[NE];
+    int16_t rt_node[NM];
+    double rt_p[NM], rt_b[NM];
+    int16_t succ_ptr[NJ + 1], pred_ptr[NJ + 1];
+    int16_t succ_idx[NSUCC], pred_idx[NE];
+    AliasDev dem[NM];
+};
+
+struct NetHandle {
+    HandleBase base;
+    NetDev dev;
+    int64_t npad;
+    int threads;  // threads per CTA that fit the shared-memory work vectors
+    size_t smem;
+    std::vector<void*> allocs;
+    double* partials;
+};
+
+// state (field[slot][env], stride npad): [key u64][X J][Y E][U M][ring sumL] f64, [period i32][episode u32]
+struct NetState {
+    uint64_t* key;
+    double *X, *Y, *U, *ring;
+    int32_t* period;
+    uint32_t* episode;
+    int64_t npad;
+    __host__ __device__ NetState(void* base, int64_t npad_, const NetDev& P) : npad(npad_) {
+        char* p = (char*)base;
+        key = (uint64_t*)p;
+        p += 8 * npad;
+        X = (double*)p;
+        Y = X + (size_t)P.J * npad;
+        U = Y + (size_t)P.E * npad;
+        ring = U + (size_t)P.M * npad;
+        p = (char*)(ring + (size_t)P.sumL * npad);
+        period = (int32_t*)p;
+        p += 4 * npad;
+        episode = (uint32_t*)p;
+    }
+};
+static int64_t net_state_bytes(const NetDev& P, int64_t npad) {
+    return npad * (8 + 8 * (int64_t)(P.J + P.E + P.M + P.sumL) + 8);
+}
+
+// observation (:334-413): [U (M), X (J), per link with L>0: R[t-L..t-1] zero-padded on the left] as float32.
+// ring slot s of a link holds the order of the latest period p with p % L == s (0 before any), so the window
+// element q (oldest first) of the observation at period t is ring[(t + q) % L].
+__device__ __forceinline__ void net_write_obs(const NetDev& P, const double* sU, const double* sX, int nthr, int tid,
+                                              const double* ring, int64_t npad, int64_t e, int t, float* o) {
+    int k = 0;
+    for (int r = 0; r < P.M; r++) o[k++] = (float)sU[r * nthr + tid];
+    for (int j = 0; j < P.J; j++) o[k++] = (float)sX[j * nthr + tid];
+    for (int i = 0; i < P.E; i++) {
+        int L = P.L[i];
+        if (L == 0) continue;  // :353
+        int s = t % L;
+        for (int q = 0; q < L; q++) {
+            o[k++] = (float)ring[(size_t)(P.roff[i] + s) * npad + e];
+            s = s + 1 == L ? 0 : s + 1;
+        }
+    }
+}
+
+__global__ void net_reset_kernel(const __grid_constant__ NetDev P, int64_t N, int64_t npad, void* state, int reseed,
+                                 uint64_t seed, int64_t env_offset, const uint8_t* __restrict__ mask,
+                                 float* __restrict__ obs) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    if (mask && !mask[e]) return;
+    NetState st(state, npad, P);
+    for (int j = 0; j < P.J; j++) st.X[(size_t)j * npad + e] = P.I0[j];  // :326
+    for (int i = 0; i < P.E; i++) st.Y[(size_t)i * npad + e] = 0.0;
+    for (int r = 0; r < P.M; r++) st.U[(size_t)r * npad + e] = 0.0;
+    for (int k = 0; k < P.sumL; k++) st.ring[(size_t)k * npad + e] = 0.0;
+    st.period[e] = 0;
+    if (reseed) {
+        st.key[e] = seed + (uint64_t)(env_offset + e);
+        st.episode[e] = 0;
+    } else
+        st.episode[e] += 1;
+    float* o = obs + e * P.obs_dim;
+    int k = 0;
+    for (int r = 0; r < P.M; r++) o[k++] = 0.0f;
+    for (int j = 0; j < P.J; j++) o[k++] = (float)P.I0[j];
+    for (; k < P.obs_dim; k++) o[k] = 0.0f;
+}
+
+struct NetSimArgs {
+    int64_t N, npad, env_offset;
+    int rollout;  // 0 = one period from / to state (STEP), 1 = fused episode (ROLLOUT)
+    void* state;  // STEP: live state; ROLLOUT: scratch for the rings
+    uint64_t seed;
+    uint32_t episode;
+    int policy;
+    const float* actions;
+    int64_t a_se, a_st;
+    const double* demand;
+    int64_t d_se, d_st;
+    int autoreset;
+    // STEP outputs
+    float* obs;
+    double* reward;
+    uint8_t* terminated;
+    uint8_t* truncated;
+    double* info_demand;
+    double* info_sales;
+    double* info_profit;
+    double* info_profit_total;
+    float* final_obs;
+    uint32_t* err;
+    // ROLLOUT outputs
+    double* ep_return;
+    double* stats;
+    double* reward_traj;
+    double* final_X;
+    double* final_Y;
+    double* final_U;
+    double* partials;
+};
+
+__global__ void net_sim_kernel(const __grid_constant__ NetDev P, const __grid_constant__ NetSimArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int nthr = blockDim.x, tid = threadIdx.x;
+    const int64_t e = (int64_t)blockIdx.x * nthr + tid;
+    const bool valid = e < A.N;
+    const int64_t ec = valid ? e : 0;  // clamp so that idle lanes stay in bounds
+    const int J = P.J, E = P.E, M = P.M;
+    double* sX = (double*)smem;      // [J]
+    double* sC = sX + J * nthr;      // [J] inventory consumed this period
+    double* sR = sC + J * nthr;      // [E] orders fulfilled this period
+    double* sY = sR + E * nthr;      // [E]
+    double* sU = sY + E * nthr;      // [M]
+    double* sS = sU + M * nthr;      // [M] retail sales this period
+    NetState st(A.state, A.npad, P);
+    double* ring = st.ring;
+    const int64_t np_ = A.npad;
+
+    uint64_t key;
+    uint32_t episode;
+    int t0, t1;
+    bool do_step = valid;
+    if (A.rollout) {
+        key = A.seed + (uint64_t)(A.env_offset + e);
+        episode = A.episode;
+        t0 = 0;
+        t1 = P.T;
+        for (int j = 0; j < J; j++) sX[j * nthr + tid] = P.I0[j];
+        for (int i = 0; i < E; i++) sY[i * nthr + tid] = 0.0;
+        for (int r = 0; r < M; r++) sU[r * nthr + tid] = 0.0;
+        if (valid)
+            for (int k = 0; k < P.sumL; k++) ring[(size_t)k * np_ + e] = 0.0;
+    } else {
+        key = st.key[ec];
+        episode = st.episode[ec];
+        t0 = st.period[ec];
+        t1 = t0 + 1;
+        if (valid && t0 >= P.T) {  // episode already over
+            do_step = false;
+            if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {
+                for (int j = 0; j < J; j++) {
+                    st.X[(size_t)j * np_ + e] = P.I0[j];
+                    sX[j * nthr + tid] = P.I0[j];
+                }
+                for (int i = 0; i < E; i++) st.Y[(size_t)i * np_ + e] = 0.0;
+                for (int r = 0; r < M; r++) {
+                    st.U[(size_t)r * np_ + e] = 0.0;
+                    sU[r * nthr + tid] = 0.0;
+                }
+                for (int k = 0; k < P.sumL; k++) ring[(size_t)k * np_ + e] = 0.0;
+                st.period[e] = 0;
+                st.episode[e] = episode + 1;
+                net_write_obs(P, sU, sX, nthr, tid, ring, np_, e, 0, A.obs + e * P.obs_dim);
+                A.reward[e] = 0.0;
+                A.terminated[e] = 0;
+                A.truncated[e] = 0;
+            } else {
+                atomicOr(A.err, ORGYM_ERR_STEP_PAST_END);
+                A.reward[e] = 0.0;
+                A.terminated[e] = 0;
+                A.truncated[e] = 1;
+            }
+        }
+        if (do_step) {
+            for (int j = 0; j < J; j++) sX[j * nthr + tid] = st.X[(size_t)j * np_ + e];
+            for (int i = 0; i < E; i++) sY[i * nthr + tid] = st.Y[(size_t)i * np_ + e];
+            for (int r = 0; r < M; r++) sU[r * nthr + tid] = st.U[(size_t)r * np_ + e];
+        }
+    }
+    double ret = 0.0, s_sales = 0.0, s_dem = 0.0, s_unf = 0.0, s_inv = 0.0, last_reward = 0.0;
+    if (!A.rollout && !do_step) t1 = t0;  // nothing to simulate for this lane
+
+    for (int t = t0; t < t1; t++) {
+        // ---- 0) place orders: sequential greedy allocation in sorted (supplier, purchaser) order (:448-490)
+        for (int j = 0; j < J; j++) sC[j * nthr + tid] = 0.0;
+        double cons_s = 0.0;
+        for (int i = 0; i < E; i++) {
+            float a;
+            if (A.policy == ORGYM_NET_POLICY_CONSTANT)
+                a = A.actions[i];
+            else
+                a = A.actions[ec * A.a_se + (int64_t)(A.rollout ? t : 0) * A.a_st + i];
+            double req = rint((double)a);  // Python round(): half to even
+            req = req > 0.0 ? req : 0.0;   // max(0, .)
+            const int s = P.sup[i];
+            double f = 0.0;
+            if (s == -1)
+                f = req;  // raw material: unlimited (:453-455)
+            else if (s >= 0) {
+                if (i == 0 || P.sup[i - 1] != s) cons_s = 0.0;
+                double avail = sX[s * nthr + tid] - cons_s;  // :459
+                avail = avail > 0.0 ? avail : 0.0;           // :460
+                double oa = avail;
+                if (P.is_factory[s]) {  // :464-478
+                    double mp = P.v[s] * avail;
+                    double lim = mp < P.C[s] ? mp : P.C[s];
+                    oa = lim < oa ? lim : oa;
+                }
+                f = oa < req ? oa : req;  // :481
+                cons_s += f / P.v[s];     // :484-485
+                if (i == E - 1 || P.sup[i + 1] != s) sC[s * nthr + tid] = cons_s;
+            }
+            sR[i * nthr + tid] = f;  // R[t] = S[t] = f (:488-490)
+        }
+        // ---- 1) pipeline inventory (:494-511); arrivals are re-read from the rings in predecessor order below
+        for (int i = 0; i < E; i++) {
+            const int L = P.L[i];
+            double arriving = L == 0 ? sR[i * nthr + tid] : ring[(size_t)(P.roff[i] + t % L) * np_ + ec];
+            sY[i * nthr + tid] = (sY[i * nthr + tid] - arriving) + sR[i * nthr + tid];
+        }
+        // ---- on-hand inventory (:516-528)
+        for (int j = 0; j < J; j++) {
+            double arr = 0.0;
+            for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
+                const int i = P.pred_idx[z], L = P.L[i];
+                arr += L == 0 ? sR[i * nthr + tid] : ring[(size_t)(P.roff[i] + t % L) * np_ + ec];
+            }
+            sX[j * nthr + tid] = (sX[j * nthr + tid] + arr) - sC[j * nthr + tid];
+        }
+        // ---- 2-4) market demand, sales, backlog (:536-566)
+        for (int r = 0; r < M; r++) {
+            double d;
+            if (A.demand) {
+                d = rint(A.demand[ec * A.d_se + (int64_t)(A.rollout ? t : 0) * A.d_st + r]);
+            } else
+                d = (double)sample_fixed(P.dem[r], P.dem[r].table, key, episode, t, (uint32_t)r);
+            d = d > 0.0 ? d : 0.0;  // max(0, int(round(.))) (:540)
+            const int j = P.rt_node[r];
+            double fill = d + sU[r * nthr + tid];
+            double x = sX[j * nthr + tid];
+            double invr = x > 0.0 ? x : 0.0;
+            double s = invr < fill ? invr : fill;  // min(demand_to_fill, inv) (:548)
+            sS[r * nthr + tid] = s;
+            sX[j * nthr + tid] = x - s;
+            double un = fill - s;
+            sU[r * nthr + tid] = P.backlog ? un : 0.0;  // :560-563
+            s_sales += s;
+            s_dem += d;
+            s_unf += P.backlog ? un : 0.0;
+            if (!A.rollout && A.info_demand && do_step) A.info_demand[e * M + r] = d;
+        }
+        // ---- 5) profit per node, Python sum order (:578-613)
+        double total = 0.0;
+        for (int j = 0; j < J; j++) {
+            double SR = 0.0, PC = 0.0, HCp = 0.0, sold = 0.0, UP = 0.0;
+            for (int z = P.succ_ptr[j]; z < P.succ_ptr[j + 1]; z++) {
+                const int l = P.succ_idx[z];
+                double q, pr;
+                if (l < E) {
+                    q = sR[l * nthr + tid];
+                    pr = P.p[l];
+                } else {
+                    q = sS[(l - E) * nthr + tid];
+                    pr = P.rt_p[l - E];
+                    UP += P.rt_b[l - E] * sU[(l - E) * nthr + tid];  // :608
+                }
+                SR += pr * q;  // :582
+                sold += q;     // :599
+            }
+            for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
+                const int i = P.pred_idx[z];
+                PC += P.p[i] * sR[i * nthr + tid];  // :586
+                double y = sY[i * nthr + tid];
+                HCp += P.g[i] * (y > 0.0 ? y : 0.0);  // :591
+            }
+            double x = sX[j * nthr + tid];
+            double xp = x > 0.0 ? x : 0.0;
+            double HC = P.h[j] * xp + HCp;  // :590-593
+            double OC = 0.0;
+            if (P.is_factory[j]) OC = P.v[j] > 0.0 ? P.o[j] * (sold / P.v[j]) : 0.0;  // :597-601
+            if (!P.is_retail[j]) UP = 0.0;                                            // :605
+            double pj = (((SR - PC) - OC) - HC) - UP;                                 // :611
+            total += pj;
+            s_inv += xp;
+            if (!A.rollout && A.info_profit && do_step) A.info_profit[e * J + j] = pj;
+        }
+        last_reward = P.disc[t] * total;  // :619
+        ret += last_reward;
+        if (A.rollout && A.reward_traj && valid) A.reward_traj[e * P.T + t] = last_reward;
+        if (!A.rollout && do_step) {
+            if (A.info_profit_total) A.info_profit_total[e] = total;
+            if (A.info_sales) {
+                for (int i = 0; i < E; i++) A.info_sales[e * (E + M) + i] = sR[i * nthr + tid];
+                for (int r = 0; r < M; r++) A.info_sales[e * (E + M) + E + r] = sS[r * nthr + tid];
+            }
+        }
+        // ---- commit the lead-time rings: slot t % L now holds R[t]
+        if (valid)
+            for (int i = 0; i < E; i++) {
+                const int L = P.L[i];
+                if (L > 0) ring[(size_t)(P.roff[i] + t % L) * np_ + e] = sR[i * nthr + tid];
+            }
+    }
+
+    if (A.rollout) {
+        if (valid) {
+            if (A.ep_return) A.ep_return[e] = ret;
+            if (A.stats) {
+                A.stats[e * 4 + 0] = s_sales; A.stats[e * 4 + 1] = s_dem; A.stats[e * 4 + 2] = s_unf; A.stats[e * 4 + 3] = s_inv;
+            }
+            if (A.final_X) for (int j = 0; j < J; j++) A.final_X[e * J + j] = sX[j * nthr + tid];
+            if (A.final_Y) for (int i = 0; i < E; i++) A.final_Y[e * E + i] = sY[i * nthr + tid];
+            if (A.final_U) for (int r = 0; r < M; r++) A.final_U[e * M + r] = sU[r * nthr + tid];
+        }
+        if (A.partials) {
+            double v[7] = {valid ? 1.0 : 0.0, valid ? ret : 0.0, valid ? ret * ret : 0.0, valid ? s_sales : 0.0,
+                           valid ? s_dem : 0.0, valid ? s_unf : 0.0, valid ? s_inv : 0.0};
+            __shared__ double red[8][7];
+            __syncthreads();
+#pragma unroll
+            for (int z = 0; z < 7; z++) {
+                double x = v[z];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                if ((tid & 31) == 0) red[tid >> 5][z] = x;
+            }
+            __syncthreads();
+            if (tid < 7) {
+                double x = 0.0;
+                for (int wv = 0; wv < nthr / 32; wv++) x += red[wv][tid];
+                A.partials[(size_t)blockIdx.x * 8 + tid] = x;
+            }
+        }
+    } else if (do_step) {
+        const int tn = t0 + 1;
+        const bool trunc = tn >= P.T;  // :624
+        const bool reset_now = trunc && A.autoreset == ORGYM_AUTORESET_SAME_STEP;
+        if (!reset_now) {
+            for (int j = 0; j < J; j++) st.X[(size_t)j * np_ + e] = sX[j * nthr + tid];
+            for (int i = 0; i < E; i++) st.Y[(size_t)i * np_ + e] = sY[i * nthr + tid];
+            for (int r = 0; r < M; r++) st.U[(size_t)r * np_ + e] = sU[r * nthr + tid];
+            st.period[e] = tn;
+            net_write_obs(P, sU, sX, nthr, tid, ring, np_, e, tn, A.obs + e * P.obs_dim);
+        } else {
+            if (A.final_obs) net_write_obs(P, sU, sX, nthr, tid, ring, np_, e, tn, A.final_obs + e * P.obs_dim);
+            for (int j = 0; j < J; j++) {
+                st.X[(size_t)j * np_ + e] = P.I0[j];
+                sX[j * nthr + tid] = P.I0[j];
+            }
+            for (int i = 0; i < E; i++) st.Y[(size_t)i * np_ + e] = 0.0;
+            for (int r = 0; r < M; r++) {
+                st.U[(size_t)r * np_ + e] = 0.0;
+                sU[r * nthr + tid] = 0.0;
+            }
+            for (int k = 0; k < P.sumL; k++) ring[(size_t)k * np_ + e] = 0.0;
+            st.period[e] = 0;
+            st.episode[e] = episode + 1;
+            net_write_obs(P, sU, sX, nthr, tid, ring, np_, e, 0, A.obs + e * P.obs_dim);
+        }
+        A.reward[e] = last_reward;
+        A.terminated[e] = 0;
+        A.truncated[e] = trunc ? 1 : 0;
+    }
+}
+
+__global__ void net_export_kernel(const __grid_constant__ NetDev P, int64_t N, int64_t npad, const void* state,
+                                  double* __restrict__ X, double* __restrict__ Y, double* __restrict__ U,
+                                  int32_t* __restrict__ period) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    NetState st((void*)state, npad, P);
+    if (X) for (int j = 0; j < P.J; j++) X[e * P.J + j] = st.X[(size_t)j * npad + e];
+    if (Y) for (int i = 0; i < P.E; i++) Y[e * P.E + i] = st.Y[(size_t)i * npad + e];
+    if (U) for (int r = 0; r < P.M; r++) U[e * P.M + r] = st.U[(size_t)r * npad + e];
+    if (period) period[e] = st.period[e];
+}
+
+__global__ void orgym_reduce_partials_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out);
+
+// ------------------------------------------------------------------------------------------------
+// host side of the C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int orgym_netinv_create(const orgym_netinv_config_t* c, int64_t num_envs, int device, orgym_handle_t* out) {
+    ORGYM_REQUIRE(c && out, "null argument");
+    // mirrors network_management.py:197-238
+    ORGYM_REQUIRE(c->num_periods > 0, "num_periods must be positive");
+    ORGYM_REQUIRE(c->alpha > 0 && c->alpha <= 1, "alpha must be in (0, 1]");
+    ORGYM_REQUIRE(c->num_main >= 1 && c->num_reorder >= 0 && c->num_retail >= 0, "empty network");
+    if (c->num_main > NJ || c->num_reorder > NE || c->num_retail > NM) {
+        orgym_set_error("network too large for this build: %d main nodes (max %d), %d reorder links (max %d), %d retail links (max %d)",
+                        c->num_main, NJ, c->num_reorder, NE, c->num_retail, NM);
+        return ORGYM_E_UNSUPPORTED;
+    }
+    NetHandle* H = new NetHandle();
+    NetDev& P = H->dev;
+    memset(&P, 0, sizeof(P));
+    P.T = c->num_periods;
+    P.backlog = c->backlog ? 1 : 0;
+    P.J = c->num_main;
+    P.E = c->num_reorder;
+    P.M = c->num_retail;
+    int rc = ORGYM_OK;
+#define FAIL(code, ...)            \
+    do {                           \
+        orgym_set_error(__VA_ARGS__); \
+        rc = code;                 \
+        goto done;                 \
+    } while (0)
+    {
+        for (int j = 0; j < P.J; j++) {
+            P.I0[j] = c->node_I0[j];
+            P.h[j] = c->node_h[j];
+            P.is_factory[j] = c->node_is_factory[j];
+            P.is_retail[j] = c->node_is_retail[j];
+            P.C[j] = c->node_C[j];
+            P.v[j] = c->node_v[j];
+            P.o[j] = c->node_o[j];
+            if (!(P.I0[j] >= 0)) FAIL(ORGYM_E_INVALID, "Node %d: Invalid or missing I0>=0", j);
+            if (!(P.h[j] >= 0)) FAIL(ORGYM_E_INVALID, "Node %d: Invalid or missing h>=0", j);
+            if (P.is_factory[j]) {
+                if (!(P.C[j] > 0)) FAIL(ORGYM_E_INVALID, "Node %d: Invalid or missing C>0", j);
+                if (!(P.o[j] >= 0)) FAIL(ORGYM_E_INVALID, "Node %d: Invalid or missing o>=0", j);
+                if (!(P.v[j] > 0 && P.v[j] <= 1)) FAIL(ORGYM_E_INVALID, "Node %d: Invalid or missing v in (0, 1]", j);
+            } else if (!(P.v[j] > 0))
+                FAIL(ORGYM_E_INVALID, "Node %d: yield must be positive", j);
+        }
+        for (int i = 0; i < P.E; i++) {
+            int s = c->re_supplier[i], pu = c->re_purchaser[i], L = c->re_lead[i];
+            if (s < -2 || s >= P.J || pu < -1 || pu >= P.J) FAIL(ORGYM_E_INVALID, "reorder link %d: bad node index", i);
+            if (L < 0) FAIL(ORGYM_E_INVALID, "Edge %d: Invalid or missing L>=0", i);
+            if (L > ORGYM_NET_MAX_LEAD) FAIL(ORGYM_E_UNSUPPORTED, "lead time %d exceeds this build's limit of %d", L, ORGYM_NET_MAX_LEAD);
+            if (!(c->re_p[i] >= 0) || !(c->re_g[i] >= 0)) FAIL(ORGYM_E_INVALID, "Edge %d: Invalid or missing p>=0 / g>=0", i);
+            if (i > 0 && s >= 0 && c->re_supplier[i - 1] > s)
+                FAIL(ORGYM_E_INVALID, "reorder links must be sorted by supplier (network_management.py:179)");
+            P.sup[i] = (int16_t)s;
+            P.pur[i] = (int16_t)pu;
+            P.L[i] = (int16_t)L;
+            P.roff[i] = P.sumL;
+            P.sumL += L;
+            P.p[i] = c->re_p[i];
+            P.g[i] = c->re_g[i];
+        }
+        // a supplier's links must be contiguous (they are, in sorted order); raw (-1) / unclassified (-2) may interleave
+        for (int i = 1; i < P.E; i++)
+            for (int k = 0; k + 1 < i; k++)
+                if (P.sup[i] >= 0 && P.sup[k] == P.sup[i] && P.sup[i - 1] != P.sup[i])
+                    FAIL(ORGYM_E_INVALID, "links of supplier %d are not contiguous", (int)P.sup[i]);
+        for (int r = 0; r < P.M; r++) {
+            int j = c->rt_retailer[r];
+            if (j < 0 || j >= P.J) FAIL(ORGYM_E_INVALID, "retail link %d: retailer is not an inventory-holding node", r);
+            if (!(c->rt_p[r] >= 0) || !(c->rt_b[r] >= 0)) FAIL(ORGYM_E_INVALID, "Edge %d: Invalid or missing p>=0 / b>=0", r);
+            P.rt_node[r] = (int16_t)j;
+            P.rt_p[r] = c->rt_p[r];
+            P.rt_b[r] = c->rt_b[r];
+        }
+        if (c->succ_ptr[P.J] > NSUCC || c->pred_ptr[P.J] > NE) FAIL(ORGYM_E_UNSUPPORTED, "adjacency lists too long");
+        for (int j = 0; j <= P.J; j++) {
+            P.succ_ptr[j] = (int16_t)c->succ_ptr[j];
+            P.pred_ptr[j] = (int16_t)c->pred_ptr[j];
+        }
+        for (int z = 0; z < c->succ_ptr[P.J]; z++) {
+            if (c->succ_idx[z] < 0 || c->succ_idx[z] >= P.E + P.M) FAIL(ORGYM_E_INVALID, "bad successor link id");
+            P.succ_idx[z] = (int16_t)c->succ_idx[z];
+        }
+        for (int z = 0; z < c->pred_ptr[P.J]; z++) {
+            if (c->pred_idx[z] < 0 || c->pred_idx[z] >= P.E) FAIL(ORGYM_E_INVALID, "bad predecessor link id");
+            P.pred_idx[z] = (int16_t)c->pred_idx[z];
+        }
+        P.obs_dim = P.M + P.J + P.sumL;  // :190
+        rc = orgym_handle_base_init(&H->base, FAM_NETINV, device, num_envs);
+        if (rc != ORGYM_OK) goto done;
+        {
+            DeviceGuard g(device);
+            H->npad = round_up(num_envs, 32);
+            std::vector<double> disc((size_t)P.T);
+            for (int t = 0; t < P.T; t++) disc[(size_t)t] = std::pow(c->alpha, (double)t);
+            double* dd = nullptr;
+            if (cudaMalloc(&dd, 8 * (size_t)P.T) != cudaSuccess) FAIL(ORGYM_E_CUDA, "device allocation failed");
+            H->allocs.push_back(dd);
+            cudaMemcpy(dd, disc.data(), 8 * (size_t)P.T, cudaMemcpyHostToDevice);
+            P.disc = dd;
+            for (int r = 0; r < P.M; r++) {
+                rc = orgym_build_alias(&c->rt_dist[r], 1, &P.dem[r], &H->allocs);
+                if (rc != ORGYM_OK) goto done;
+                if (P.dem[r].kind == ORGYM_DIST_USER && P.dem[r].user_D_len != P.T)
+                    FAIL(ORGYM_E_INVALID, "Edge %d: user_D length %d != num_periods %d", r, P.dem[r].user_D_len, P.T);
+            }
+            size_t per_thread = 8 * (size_t)(2 * P.J + 2 * P.E + 2 * P.M);
+            H->threads = 128;
+            while (H->threads > 32 && per_thread * H->threads > 200 * 1024) H->threads /= 2;
+            if (per_thread * H->threads > 200 * 1024) FAIL(ORGYM_E_UNSUPPORTED, "network work vectors do not fit in shared memory");
+            H->smem = per_thread * H->threads;
+            int nblocks = (int)((num_envs + H->threads - 1) / H->threads);
+            H->partials = nullptr;
+            if (cudaMalloc(&H->partials, 64 * (size_t)nblocks) != cudaSuccess) FAIL(ORGYM_E_CUDA, "device allocation failed");
+            H->allocs.push_back(H->partials);
+            cudaFuncSetAttribute(net_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+        }
+    }
+done:
+#undef FAIL
+    if (rc != ORGYM_OK) {
+        if (H->base.magic == ORGYM_MAGIC) {
+            DeviceGuard g(device);
+            for (void* p : H->allocs) cudaFree(p);
+            orgym_handle_base_free(&H->base);
+        }
+        delete H;
+        return rc;
+    }
+    *out = (orgym_handle_t)H;
+    return ORGYM_OK;
+}
+
+extern "C" int orgym_netinv_destroy(orgym_handle_t h) {
+    if (orgym_check_handle(h, FAM_NETINV)) return ORGYM_E_INVALID;
+    NetHandle* H = (NetHandle*)h;
+    {
+        DeviceGuard g(H->base.device);
+        for (void* p : H->allocs) cudaFree(p);
+    }
+    orgym_handle_base_free(&H->base);
+    delete H;
+    return ORGYM_OK;
+}
+
+extern "C" int64_t orgym_netinv_state_bytes(orgym_handle_t h) {
+    if (orgym_check_handle(h, FAM_NETINV)) return -1;
+    NetHandle* H = (NetHandle*)h;
+    return net_state_bytes(H->dev, H->npad);
+}
+extern "C" int32_t orgym_netinv_obs_dim(orgym_handle_t h) {
+    if (orgym_check_handle(h, FAM_NETINV)) return -1;
+    return ((NetHandle*)h)->dev.obs_dim;
+}
+
+extern "C" int orgym_netinv_reset(orgym_handle_t h, void* state_dev, int reseed, uint64_t seed, int64_t env_offset,
+                                  const uint8_t* mask_dev, float* obs_dev, void* stream) {
+    if (orgym_check_handle(h, FAM_NETINV)) return ORGYM_E_INVALID;
+    NetHandle* H = (NetHandle*)h;
+    ORGYM_REQUIRE(state_dev && obs_dev, "state_dev and obs_dev are required");
+    DeviceGuard g(H->base.device);
+    int64_t N = H->base.num_envs;
+    net_reset_kernel<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(H->dev, N, H->npad, state_dev, reseed,
+                                                                                  seed, env_offset, mask_dev, obs_dev);
+    ORGYM_CUDA(cudaGetLastError());
+    return ORGYM_OK;
+}
+
+extern "C" int orgym_netinv_step(orgym_handle_t h, void* state_dev, const float* actions_dev,
+                                 const double* demand_override_dev, int autoreset_mode, float* obs_dev,
+                                 double* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
+                                 const orgym_netinv_info_t* info, void* stream) {
+    if (orgym_check_handle(h, FAM_NETINV)) return ORGYM_E_INVALID;
+    NetHandle* H = (NetHandle*)h;
+    ORGYM_REQUIRE(state_dev && actions_dev && obs_dev && reward_dev && terminated_dev && truncated_dev,
+                  "state, actions, obs, reward, terminated and truncated pointers are required");
+    ORGYM_REQUIRE(autoreset_mode >= 0 && autoreset_mode <= 2, "bad autoreset mode");
+    DeviceGuard g(H->base.device);
+    const NetDev& P = H->dev;
+    NetSimArgs A;
+    memset(&A, 0, sizeof(A));
+    A.N = H->base.num_envs;
+    A.npad = H->npad;
+    A.rollout = 0;
+    A.state = state_dev;
+    A.policy = ORGYM_NET_POLICY_ACTIONS;
+    A.actions = actions_dev;
+    A.a_se = P.E;
+    A.a_st = 0;
+    A.demand = demand_override_dev;
+    A.d_se = P.M;
+    A.d_st = 0;
+    A.autoreset = autoreset_mode;
+    A.obs = obs_dev;
+    A.reward = reward_dev;
+    A.terminated = terminated_dev;
+    A.truncated = truncated_dev;
+    if (info) {
+        A.info_demand = info->demand_dev;
+        A.info_sales = info->sales_dev;
+        A.info_profit = info->profit_dev;
+        A.info_profit_total = info->profit_total_dev;
+        A.final_obs = info->final_obs_dev;
+    }
+    A.err = H->base.err_dev;
+    net_sim_kernel<<<(unsigned)((A.N + H->threads - 1) / H->threads), H->threads, H->smem, (cudaStream_t)stream>>>(P, A);
+    ORGYM_CUDA(cudaGetLastError());
+    return ORGYM_OK;
+}
+
+extern "C" int orgym_netinv_export_state(orgym_handle_t h, const void* state_dev, double* X_dev, double* Y_dev,
+                                         double* U_dev, int32_t* period_dev, void* stream) {
+    if (orgym_check_handle(h, FAM_NETINV)) return ORGYM_E_INVALID;
+    NetHandle* H = (NetHandle*)h;
+    ORGYM_REQUIRE(state_dev, "state_dev is required");
+    DeviceGuard g(H->base.device);
+    int64_t N = H->base.num_envs;
+    net_export_kernel<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(H->dev, N, H->npad, state_dev, X_dev,
+                                                                                   Y_dev, U_dev, period_dev);
+    ORGYM_CUDA(cudaGetLastError());
+    return ORGYM_OK;
+}
+
+extern "C" int orgym_netinv_rollout(orgym_handle_t h, void* scratch_dev, uint64_t seed, int64_t env_offset,
+                                    uint32_t episode, const orgym_netinv_rollout_in_t* in,
+                                    const orgym_netinv_rollout_out_t* out, void* stream) {
+    if (orgym_check_handle(h, FAM_NETINV)) return ORGYM_E_INVALID;
+    NetHandle* H = (NetHandle*)h;
+    ORGYM_REQUIRE(in && out && scratch_dev, "null argument");
+    ORGYM_REQUIRE(in->policy == ORGYM_NET_POLICY_ACTIONS || in->policy == ORGYM_NET_POLICY_CONSTANT, "unknown policy %d",
+                  in->policy);
+    ORGYM_REQUIRE(in->actions_dev, "actions_dev is required");
+    DeviceGuard g(H->base.device);
+    const NetDev& P = H->dev;
+    NetSimArgs A;
+    memset(&A, 0, sizeof(A));
+    A.N = H->base.num_envs;
+    A.npad = H->npad;
+    A.env_offset = env_offset;
+    A.rollout = 1;
+    A.state = scratch_dev;
+    A.seed = seed;
+    A.episode = episode;
+    A.policy = in->policy;
+    A.actions = in->actions_dev;
+    A.a_se = in->act_stride_env;
+    A.a_st = in->act_stride_t;
+    A.demand = in->demand_dev;
+    A.d_se = in->dem_stride_env;
+    A.d_st = in->dem_stride_t;
+    A.ep_return = out->ep_return_dev;
+    A.stats = out->stats_dev;
+    A.reward_traj = out->reward_traj_dev;
+    A.final_X = out->final_X_dev;
+    A.final_Y = out->final_Y_dev;
+    A.final_U = out->final_U_dev;
+    A.partials = out->summary_dev ? H->partials : nullptr;
+    int nblocks = (int)((A.N + H->threads - 1) / H->threads);
+    net_sim_kernel<<<nblocks, H->threads, H->smem, (cudaStream_t)stream>>>(P, A);
+    ORGYM_CUDA(cudaGetLastError());
+    if (out->summary_dev) {
+        orgym_reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(H->partials, nblocks, out->summary_dev);
+        ORGYM_CUDA(cudaGetLastError());
+    }
+    return ORGYM_OK;
+}

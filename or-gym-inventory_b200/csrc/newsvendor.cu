@@ -1,0 +1,645 @@
+// newsvendor.cu -- multi-period newsvendor with lead time (reference: newsvendor.py).
+//
+//   nv_reset_kernel    reset (newsvendor.py:100-123): five-uniform parameter recipe from the env's Philox stream
+//   nv_step_kernel     one period (:125-204) + observation (:206-208)
+//   nv_rollout_kernel  fused reset + step_limit periods with on-device drivers (order-up-to, classic newsvendor,
+//                      (s,S)) and per-env Poisson demand (PTRS / inversion)
+//
+// The reward is a chain of mixed float32 / float64 / Python-float operations whose precision depends on which
+// branch produced each operand (NumPy >= 2 promotion rules); `Sc` carries the operand kind so the chain is
+// reproduced bit for bit.  Pipeline state is float32 like the reference's `state` vector.
+#include "common.cuh"
+
+#define NV_MAXL ORGYM_NV_MAX_LEAD
+
+struct NvDev {
+    int L, T, obs_dim;
+    double max_inv, max_q, p_max, h_max, k_max, mu_max;
+};
+
+struct NvHandle {
+    HandleBase base;
+    NvDev dev;
+    int64_t npad;
+    std::vector<void*> allocs;
+    double* partials;
+};
+
+// state layout (field[slot][env], stride npad): [key u64][params f64 x5][pipe f32 x L][step i32][episode u32]
+struct NvState {
+    uint64_t* key;
+    double* par;
+    float* pipe;
+    int32_t* step;
+    uint32_t* episode;
+    int64_t npad;
+    __host__ __device__ NvState(void* base, int64_t npad_, int L) : npad(npad_) {
+        char* p = (char*)base;
+        key = (uint64_t*)p;
+        p += 8 * npad;
+        par = (double*)p;
+        p += 8 * 5 * npad;
+        pipe = (float*)p;
+        p += 4 * (size_t)L * npad;
+        step = (int32_t*)p;
+        p += 4 * npad;
+        episode = (uint32_t*)p;
+    }
+};
+static int64_t nv_state_bytes(int64_t npad, int L) { return npad * (8 + 40 + 4 * (int64_t)L + 8); }
+
+// ---- numpy scalar kinds (NEP 50): PY = Python int/float (weak), F32 = np.float32, F64 = np.float64 -----------------
+enum { K_PY = 0, K_F32 = 1, K_F64 = 2 };
+struct Sc {
+    double v;
+    int k;
+};
+__device__ __forceinline__ Sc mk(double v, int k) {
+    Sc s;
+    s.v = v;
+    s.k = k;
+    return s;
+}
+__device__ __forceinline__ Sc sc_mul(Sc a, Sc b) {
+    if (a.k == K_F64 || b.k == K_F64) return mk(a.v * b.v, K_F64);
+    if (a.k == K_PY && b.k == K_PY) return mk(a.v * b.v, K_PY);
+    return mk((double)((float)a.v * (float)b.v), K_F32);
+}
+__device__ __forceinline__ Sc sc_sub(Sc a, Sc b) {
+    if (a.k == K_F64 || b.k == K_F64) return mk(a.v - b.v, K_F64);
+    if (a.k == K_PY && b.k == K_PY) return mk(a.v - b.v, K_PY);
+    return mk((double)((float)a.v - (float)b.v), K_F32);
+}
+
+struct NvParams {
+    double price, cost, h, k, mu;
+};
+
+// newsvendor.py:105-111 from five uniforms
+__device__ __forceinline__ NvParams nv_draw_params(const NvDev& P, uint64_t key, uint32_t episode) {
+    uint4 b0 = philox_block(key, 0u, episode, STREAM_PARAMS, 0u);
+    uint4 b1 = philox_block(key, 1u, episode, STREAM_PARAMS, 0u);
+    uint4 b2 = philox_block(key, 2u, episode, STREAM_PARAMS, 0u);
+    double u0 = u53(b0.x, b0.y), u1 = u53(b0.z, b0.w), u2 = u53(b1.x, b1.y), u3 = u53(b1.z, b1.w), u4 = u53(b2.x, b2.y);
+    NvParams q;
+    double x = u0 * P.p_max;
+    q.price = x > 1.0 ? x : 1.0;  // max(1, .)
+    x = u1 * q.price;
+    q.cost = x > 1.0 ? x : 1.0;
+    q.h = u2 * (P.h_max < q.cost ? P.h_max : q.cost);  // min(cost, h_max)
+    q.k = u3 * P.k_max;
+    q.mu = u4 * P.mu_max;
+    return q;
+}
+
+// fp32 np.sum over the logical pipeline (oldest first); get(j) returns element j
+template <typename F>
+__device__ __forceinline__ float nv_pipe_sum(int L, F get) {
+    if (L < 8) {
+        float r = 0.0f;
+        for (int j = 0; j < L; j++) r = r + get(j);
+        return r;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = get(j);
+    int full = L - (L % 8), i = 8;
+    for (; i < full; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = r[j] + get(i + j);
+    }
+    float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < L; i++) res = res + get(i);
+    return res;
+}
+
+// one period (newsvendor.py:125-204).  pipe0 = state[5] (arriving now), psum = fp32 sum of the pipeline.
+// returns the reward; *oq_out = order actually placed (float32 value stored in the pipeline); parts optional.
+__device__ __forceinline__ double nv_period(const NvDev& P, const NvParams& q, float action, long long demand, float pipe0,
+                                            float psum, float* oq_out, double* parts, double* su_out, double* ex_out,
+                                            double* sh_out) {
+    double a = (double)action;                        // .item() -> Python float (:131)
+    a = a < 0.0 ? 0.0 : (a > P.max_q ? P.max_q : a);  // np.clip -> np.float64 (:132)
+    Sc order = mk(a, K_F64);
+    Sc inv = P.L > 0 ? mk((double)pipe0, K_F32) : order;     // :136-139
+    Sc cap = mk((double)((float)P.max_inv - psum), K_F32);   // int - np.float32 -> float32 (:143)
+    Sc mn = cap.v < order.v ? cap : order;                   // min(order_qty, cap)
+    Sc oq = mn.v > 0.0 ? mn : mk(0.0, K_PY);                 // max(0, .)
+    Sc dem = mk((double)demand, K_PY);
+    Sc su = dem.v < inv.v ? dem : inv;                       // min(inv_on_hand, demand) (:149)
+    Sc rev = sc_mul(su, mk(q.price, K_PY));                  // :150
+    Sc ex = sc_sub(inv, dem);
+    Sc exs = ex.v > 0.0 ? ex : mk(0.0, K_PY);                // :152
+    Sc sh = sc_sub(dem, inv);
+    Sc shs = sh.v > 0.0 ? sh : mk(0.0, K_PY);                // :153
+    Sc pc = sc_mul(oq, mk(q.cost, K_PY));                    // :162
+    Sc hc = sc_mul(exs, mk(q.h, K_PY));                      // :166
+    Sc lp = sc_mul(shs, mk(q.k, K_PY));                      // :167
+    Sc rew = sc_sub(sc_sub(sc_sub(rev, pc), hc), lp);        // :170
+    *oq_out = (float)oq.v;                                   // new_pipeline[-1] = order_qty (:179)
+    if (parts) {
+        parts[0] = rev.v;
+        parts[1] = pc.v;
+        parts[2] = hc.v;
+        parts[3] = lp.v;
+    }
+    if (su_out) {
+        *su_out = su.v;
+        *ex_out = exs.v;
+        *sh_out = shs.v;
+    }
+    return rew.v;
+}
+
+// ---- reset ------------------------------------------------------------------------------------------------------
+__global__ void nv_reset_kernel(const __grid_constant__ NvDev P, int64_t N, int64_t npad, void* state, int reseed,
+                                uint64_t seed, int64_t env_offset, const uint8_t* __restrict__ mask,
+                                const double* __restrict__ fixed, float* __restrict__ obs) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    if (mask && !mask[e]) return;
+    NvState st(state, npad, P.L);
+    uint64_t key;
+    uint32_t ep;
+    if (reseed) {
+        key = seed + (uint64_t)(env_offset + e);
+        ep = 0;
+        st.key[e] = key;
+    } else {
+        key = st.key[e];
+        ep = st.episode[e] + 1;
+    }
+    st.episode[e] = ep;
+    NvParams q;
+    if (fixed) {
+        q.price = fixed[e * 5 + 0]; q.cost = fixed[e * 5 + 1]; q.h = fixed[e * 5 + 2]; q.k = fixed[e * 5 + 3];
+        q.mu = fixed[e * 5 + 4];
+    } else
+        q = nv_draw_params(P, key, ep);
+    st.par[0 * npad + e] = q.price;
+    st.par[1 * npad + e] = q.cost;
+    st.par[2 * npad + e] = q.h;
+    st.par[3 * npad + e] = q.k;
+    st.par[4 * npad + e] = q.mu;
+    for (int j = 0; j < P.L; j++) st.pipe[(size_t)j * npad + e] = 0.0f;
+    st.step[e] = 0;
+    float* o = obs + e * P.obs_dim;
+    o[0] = (float)q.price; o[1] = (float)q.cost; o[2] = (float)q.h; o[3] = (float)q.k; o[4] = (float)q.mu;  // :115
+    for (int j = 0; j < P.L; j++) o[5 + j] = 0.0f;
+}
+
+// ---- step ------------------------------------------------------------------------------------------------------
+struct NvStepArgs {
+    int64_t N, npad;
+    void* state;
+    const float* actions;
+    const int64_t* demand;
+    int autoreset;
+    float* obs;
+    double* reward;
+    uint8_t* terminated;
+    uint8_t* truncated;
+    int64_t* info_demand;
+    double* info_parts;
+    float* final_obs;
+    uint32_t* err;
+    int use_bulk;
+};
+
+__global__ void __launch_bounds__(ORGYM_TILE) nv_step_kernel(const __grid_constant__ NvDev P, const NvStepArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* tile = (float*)smem;
+    const int tid = threadIdx.x, W = P.obs_dim;
+    const int64_t e0 = (int64_t)blockIdx.x * ORGYM_TILE, e = e0 + tid;
+    const int nvalid = (int)((A.N - e0) < ORGYM_TILE ? (A.N - e0) : ORGYM_TILE);
+    const bool valid = tid < nvalid;
+    const bool dense = (W % 4) != 0;  // <= 2-way bank conflicts on the dense tile
+    const int stride = dense ? W : W + 1;
+    const bool bulk = A.use_bulk && dense && nvalid == ORGYM_TILE;
+    NvState st(A.state, A.npad, P.L);
+    if (valid) {
+        float* row = tile + tid * stride;
+        int sc = st.step[e];
+        uint32_t ep = st.episode[e];
+        uint64_t key = st.key[e];
+        NvParams q;
+        q.price = st.par[0 * A.npad + e]; q.cost = st.par[1 * A.npad + e]; q.h = st.par[2 * A.npad + e];
+        q.k = st.par[3 * A.npad + e]; q.mu = st.par[4 * A.npad + e];
+        bool do_step = true;
+        if (sc >= P.T) {
+            do_step = false;
+            if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {
+                ep += 1;
+                q = nv_draw_params(P, key, ep);
+                st.episode[e] = ep;
+                for (int z = 0; z < 5; z++) st.par[(size_t)z * A.npad + e] = (&q.price)[z];
+                for (int j = 0; j < P.L; j++) st.pipe[(size_t)j * A.npad + e] = 0.0f;
+                st.step[e] = 0;
+                for (int z = 0; z < 5; z++) row[z] = (float)(&q.price)[z];
+                for (int j = 0; j < P.L; j++) row[5 + j] = 0.0f;
+                A.reward[e] = 0.0; A.terminated[e] = 0; A.truncated[e] = 0;
+            } else {
+                atomicOr(A.err, ORGYM_ERR_STEP_PAST_END);
+                const float* old = A.obs + e * W;
+                for (int z = 0; z < W; z++) row[z] = old[z];
+                A.reward[e] = 0.0; A.terminated[e] = 0; A.truncated[e] = 1;
+            }
+        }
+        if (do_step) {
+            const float* pp = st.pipe + e;
+            const int64_t np_ = A.npad;
+            float psum = nv_pipe_sum(P.L, [&](int j) { return pp[(size_t)j * np_]; });
+            float pipe0 = P.L > 0 ? pp[0] : 0.0f;
+            long long d = A.demand ? A.demand[e] : poisson_mu(q.mu, key, ep, sc);
+            float oq;
+            double parts[4];
+            double r = nv_period(P, q, A.actions[e], d, pipe0, psum, &oq, parts, nullptr, nullptr, nullptr);
+            int sc1 = sc + 1;
+            bool trunc = sc1 >= P.T;  // :190
+            bool reset_now = trunc && A.autoreset == ORGYM_AUTORESET_SAME_STEP;
+            for (int z = 0; z < 5; z++) row[z] = (float)(&q.price)[z];
+            for (int j = 0; j + 1 < P.L; j++) row[5 + j] = pp[(size_t)(j + 1) * np_];  // shift left (:177)
+            if (P.L > 0) row[5 + P.L - 1] = oq;
+            if (!reset_now) {
+                float* pw = st.pipe + e;
+                for (int j = 0; j < P.L; j++) pw[(size_t)j * np_] = row[5 + j];
+                st.step[e] = sc1;
+            } else {
+                if (A.final_obs)
+                    for (int z = 0; z < W; z++) A.final_obs[e * W + z] = row[z];
+                ep += 1;
+                q = nv_draw_params(P, key, ep);
+                st.episode[e] = ep;
+                for (int z = 0; z < 5; z++) st.par[(size_t)z * A.npad + e] = (&q.price)[z];
+                for (int j = 0; j < P.L; j++) st.pipe[(size_t)j * A.npad + e] = 0.0f;
+                st.step[e] = 0;
+                for (int z = 0; z < 5; z++) row[z] = (float)(&q.price)[z];
+                for (int j = 0; j < P.L; j++) row[5 + j] = 0.0f;
+            }
+            A.reward[e] = r;
+            A.terminated[e] = 0;
+            A.truncated[e] = trunc ? 1 : 0;
+            if (A.info_demand) A.info_demand[e] = d;
+            if (A.info_parts)
+                for (int z = 0; z < 4; z++) A.info_parts[e * 4 + z] = parts[z];
+        }
+    }
+    float* g = A.obs + (size_t)e0 * W;
+    if (bulk) {
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(g, tile, (uint32_t)(ORGYM_TILE * W * 4));
+            bulk_commit();
+            bulk_wait_read0();
+        }
+    } else {
+        __syncthreads();
+        int total = nvalid * W;
+        for (int i = tid; i < total; i += ORGYM_TILE) {
+            int r = i / W, c = i - r * W;
+            g[i] = tile[r * stride + c];
+        }
+    }
+}
+
+__global__ void nv_export_params_kernel(int64_t N, int64_t npad, int L, const void* state, double* __restrict__ out) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    NvState st((void*)state, npad, L);
+    for (int z = 0; z < 5; z++) out[e * 5 + z] = st.par[(size_t)z * npad + e];
+}
+
+// ---- Poisson quantile: smallest k with cdf(k) >= q (scipy.stats.poisson.ppf) ---------------------------------------
+__device__ __forceinline__ double poisson_ppf_dev(double q, double mu) {
+    if (!(q > 0.0)) return -1.0;
+    if (q >= 1.0) return INFINITY;
+    double lo = floor(mu - 12.0 * sqrt(mu) - 12.0);
+    if (lo < 0.0) lo = 0.0;
+    double term = exp(-mu + lo * log(mu) - lgamma(lo + 1.0)), cdf = 0.0, k = lo;
+    for (;;) {
+        cdf += term;
+        if (cdf >= q) return k;
+        k += 1.0;
+        term *= mu / k;
+        if (term == 0.0 && k > mu) return k;
+    }
+}
+
+// ---- fused rollout ----------------------------------------------------------------------------------------------
+struct NvRolloutArgs {
+    int64_t N, env_offset;
+    uint64_t seed;
+    uint32_t episode;
+    int policy;
+    double param0;
+    const float* actions;
+    int64_t a_se, a_st;
+    const int64_t* demand;
+    int64_t d_se, d_st;
+    const double* fixed;
+    double* ep_return;
+    double* stats;
+    double* reward_traj;
+    float* action_traj;
+    float* final_obs;
+    double* partials;
+};
+
+#define NV_ROLL_THREADS 128
+
+__device__ __forceinline__ float clipf(float q, float hi) { return q < 0.0f ? 0.0f : (q > hi ? hi : q); }
+
+__global__ void __launch_bounds__(NV_ROLL_THREADS) nv_rollout_kernel(const __grid_constant__ NvDev P,
+                                                                     const __grid_constant__ NvRolloutArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* ring = (float*)smem;  // [L][threads], logical index j lives at slot (head + j) % L
+    const int tid = threadIdx.x, L = P.L;
+    const int64_t e = (int64_t)blockIdx.x * NV_ROLL_THREADS + tid;
+    const bool valid = e < A.N;
+    for (int j = 0; j < L; j++) ring[j * NV_ROLL_THREADS + tid] = 0.0f;
+    const uint64_t key = A.seed + (uint64_t)(A.env_offset + e);
+    NvParams q;
+    if (A.fixed && valid) {
+        q.price = A.fixed[e * 5 + 0]; q.cost = A.fixed[e * 5 + 1]; q.h = A.fixed[e * 5 + 2]; q.k = A.fixed[e * 5 + 3];
+        q.mu = A.fixed[e * 5 + 4];
+    } else
+        q = nv_draw_params(P, key, A.episode);
+    const float fh = (float)q.h, fk = (float)q.k, fmu = (float)q.mu, hi = (float)P.max_q;
+    // per-episode constants of the drivers (they only read the float32 observation entries h, k, mu)
+    double level = 0.0;
+    bool fallback = false;
+    if (A.policy == ORGYM_NV_POLICY_CLASSIC) {  // benchmark_newsvendor.py:113-161 (k_vs_h)
+        float hk = fh + fk;
+        fallback = hk <= 1e-6f || fk < 0.0f || fh < 0.0f;
+        if (!fallback) {
+            float cr = fk / hk;
+            float eff = (fmu * (float)(L + 1)) * (float)A.param0;
+            level = poisson_ppf_dev((double)cr, eff > 1e-6f ? (double)eff : 1e-6);
+        }
+    } else if (A.policy == ORGYM_NV_POLICY_SS) {  // benchmark_newsvendor_sb3_rllib.py:363-371
+        if (fh + fk > 1e-6f) {
+            float cr = fk / (fh + fk);
+            cr = cr < 0.001f ? 0.001f : (cr > 0.999f ? 0.999f : cr);
+            float eff = fmu * (float)(L + 1);
+            level = poisson_ppf_dev((double)cr, eff > 1e-6f ? (double)eff : 1e-6);
+        }
+        level = level > 0.0 ? level : 0.0;
+    }
+    int head = 0;
+    double ret = 0.0, s_sales = 0.0, s_dem = 0.0, s_lost = 0.0, s_ex = 0.0;
+    for (int t = 0; t < P.T; t++) {
+        auto get = [&](int j) {
+            int s = head + j;
+            s = s >= L ? s - L : s;
+            return ring[s * NV_ROLL_THREADS + tid];
+        };
+        float psum = nv_pipe_sum(L, get);
+        float pipe0 = L > 0 ? ring[head * NV_ROLL_THREADS + tid] : 0.0f;
+        float act;
+        if (A.policy == ORGYM_NV_POLICY_ACTIONS)
+            act = valid ? A.actions[e * A.a_se + (int64_t)t * A.a_st] : 0.0f;
+        else if (A.policy == ORGYM_NV_POLICY_ORDER_UP_TO || (A.policy == ORGYM_NV_POLICY_CLASSIC && fallback)) {
+            // benchmark_newsvendor.py:103-111 -- all float32
+            float target = fmu * (float)(L + 1);
+            if (A.policy == ORGYM_NV_POLICY_ORDER_UP_TO) target = target * (float)A.param0;
+            float x = target - psum;
+            act = clipf(x > 0.0f ? x : 0.0f, hi);
+        } else if (A.policy == ORGYM_NV_POLICY_CLASSIC) {
+            double x = level - (double)psum;  // np.float64 - np.float32
+            x = x > 0.0 ? x : 0.0;
+            x = x > (double)hi ? (double)hi : x;
+            act = (float)x;
+        } else {  // (s,S)
+            double x = 0.0;
+            if ((double)psum < level) {
+                x = level * A.param0 - (double)psum;
+                x = x > 0.0 ? x : 0.0;
+            }
+            x = x > (double)hi ? (double)hi : x;
+            act = (float)x;
+        }
+        long long d;
+        if (A.demand)
+            d = valid ? A.demand[e * A.d_se + (int64_t)t * A.d_st] : 0;
+        else
+            d = poisson_mu(q.mu, key, A.episode, t);
+        float oq;
+        double su, ex, sh;
+        double r = nv_period(P, q, act, d, pipe0, psum, &oq, nullptr, &su, &ex, &sh);
+        ret += r;
+        s_sales += su; s_dem += (double)d; s_lost += sh; s_ex += ex;
+        if (valid && A.reward_traj) A.reward_traj[e * P.T + t] = r;
+        if (valid && A.action_traj) A.action_traj[e * P.T + t] = act;
+        if (L > 0) {  // shift left, append: overwrite the slot that just arrived and advance the head
+            ring[head * NV_ROLL_THREADS + tid] = oq;
+            head = head + 1 == L ? 0 : head + 1;
+        }
+    }
+    if (valid) {
+        if (A.ep_return) A.ep_return[e] = ret;
+        if (A.stats) {
+            A.stats[e * 4 + 0] = s_sales; A.stats[e * 4 + 1] = s_dem; A.stats[e * 4 + 2] = s_lost; A.stats[e * 4 + 3] = s_ex;
+        }
+        if (A.final_obs) {
+            float* o = A.final_obs + e * P.obs_dim;
+            o[0] = (float)q.price; o[1] = (float)q.cost; o[2] = fh; o[3] = fk; o[4] = fmu;
+            for (int j = 0; j < L; j++) {
+                int s = head + j;
+                s = s >= L ? s - L : s;
+                o[5 + j] = ring[s * NV_ROLL_THREADS + tid];
+            }
+        }
+    }
+    if (A.partials) {
+        double v[7] = {valid ? 1.0 : 0.0, valid ? ret : 0.0, valid ? ret * ret : 0.0, valid ? s_sales : 0.0,
+                       valid ? s_dem : 0.0, valid ? s_lost : 0.0, valid ? s_ex : 0.0};
+        __shared__ double red[NV_ROLL_THREADS / 32][7];
+#pragma unroll
+        for (int z = 0; z < 7; z++) {
+            double x = v[z];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if ((tid & 31) == 0) red[tid >> 5][z] = x;
+        }
+        __syncthreads();
+        if (tid < 7) {
+            double x = 0.0;
+            for (int wv = 0; wv < NV_ROLL_THREADS / 32; wv++) x += red[wv][tid];
+            A.partials[(size_t)blockIdx.x * 8 + tid] = x;
+        }
+    }
+}
+
+__global__ void orgym_reduce_partials_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out);
+
+// ------------------------------------------------------------------------------------------------
+// host side of the C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int orgym_newsvendor_create(const orgym_newsvendor_config_t* cfg, int64_t num_envs, int device,
+                                       orgym_handle_t* out) {
+    ORGYM_REQUIRE(cfg && out, "null argument");
+    ORGYM_REQUIRE(cfg->lead_time >= 0, "lead_time must be >= 0 (the reference clamps it, newsvendor.py:65)");
+    ORGYM_REQUIRE(cfg->step_limit > 0, "step_limit must be positive");
+    if (cfg->lead_time > NV_MAXL) {
+        orgym_set_error("lead_time %d exceeds this build's limit of %d", cfg->lead_time, NV_MAXL);
+        return ORGYM_E_UNSUPPORTED;
+    }
+    NvHandle* H = new NvHandle();
+    NvDev& P = H->dev;
+    P.L = cfg->lead_time;
+    P.T = cfg->step_limit;
+    P.obs_dim = P.L + 5;
+    P.max_inv = cfg->max_inventory;
+    P.max_q = cfg->max_order_quantity;
+    P.p_max = cfg->p_max; P.h_max = cfg->h_max; P.k_max = cfg->k_max; P.mu_max = cfg->mu_max;
+    int rc = orgym_handle_base_init(&H->base, FAM_NEWSVENDOR, device, num_envs);
+    if (rc != ORGYM_OK) {
+        delete H;
+        return rc;
+    }
+    DeviceGuard g(device);
+    H->npad = round_up(num_envs, 32);
+    int nblocks = (int)((num_envs + NV_ROLL_THREADS - 1) / NV_ROLL_THREADS);
+    H->partials = nullptr;
+    cudaError_t ce = cudaMalloc(&H->partials, sizeof(double) * 8 * (size_t)nblocks);
+    if (ce != cudaSuccess) {
+        orgym_set_error("device allocation failed: %s", cudaGetErrorString(ce));
+        orgym_handle_base_free(&H->base);
+        delete H;
+        return ORGYM_E_CUDA;
+    }
+    H->allocs.push_back(H->partials);
+    *out = (orgym_handle_t)H;
+    return ORGYM_OK;
+}
+
+extern "C" int orgym_newsvendor_destroy(orgym_handle_t h) {
+    if (orgym_check_handle(h, FAM_NEWSVENDOR)) return ORGYM_E_INVALID;
+    NvHandle* H = (NvHandle*)h;
+    {
+        DeviceGuard g(H->base.device);
+        for (void* p : H->allocs) cudaFree(p);
+    }
+    orgym_handle_base_free(&H->base);
+    delete H;
+    return ORGYM_OK;
+}
+
+extern "C" int64_t orgym_newsvendor_state_bytes(orgym_handle_t h) {
+    if (orgym_check_handle(h, FAM_NEWSVENDOR)) return -1;
+    NvHandle* H = (NvHandle*)h;
+    return nv_state_bytes(H->npad, H->dev.L);
+}
+extern "C" int32_t orgym_newsvendor_obs_dim(orgym_handle_t h) {
+    if (orgym_check_handle(h, FAM_NEWSVENDOR)) return -1;
+    return ((NvHandle*)h)->dev.obs_dim;
+}
+
+extern "C" int orgym_newsvendor_reset(orgym_handle_t h, void* state_dev, int reseed, uint64_t seed, int64_t env_offset,
+                                      const uint8_t* mask_dev, const double* fixed_params_dev, float* obs_dev,
+                                      void* stream) {
+    if (orgym_check_handle(h, FAM_NEWSVENDOR)) return ORGYM_E_INVALID;
+    NvHandle* H = (NvHandle*)h;
+    ORGYM_REQUIRE(state_dev && obs_dev, "state_dev and obs_dev are required");
+    DeviceGuard g(H->base.device);
+    int64_t N = H->base.num_envs;
+    nv_reset_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        H->dev, N, H->npad, state_dev, reseed, seed, env_offset, mask_dev, fixed_params_dev, obs_dev);
+    ORGYM_CUDA(cudaGetLastError());
+    return ORGYM_OK;
+}
+
+static int nv_use_bulk() {
+    const char* v = getenv("ORGYM_NO_BULK");
+    return (v && v[0] == '1') ? 0 : 1;
+}
+
+extern "C" int orgym_newsvendor_step(orgym_handle_t h, void* state_dev, const float* actions_dev,
+                                     const int64_t* demand_override_dev, int autoreset_mode, float* obs_dev,
+                                     double* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
+                                     const orgym_newsvendor_info_t* info, void* stream) {
+    if (orgym_check_handle(h, FAM_NEWSVENDOR)) return ORGYM_E_INVALID;
+    NvHandle* H = (NvHandle*)h;
+    ORGYM_REQUIRE(state_dev && actions_dev && obs_dev && reward_dev && terminated_dev && truncated_dev,
+                  "state, actions, obs, reward, terminated and truncated pointers are required");
+    ORGYM_REQUIRE(autoreset_mode >= 0 && autoreset_mode <= 2, "bad autoreset mode");
+    DeviceGuard g(H->base.device);
+    NvStepArgs A;
+    memset(&A, 0, sizeof(A));
+    A.N = H->base.num_envs;
+    A.npad = H->npad;
+    A.state = state_dev;
+    A.actions = actions_dev;
+    A.demand = demand_override_dev;
+    A.autoreset = autoreset_mode;
+    A.obs = obs_dev;
+    A.reward = reward_dev;
+    A.terminated = terminated_dev;
+    A.truncated = truncated_dev;
+    if (info) {
+        A.info_demand = info->demand_dev;
+        A.info_parts = info->parts_dev;
+        A.final_obs = info->final_obs_dev;
+    }
+    A.err = H->base.err_dev;
+    A.use_bulk = nv_use_bulk() && ((uintptr_t)obs_dev % 16 == 0);
+    size_t smem = (size_t)ORGYM_TILE * (H->dev.obs_dim + 1) * 4;
+    cudaFuncSetAttribute(nv_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    nv_step_kernel<<<(unsigned)((A.N + ORGYM_TILE - 1) / ORGYM_TILE), ORGYM_TILE, smem, (cudaStream_t)stream>>>(H->dev, A);
+    ORGYM_CUDA(cudaGetLastError());
+    return ORGYM_OK;
+}
+
+extern "C" int orgym_newsvendor_export_params(orgym_handle_t h, const void* state_dev, double* params_dev, void* stream) {
+    if (orgym_check_handle(h, FAM_NEWSVENDOR)) return ORGYM_E_INVALID;
+    NvHandle* H = (NvHandle*)h;
+    ORGYM_REQUIRE(state_dev && params_dev, "null argument");
+    DeviceGuard g(H->base.device);
+    int64_t N = H->base.num_envs;
+    nv_export_params_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, H->npad, H->dev.L, state_dev,
+                                                                                         params_dev);
+    ORGYM_CUDA(cudaGetLastError());
+    return ORGYM_OK;
+}
+
+extern "C" int orgym_newsvendor_rollout(orgym_handle_t h, uint64_t seed, int64_t env_offset, uint32_t episode,
+                                        const orgym_newsvendor_rollout_in_t* in,
+                                        const orgym_newsvendor_rollout_out_t* out, void* stream) {
+    if (orgym_check_handle(h, FAM_NEWSVENDOR)) return ORGYM_E_INVALID;
+    NvHandle* H = (NvHandle*)h;
+    ORGYM_REQUIRE(in && out, "null argument");
+    ORGYM_REQUIRE(in->policy >= 0 && in->policy <= 3, "unknown policy %d", in->policy);
+    ORGYM_REQUIRE(in->policy != ORGYM_NV_POLICY_ACTIONS || in->actions_dev, "policy ACTIONS needs actions_dev");
+    DeviceGuard g(H->base.device);
+    NvRolloutArgs A;
+    memset(&A, 0, sizeof(A));
+    A.N = H->base.num_envs;
+    A.env_offset = env_offset;
+    A.seed = seed;
+    A.episode = episode;
+    A.policy = in->policy;
+    A.param0 = in->param[0];
+    A.actions = in->actions_dev;
+    A.a_se = in->act_stride_env;
+    A.a_st = in->act_stride_t;
+    A.demand = in->demand_dev;
+    A.d_se = in->dem_stride_env;
+    A.d_st = in->dem_stride_t;
+    A.fixed = in->fixed_params_dev;
+    A.ep_return = out->ep_return_dev;
+    A.stats = out->stats_dev;
+    A.reward_traj = out->reward_traj_dev;
+    A.action_traj = out->action_traj_dev;
+    A.final_obs = out->final_obs_dev;
+    A.partials = out->summary_dev ? H->partials : nullptr;
+    size_t smem = (size_t)H->dev.L * NV_ROLL_THREADS * 4 + 16;
+    int nblocks = (int)((A.N + NV_ROLL_THREADS - 1) / NV_ROLL_THREADS);
+    nv_rollout_kernel<<<nblocks, NV_ROLL_THREADS, smem, (cudaStream_t)stream>>>(H->dev, A);
+    ORGYM_CUDA(cudaGetLastError());
+    if (out->summary_dev) {
+        orgym_reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(H->partials, nblocks, out->summary_dev);
+        ORGYM_CUDA(cudaGetLastError());
+    }
+    return ORGYM_OK;
+}

@@ -29,3 +29,17 @@ def seq_sum(x):
     for v in np.asarray(x).tolist():
         s += v
     return s
+
+
+def net_params(meta, pkg):
+    """NetInvMgmtParams for a golden network case (graph spec + flags recorded by make_golden.py)."""
+    return pkg.NetInvMgmtParams(graph=meta["graph"], num_periods=meta["num_periods"], backlog=meta["backlog"],
+                                alpha=meta["alpha"])
+
+
+def net_S_columns(meta):
+    """The reference's S frame is ordered by sorted network_links; ours is reorder links then retail links."""
+    nl = [tuple(x) for x in meta["network_links"]]
+    re = [tuple(x) for x in meta["reorder_links"]]
+    rt = [tuple(x) for x in meta["retail_links"]]
+    return [nl.index(e) for e in re] + [nl.index(e) for e in rt]

@@ -51,3 +51,106 @@ def test_invmgmt_known_answers():
     assert o["LS"].sum(axis=0).tolist() == [43, 0, 0, 0]
     assert oracle.invmgmt_episode(pkg.InvManagementParams(), actions=np.zeros((30, 3)), seed=42)["obs"][0].tolist() == \
         [100, 150, 200] + [0] * 30
+
+
+NV = golden_files("newsvendor_")
+NV_PP = {"order_up_to": 1.0, "classic": 1.0, "sS": 1.2}
+
+
+@pytest.mark.parametrize("path", NV, ids=ids(NV))
+def test_newsvendor_oracle_matches_reference(path):
+    g, meta = load_golden(path)
+    P = pkg.NewsvendorParams(**meta["cfg"])
+    for e in range(len(g["seeds"])):
+        seed = int(g["seeds"][e])
+        fixed = None if meta["fixed"] is None else g["params"][e]
+        # replay: recorded actions + recorded demand; parameters from the numpy-compatible reset stream
+        o = oracle.newsvendor_episode(P, actions=g["actions"][e], demand=g["demand"][e], fixed=fixed, seed=seed)
+        assert np.array_equal(o["params"], g["params"][e])
+        assert np.array_equal(o["obs"], g["obs"][e])
+        assert np.array_equal(o["reward"], g["reward"][e])
+        assert np.array_equal(o["parts"], g["parts"][e])
+        if fixed is None:  # the whole episode from the seed alone, demand included
+            o2 = oracle.newsvendor_episode(P, actions=g["actions"][e], seed=seed)
+            assert np.array_equal(o2["demand"], g["demand"][e])
+            assert np.array_equal(o2["reward"], g["reward"][e])
+        if meta["policy"] in NV_PP:  # the drivers recompute the recorded actions
+            o3 = oracle.newsvendor_episode(P, policy=meta["policy"], pparam=NV_PP[meta["policy"]],
+                                           demand=g["demand"][e], fixed=fixed, seed=seed)
+            assert np.array_equal(o3["actions"], g["actions"][e, :, 0])
+            assert np.array_equal(o3["reward"], g["reward"][e])
+
+
+def test_newsvendor_known_answers():
+    """NewsvendorEnv() reset(seed=42), seven steps with action 50.5."""
+    P = pkg.NewsvendorParams()
+    o = oracle.newsvendor_episode(P, actions=np.full(40, 50.5, np.float32), seed=42)
+    assert o["params"].tolist() == [77.39560485559633, 33.967262302690486, 4.292989599556912, 6.973680290593639,
+                                    18.835469577529906]
+    assert o["demand"][0] == 23 and o["reward"][0] == -1875.741399606182
+    assert o["demand"][6] == 25 and o["reward"][6] == 110.07213792142147
+
+
+def test_poisson_ppf_matches_scipy():
+    from scipy.stats import poisson
+    rng = np.random.default_rng(1)
+    q = np.concatenate([rng.random(3000), [1e-12, 1e-6, 0.001, 0.5, 0.999, 1 - 1e-9]])
+    mu = np.concatenate([rng.random(3000) * 1300 + 1e-3, [1e-6, 0.5, 20, 200, 1200, 1200]])
+    mine = np.array([oracle.poisson_ppf(a, b) for a, b in zip(q, mu)])
+    ref = poisson.ppf(q, mu)
+    assert np.array_equal(mine, ref)
+    assert oracle.poisson_ppf(0.0, 5.0) == poisson.ppf(0.0, 5.0) == -1.0
+    assert np.isinf(oracle.poisson_ppf(1.0, 5.0)) and np.isinf(poisson.ppf(1.0, 5.0))
+
+
+NET = golden_files("net_")
+
+
+@pytest.mark.parametrize("path", NET, ids=ids(NET))
+def test_netinv_oracle_matches_reference(path):
+    from helpers import net_params, net_S_columns
+    g, meta = load_golden(path)
+    P = net_params(meta, pkg)
+    # host-side classification reproduces the reference's (network_management.py:146-195)
+    assert [int(j) for j in P.main_nodes] == meta["main_nodes"]
+    assert [list(e) for e in P.reorder_links] == meta["reorder_links"]
+    assert [list(e) for e in P.retail_links] == meta["retail_links"]
+    assert P.obs_dim == meta["obs_dim"]
+    obs_space, act_space = P.spaces()
+    assert float(act_space.high[0]) == meta["action_high"]
+    assert np.array_equal(obs_space.low, np.asarray(meta["obs_low"], np.float32))
+    assert np.array_equal(obs_space.high, np.asarray(meta["obs_high"], np.float32))
+    cols = net_S_columns(meta)
+    for e in range(len(g["seeds"])):
+        o = oracle.netinv_episode(P, actions=g["actions"][e], demand=g["D"][e])
+        for k in ("obs", "reward", "profit", "X", "Y", "U", "R", "P"):
+            assert np.array_equal(o[k], g[k][e]), (k, e)
+        assert np.array_equal(o["S"], g["S"][e][:, cols])
+        # the reference's own PCG64 Poisson demand, from the seed (one draw per retail link per period)
+        o2 = oracle.netinv_episode(P, actions=g["actions"][e], seed=int(g["seeds"][e]))
+        assert np.array_equal(o2["D"], g["D"][e])
+        assert np.array_equal(o2["reward"], g["reward"][e])
+
+
+def test_netinv_known_answers():
+    """default graph, seed 6000, constant action 170 on all links."""
+    P = pkg.NetInvMgmtParams()
+    assert P.obs_dim == 68 and len(P.reorder_links) == 11 and P.spaces()[1].high[0] == 1700
+    o = oracle.netinv_episode(P, actions=np.full(11, 170, np.float32), seed=6000, constant=True)
+    assert o["D"][:, 0].tolist() == [20, 17, 23, 23, 18, 17, 15, 15, 14, 25, 16, 19, 15, 9, 12, 13, 21, 16, 20, 16, 20,
+                                     15, 21, 20, 22, 20, 22, 23, 22, 14]
+    assert o["X"][30].tolist() == [4947, 1900, 170, 170, 7340, 680]
+    assert o["Y"][30].tolist() == [850, 510, 720, 830, 810, 880, 960, 0, 170, 340, 0]
+    assert abs(seq_sum(o["reward"]) + 5901.330000000001) < 1e-9
+    Pc = pkg.NetInvMgmtParams(num_periods=40, default_graph_kind="custom")
+    assert Pc.obs_dim == 12 and Pc.spaces()[1].high[0] == 3200
+    oc = oracle.netinv_episode(Pc, actions=np.full(5, 320, np.float32), seed=7000, constant=True)
+    assert oc["D"][0].tolist() == [20, 28, 21]
+    assert abs(seq_sum(oc["reward"]) + 4220.000000000002) < 1e-9
+
+
+def test_netinv_lostsales_class_quirk():
+    """NetInvMgmtLostSalesEnv() runs backlog dynamics in the reference (ctor arg overrides env_config, :83-85)."""
+    P = pkg.NetInvMgmtParams(env_config={"backlog": False})
+    assert P.backlog is True
+    assert pkg.NetInvMgmtParams(backlog=False).backlog is False
