@@ -18,6 +18,7 @@
 struct InvDev {
     int n, m, T, backlog, lt_max, obs_dim, sumL;
     int L[MAXN], roff[MAXN];
+    uint32_t Lmagic[MAXN], Lm_magic;  // ceil(2^32 / d): t % d without a division (mod_small)
     long long c[MAXN], I0[MAXN];
     double up[MAXN + 1], uc[MAXN + 1], kc[MAXN + 1], hc[MAXN + 1];
     const double* disc;  // [T] alpha**t, computed on the host with libm pow like CPython's float.__pow__
@@ -197,9 +198,57 @@ __global__ void inv_reset_kernel(const __grid_constant__ InvDev P, int64_t N, in
 }
 
 // ---- step ------------------------------------------------------------------------------------------------------
+// t % d for 0 <= t < 2^20 and 1 <= d <= 64 without a division: q = mulhi(t, ceil(2^32 / d)) is exact in that range
+#ifndef ORGYM_STEP_MIN_BLOCKS
+#define ORGYM_STEP_MIN_BLOCKS 8
+#endif
+__device__ __forceinline__ int mod_small(int t, int d, uint32_t magic) {
+    return magic ? t - (int)__umulhi((uint32_t)t, magic) * d : 0;  // magic == 0 encodes d == 1
+}
+
+// Shared-memory staging tile of the [env][obs_dim] int64 observation block.  With the compact int32 state the tile
+// is kept in int32 (half the shared memory -> twice the resident CTAs) and widened to int64 on the way out with
+// 16-byte coalesced stores; with the wide state the dense int64 tile leaves through one TMA bulk copy.
+template <typename S>
+__device__ __forceinline__ void obs_tile_store(int64_t* __restrict__ g, const S* tile, int width, int stride, int nvalid,
+                                               bool bulk) {
+    if (sizeof(S) == 8 && bulk) {
+        fence_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_s2g(g, tile, (uint32_t)(nvalid * width * 8));
+            bulk_commit();
+            bulk_wait_read0();
+        }
+        return;
+    }
+    __syncthreads();
+    const int total = nvalid * width;
+    if (stride == width) {  // dense tile: element i of the block is tile[i]
+        if (sizeof(S) == 4) {
+            const int pairs = total >> 1;
+            for (int i = threadIdx.x; i < pairs; i += ORGYM_TILE) {
+                int2 v = reinterpret_cast<const int2*>(tile)[i];
+                longlong2 w = make_longlong2((long long)v.x, (long long)v.y);
+                __stcs(reinterpret_cast<longlong2*>(g) + i, w);
+            }
+            if ((total & 1) && threadIdx.x == 0) g[total - 1] = (int64_t)tile[total - 1];
+        } else {
+            for (int i = threadIdx.x; i < total; i += ORGYM_TILE) g[i] = (int64_t)tile[i];
+        }
+    } else {
+        for (int i = threadIdx.x; i < total; i += ORGYM_TILE) {
+            int r = i / width, c = i - r * width;
+            g[i] = (int64_t)tile[r * stride + c];
+        }
+    }
+}
+
 template <int NS, bool EXACT, typename S>
-__global__ void __launch_bounds__(ORGYM_TILE) inv_step_kernel(const __grid_constant__ InvDev P, const InvStepArgs A) {
+__global__ void __launch_bounds__(ORGYM_TILE, (NS <= 4 && sizeof(S) == 4) ? ORGYM_STEP_MIN_BLOCKS : 1)
+    inv_step_kernel(const __grid_constant__ InvDev P, const InvStepArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int CH = NS <= 3 ? 8 : (NS <= 6 ? 4 : 2);  // window periods loaded per batch (CH*NS loads in flight)
     const int n = EXACT ? NS : P.n, m = n + 1;
     const int tid = threadIdx.x;
     const int64_t e0 = (int64_t)blockIdx.x * ORGYM_TILE, e = e0 + tid;
@@ -210,9 +259,9 @@ __global__ void __launch_bounds__(ORGYM_TILE) inv_step_kernel(const __grid_const
     const int ostride = obs_dense ? P.obs_dim : P.obs_dim + 1;
     const bool bulk_out = A.use_bulk && full && obs_dense;
     const bool bulk_in = A.use_bulk && full;
-    // shared: obs tile | action tile | mbarrier | alias table
-    int64_t* obs_tile = (int64_t*)smem;
-    size_t off = (size_t)ORGYM_TILE * ostride * 8;
+    // shared: obs tile (S) | action tile (8 B / element) | mbarrier | alias table
+    S* obs_tile = (S*)smem;
+    size_t off = ((size_t)ORGYM_TILE * ostride * sizeof(S) + 15) & ~(size_t)15;
     unsigned char* act_tile = smem + off;
     off += (size_t)ORGYM_TILE * n * 8;
     uint64_t* bar = (uint64_t*)(smem + off);
@@ -241,43 +290,83 @@ __global__ void __launch_bounds__(ORGYM_TILE) inv_step_kernel(const __grid_const
     uint32_t episode = 0;
     uint64_t key = 0;
     bool do_step = valid;
-    if (valid) {
+    S* orow = obs_tile + tid * ostride;
+    if (valid) {  // first round trip: everything that does not depend on the period
         t = st.period[e];
         episode = st.episode[e];
-        key = st.key[e];
-        if (t >= P.T) {  // episode already over
-            do_step = false;
-            if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {
-                inv_reset_env(P, st, e);
-                st.episode[e] = episode + 1;
-                for (int k = 0; k < P.obs_dim; k++) obs_tile[tid * ostride + k] = k < n ? P.I0[k] : 0;
-                A.reward[e] = 0.0;
-                A.terminated[e] = 0;
-                A.truncated[e] = 0;
-            } else {  // reference: IndexError on R[t] (inventory_management.py:267)
-                atomicOr(A.err, ORGYM_ERR_STEP_PAST_END);
-                const int64_t* old = A.obs + e * P.obs_dim;
-                for (int k = 0; k < P.obs_dim; k++) obs_tile[tid * ostride + k] = old[k];
-                A.reward[e] = 0.0;
-                A.terminated[e] = 0;
-                A.truncated[e] = 1;
-            }
-        }
-    }
-    if (do_step) {
+        if (sample) key = st.key[e];
 #pragma unroll
         for (int i = 0; i < NS; i++)
             if (EXACT || i < n) I[i] = st.at(st.oI + i, e);
 #pragma unroll
         for (int j = 0; j <= NS; j++)
             if (EXACT || j <= n) B[j] = st.at(st.oB + j, e);
+        if (t >= P.T) {  // episode already over
+            do_step = false;
+            if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {
+                inv_reset_env(P, st, e);
+                st.episode[e] = episode + 1;
+                for (int k = 0; k < P.obs_dim; k++) orow[k] = k < n ? (S)P.I0[k] : (S)0;
+                A.reward[e] = 0.0;
+                A.terminated[e] = 0;
+                A.truncated[e] = 0;
+            } else {  // reference: IndexError on R[t] (inventory_management.py:267)
+                atomicOr(A.err, ORGYM_ERR_STEP_PAST_END);
+                const int64_t* old = A.obs + e * P.obs_dim;
+                for (int k = 0; k < P.obs_dim; k++) orow[k] = (S)old[k];
+                A.reward[e] = 0.0;
+                A.terminated[e] = 0;
+                A.truncated[e] = 1;
+            }
+        }
     }
-    if (bulk_in)
-        mbar_wait(bar, 0);
+    // second round trip: lead-time ring slots and the action window, all addressed by the period
+    S arr[NS];
+    const int Lm = P.lt_max;
+    const int tn = t + 1;
+    const int k = tn < Lm ? tn : Lm;  // window length at t+1 (:378)
+    if (do_step) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            arr[i] = 0;
+            if ((EXACT || i < n) && P.L[i] > 0)
+                arr[i] = st.at(st.oR + P.roff[i] + mod_small(t, P.L[i], P.Lmagic[i]), e);  // slot holds R[t-L_i]
+        }
+        // observation window (:376-383): requested orders of periods tn-k .. tn-1, oldest first, left aligned.
+        // Period p lives in ring slot p % lt_max; the current period (window position k-1) is filled in below.
+        if (Lm > 0) {
+            int slot = mod_small(tn - k, Lm, P.Lm_magic);
+            for (int q0 = 0; q0 < Lm; q0 += CH) {
+                S v[CH][NS];
+#pragma unroll
+                for (int u = 0; u < CH; u++) {
+                    const int q = q0 + u;
+                    const bool in = q < k - 1;
+                    int sl = slot + q;
+                    sl = sl >= Lm ? sl - Lm : sl;
+#pragma unroll
+                    for (int i = 0; i < NS; i++) {
+                        v[u][i] = 0;
+                        if ((EXACT || i < n) && in) v[u][i] = st.at(st.oA + sl * n + i, e);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < CH; u++) {
+                    const int q = q0 + u;
+                    if (q < Lm && q != k - 1) {
+#pragma unroll
+                        for (int i = 0; i < NS; i++)
+                            if (EXACT || i < n) orow[n + q * n + i] = v[u][i];
+                    }
+                }
+            }
+        }
+    }
+    if (bulk_in) mbar_wait(bar, 0);
     __syncthreads();  // action tile (cooperative path) and alias table visible
 
     if (do_step) {
-        S req[NS], arr[NS], Rf[NS], U[NS + 1];
+        S req[NS], Rf[NS], U[NS + 1];
         bool range_bad = false;
 #pragma unroll
         for (int i = 0; i < NS; i++) {
@@ -296,8 +385,6 @@ __global__ void __launch_bounds__(ORGYM_TILE) inv_step_kernel(const __grid_const
                     a = INT32_GUARD;
                 }
                 req[i] = (S)a;
-                arr[i] = 0;
-                if (P.L[i] > 0) arr[i] = st.at(st.oR + P.roff[i] + (t % P.L[i]), e);  // ring slot holds R[t-L_i]
             }
         }
         long long dl;
@@ -305,13 +392,13 @@ __global__ void __launch_bounds__(ORGYM_TILE) inv_step_kernel(const __grid_const
             dl = A.demand[e];
         else
             dl = sample_fixed(P.dem, tab, key, episode, t, 0u);
-        if (sizeof(S) == 4) {
-            if (dl > INT32_GUARD) { range_bad = true; dl = INT32_GUARD; }
+        if (sizeof(S) == 4 && dl > INT32_GUARD) {
+            range_bad = true;
+            dl = INT32_GUARD;
         }
         S d = (S)dl, s0;
         double profit = inv_period<NS, EXACT, S>(P, req, arr, d, I, B, Rf, s0, U);
         double reward = P.disc[t] * profit;  // :322
-        // ---- write back state
         if (sizeof(S) == 4) {
 #pragma unroll
             for (int i = 0; i < NS; i++)
@@ -321,69 +408,77 @@ __global__ void __launch_bounds__(ORGYM_TILE) inv_step_kernel(const __grid_const
                 if (EXACT || j <= n) range_bad |= (U[j] > INT32_GUARD) | (U[j] < -INT32_GUARD);
             if (range_bad) atomicOr(A.err, ORGYM_ERR_INT32_RANGE);
         }
-        const int tn = t + 1;
         const bool trunc = tn >= P.T;  // :350
         const bool reset_now = trunc && A.autoreset == ORGYM_AUTORESET_SAME_STEP;
-        int64_t* orow = obs_tile + tid * ostride;
-        // observation :354-391: on-hand, then the last min(t', lt_max) requested orders, oldest first, left aligned
-        const int Lm = P.lt_max;
-        const int k = tn < Lm ? tn : Lm;
+        // finish the observation row: on-hand inventory and the current period's requested order
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+            if (EXACT || i < n) {
+                orow[i] = I[i];
+                if (Lm > 0) orow[n + (k - 1) * n + i] = req[i];
+            }
         if (!reset_now) {
+            const int aslot = Lm > 0 ? mod_small(t, Lm, P.Lm_magic) : 0;
 #pragma unroll
             for (int i = 0; i < NS; i++)
                 if (EXACT || i < n) {
                     st.at(st.oI + i, e) = I[i];
-                    orow[i] = (int64_t)I[i];
-                    if (P.L[i] > 0) st.at(st.oR + P.roff[i] + (t % P.L[i]), e) = Rf[i];
-                    if (Lm > 0) st.at(st.oA + (t % Lm) * n + i, e) = req[i];
+                    if (P.L[i] > 0) st.at(st.oR + P.roff[i] + mod_small(t, P.L[i], P.Lmagic[i]), e) = Rf[i];
+                    if (Lm > 0) st.at(st.oA + aslot * n + i, e) = req[i];
                 }
 #pragma unroll
             for (int j = 0; j <= NS; j++)
                 if (EXACT || j <= n) st.at(st.oB + j, e) = B[j];
             st.period[e] = tn;
-            for (int q = 0; q < Lm; q++) {
-                int p = tn - k + q;  // period whose action sits at window position q
-                bool in = q < k;
-                int slot = in ? (p % Lm) : 0;
-                for (int i = 0; i < n; i++) {
-                    int64_t v = 0;
-                    if (in) v = (p == t) ? (int64_t)req[i] : (int64_t)st.at(st.oA + slot * n + i, e);
-                    orow[n + q * n + i] = v;
-                }
-            }
         } else {
             // SAME_STEP autoreset: the terminal observation goes to final_obs, the env restarts immediately
             if (A.final_obs) {
                 int64_t* fo = A.final_obs + e * P.obs_dim;
-                for (int i = 0; i < n; i++) fo[i] = (int64_t)I[i];
-                for (int q = 0; q < Lm; q++) {
-                    int p = tn - k + q;
-                    bool in = q < k;
-                    int slot = in ? (p % Lm) : 0;
-                    for (int i = 0; i < n; i++) {
-                        int64_t v = 0;
-                        if (in) v = (p == t) ? (int64_t)req[i] : (int64_t)st.at(st.oA + slot * n + i, e);
-                        fo[n + q * n + i] = v;
-                    }
-                }
+                for (int q = 0; q < P.obs_dim; q++) fo[q] = (int64_t)orow[q];
             }
             inv_reset_env(P, st, e);
             st.episode[e] = episode + 1;
-            for (int q = 0; q < P.obs_dim; q++) orow[q] = q < n ? P.I0[q] : 0;
+            for (int q = 0; q < P.obs_dim; q++) orow[q] = q < n ? (S)P.I0[q] : (S)0;
         }
         A.reward[e] = reward;
         A.terminated[e] = 0;  // :349
         A.truncated[e] = trunc ? 1 : 0;
         if (A.info_demand) A.info_demand[e] = (int64_t)(d > 0 ? d : 0);
         if (A.info_profit) A.info_profit[e] = profit;
-        if (A.info_sales) {
-            A.info_sales[e * m] = (int64_t)s0;
-            for (int i = 0; i < n; i++) A.info_sales[e * m + 1 + i] = (int64_t)Rf[i];
+        if (A.info_sales || A.info_unf) {
+            // each env owns m consecutive int64: pairs go out as 16-byte stores when the row is 16-byte aligned
+            long long sv[NS + 1];
+            sv[0] = (long long)s0;
+#pragma unroll
+            for (int i = 0; i < NS; i++) sv[i + 1] = (EXACT || i < n) ? (long long)Rf[i] : 0;
+            if (A.info_sales) {
+                int64_t* row = A.info_sales + e * m;
+                if (EXACT && (((NS + 1) & 1) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < NS + 1; j += 2)
+                        *reinterpret_cast<longlong2*>(row + j) = make_longlong2(sv[j], sv[j + 1 <= NS ? j + 1 : NS]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j <= NS; j++)
+                        if (EXACT || j <= n) row[j] = sv[j];
+                }
+            }
+            if (A.info_unf) {
+                int64_t* row = A.info_unf + e * m;
+                if (EXACT && (((NS + 1) & 1) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < NS + 1; j += 2)
+                        *reinterpret_cast<longlong2*>(row + j) =
+                            make_longlong2((long long)U[j], (long long)U[j + 1 <= NS ? j + 1 : NS]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j <= NS; j++)
+                        if (EXACT || j <= n) row[j] = (long long)U[j];
+                }
+            }
         }
-        if (A.info_unf)
-            for (int j = 0; j < m; j++) A.info_unf[e * m + j] = (int64_t)U[j];
     }
-    tile_store<int64_t>(A.obs + (size_t)e0 * P.obs_dim, obs_tile, P.obs_dim, ostride, nvalid, bulk_out);
+    obs_tile_store<S>(A.obs + (size_t)e0 * P.obs_dim, obs_tile, P.obs_dim, ostride, nvalid, bulk_out);
 }
 
 // ---- export -----------------------------------------------------------------------------------------------------
@@ -685,6 +780,12 @@ extern "C" int orgym_invmgmt_create(const orgym_invmgmt_config_t* cfg, int64_t n
         rc = ORGYM_E_INVALID;
     }
     P.obs_dim = n * (P.lt_max + 1);
+    for (int i = 0; i < n; i++) P.Lmagic[i] = P.L[i] > 1 ? (uint32_t)((0x100000000ULL + P.L[i] - 1) / P.L[i]) : 0u;
+    P.Lm_magic = P.lt_max > 1 ? (uint32_t)((0x100000000ULL + P.lt_max - 1) / P.lt_max) : 0u;
+    if (rc == ORGYM_OK && cfg->periods > (1 << 20)) {
+        orgym_set_error("periods above 2^20 are not supported");
+        rc = ORGYM_E_UNSUPPORTED;
+    }
     H->wide = cfg->wide_state ? 1 : 0;
     if (rc == ORGYM_OK && !H->wide && cmax > (INT32_GUARD >> 8)) H->wide = 1;  // compact int32 state cannot hold it
     if (rc == ORGYM_OK) rc = orgym_handle_base_init(&H->base, FAM_INVMGMT, device, num_envs);
@@ -811,7 +912,7 @@ extern "C" int orgym_invmgmt_step(orgym_handle_t h, void* state_dev, const void*
     A.err = H->base.err_dev;
     A.use_bulk = use_bulk() && ((uintptr_t)actions_dev % 16 == 0) && ((uintptr_t)obs_dev % 16 == 0);
     int ostride = (P.obs_dim & 1) ? P.obs_dim : P.obs_dim + 1;
-    size_t smem = (size_t)ORGYM_TILE * ostride * 8 + (size_t)ORGYM_TILE * P.n * 8 + 16 +
+    size_t smem = (((size_t)ORGYM_TILE * ostride * (H->wide ? 8 : 4) + 15) & ~(size_t)15) + (size_t)ORGYM_TILE * P.n * 8 + 16 +
                   (P.dem.kind == ORGYM_DIST_USER ? 0 : (size_t(8) << P.dem.log2k));
     if (smem > 220 * 1024) {
         orgym_set_error("observation tile of %zu bytes does not fit in shared memory (obs_dim=%d)", smem, P.obs_dim);

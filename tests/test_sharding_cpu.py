@@ -1,0 +1,60 @@
+"""CPU suite: the N>1 host logic (shard ranges + statistics allreduce) under gloo with world_size 2."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import or_gym_inventory_b200 as pkg
+
+
+def test_shard_ranges_tile_the_id_space():
+    for n in (1, 7, 1 << 20, (1 << 24) + 3):
+        for w in (1, 2, 3, 8):
+            spans = [pkg.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+            for (o0, c0), (o1, _) in zip(spans, spans[1:]):
+                assert o0 + c0 == o1
+    with pytest.raises(ValueError):
+        pkg.shard_range(10, 2, 2)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    off, cnt = pkg.shard_range(1001, rank, world)
+    ids = np.arange(off, off + cnt, dtype=np.float64)
+    ret = np.sin(ids) * 100.0                       # stand-in per-episode returns of this shard
+    s = torch.tensor([cnt, ret.sum(), (ret * ret).sum(), 3.0 * cnt, 4.0 * cnt, 1.0 * cnt, 60.0 * cnt, 0.0],
+                     dtype=torch.float64)
+    pkg.allreduce_summary(s)
+    q.put((rank, s.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_summary_allreduce_gloo_world2():
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ids = np.arange(1001, dtype=np.float64)
+    ret = np.sin(ids) * 100.0
+    for r in range(2):
+        s = res[r]
+        assert s[0] == 1001 and np.isclose(s[1], ret.sum(), rtol=1e-12, atol=1e-9) and np.isclose(s[2], (ret * ret).sum())
+    d = pkg.describe_summary(res[0], periods=30)
+    assert d["episodes"] == 1001 and np.isclose(d["TotalReward_mean"], ret.mean(), atol=1e-9)
+    assert np.isclose(d["TotalReward_std"], ret.std(), rtol=1e-9) and d["AvgServiceLevel"] == 0.75
+    assert d["AvgEndingInv_mean"] == 2.0
