@@ -100,7 +100,7 @@ int orgym_dist_pmf(const orgym_dist_t* d, std::vector<double>* pmf, int64_t* bas
 
 // counter word 2 = stream id
 enum {
-    STREAM_DEMAND = 0,    // c0 = period >> 1 (two alias samples per block), c3 = demand source (retail link) index
+    STREAM_DEMAND = 0,    // c0 = period >> 2 (four alias samples per block), c3 = demand source (retail link) index
     STREAM_ACTION = 1,    // random-action policy: c0 = period, c3 = stage group (4 stages per block)
     STREAM_PARAMS = 2,    // newsvendor reset uniforms: c0 = 0..2
     STREAM_POISSON_MU = 3 // per-env-mean Poisson: c0 = period, c3 = attempt
@@ -137,12 +137,19 @@ __host__ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
     return (double)(x >> 11) * (1.0 / 9007199254740992.0);
 }
 
-// one alias-table draw from two random words; the table may live in shared or global memory
-__device__ __forceinline__ int32_t alias_draw(const uint2* __restrict__ table, int log2k, int base, uint32_t u1,
-                                               uint32_t u2) {
-    uint32_t idx = log2k ? (u1 >> (32 - log2k)) : 0u;
+// one alias-table draw from ONE 32-bit random word: the top log2k bits pick the bucket, the remaining bits
+// (left-aligned to 32) are compared with the bucket's acceptance threshold.  Probabilities are therefore resolved
+// to 2^-(32-log2k) per bucket (<= 2.4e-10 absolute for the 128-bucket Poisson(20) table) -- far below what any
+// goodness-of-fit test on <= 1e12 samples can see -- and one Philox block feeds four periods.
+__device__ __forceinline__ int32_t alias_draw(const uint2* __restrict__ table, int log2k, int base, uint32_t w) {
+    uint32_t idx = log2k ? (w >> (32 - log2k)) : 0u;
+    uint32_t frac = w << log2k;
     uint2 e = table[idx];
-    return base + (int32_t)(u2 < e.x ? idx : e.y);
+    return base + (int32_t)(frac < e.x ? idx : e.y);
+}
+
+__device__ __forceinline__ uint32_t pick_word(const uint4& w, int i) {
+    return i == 0 ? w.x : (i == 1 ? w.y : (i == 2 ? w.z : w.w));
 }
 
 // demand for (key, episode, period t, source r) from a fixed distribution
@@ -153,18 +160,58 @@ __device__ __forceinline__ int64_t sample_fixed(const AliasDev& A, const uint2* 
         if (A.user_clamp) idx = t < A.user_D_len - 1 ? t : A.user_D_len - 1;
         return (idx >= 0 && idx < A.user_D_len) ? A.user_D[idx] : 0;
     }
-    uint4 w = philox_block(key, (uint32_t)t >> 1, episode, STREAM_DEMAND, source);
-    return (t & 1) ? alias_draw(table, A.log2k, A.base, w.z, w.w) : alias_draw(table, A.log2k, A.base, w.x, w.y);
+    uint4 w = philox_block(key, (uint32_t)t >> 2, episode, STREAM_DEMAND, source);
+    return alias_draw(table, A.log2k, A.base, pick_word(w, t & 3));
+}
+
+// log(k!) for integer-valued k >= 0: exact table below 16, Stirling series above (error < 2e-12)
+__device__ __forceinline__ double log_factorial(double k) {
+    if (k < 16.0) {
+        const double tab[16] = {0.0, 0.0, 0.69314718055994530942, 1.79175946922805500081, 3.17805383034794561965,
+                                4.78749174278204599425, 6.57925121201010099506, 8.52516136106541430017,
+                                10.60460290274525022842, 12.80182748008146961121, 15.10441257307551529523,
+                                17.50230784587388583929, 19.98721449566188614952, 22.55216385312342288557,
+                                25.19122118273868150009, 27.89927138384089156609};
+        return tab[(int)k];
+    }
+    const double x = k + 1.0, r = 1.0 / x, r2 = r * r;
+    return (x - 0.5) * log(x) - x + 0.91893853320467274178 + r * (1.0 / 12.0 - r2 * (1.0 / 360.0 - r2 * (1.0 / 1260.0)));
 }
 
 // Poisson with a per-call mean (Newsvendor: mu differs per env).  mu >= 10: Hoermann's PTRS transformed
-// rejection in float64 (the algorithm numpy uses); mu < 10: CDF inversion by sequential search from one
-// 53-bit uniform.  Keyed by (key, episode, t); rejection attempts advance counter word 3.
-__device__ __forceinline__ int64_t poisson_mu(double mu, uint64_t key, uint32_t episode, int t) {
+// rejection in float64 (the algorithm numpy uses, with the acceptance test folded into a single logarithm and a
+// Stirling log-factorial); mu < 10: CDF inversion by sequential search from one 53-bit uniform.
+// Keyed by (key, episode, t); rejection attempts advance counter word 3.
+struct PoissonMu {
+    double mu, b, a, vr, e_or_loglam, inv_alpha;  // e_or_loglam: exp(-mu) for mu < 10, log(mu) otherwise
+};
+// full = false: only what the squeeze (fast acceptance) needs; the rest is computed on demand in the slow path
+template <bool FULL>
+__device__ __forceinline__ PoissonMu poisson_setup(double mu) {
+    PoissonMu c;
+    c.mu = mu;
+    c.b = c.a = c.vr = c.e_or_loglam = c.inv_alpha = 0.0;
+    if (!(mu > 0.0)) return c;
+    if (mu < 10.0) {
+        c.e_or_loglam = exp(-mu);
+        return c;
+    }
+    c.b = 0.931 + 2.53 * sqrt(mu);
+    c.a = -0.059 + 0.02483 * c.b;
+    c.vr = 0.9277 - 3.6224 / (c.b - 2.0);
+    if (FULL) {
+        c.e_or_loglam = log(mu);
+        c.inv_alpha = 1.1239 + 1.1328 / (c.b - 3.4);
+    }
+    return c;
+}
+template <bool FULL>
+__device__ __forceinline__ int64_t poisson_draw(const PoissonMu& c, uint64_t key, uint32_t episode, int t) {
+    const double mu = c.mu;
     if (!(mu > 0.0)) return 0;
     if (mu < 10.0) {
         uint4 w = philox_block(key, (uint32_t)t, episode, STREAM_POISSON_MU, 0);
-        double u = u53(w.x, w.y), p = exp(-mu), s = p;
+        double u = u53(w.x, w.y), p = c.e_or_loglam, s = p;
         int64_t x = 0;
         while (u > s && x < 200) {
             x += 1;
@@ -173,18 +220,21 @@ __device__ __forceinline__ int64_t poisson_mu(double mu, uint64_t key, uint32_t 
         }
         return x;
     }
-    double slam = sqrt(mu), loglam = log(mu), b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
-    double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
     for (uint32_t attempt = 0;; attempt++) {
         uint4 w = philox_block(key, (uint32_t)t, episode, STREAM_POISSON_MU, attempt);
         double U = u53(w.x, w.y) - 0.5, V = u53(w.z, w.w), us = 0.5 - fabs(U);
-        double kf = floor((2.0 * a / us + b) * U + mu + 0.43);
-        if (us >= 0.07 && V <= vr) return (int64_t)kf;
+        double kf = floor((2.0 * c.a / us + c.b) * U + mu + 0.43);
+        if (us >= 0.07 && V <= c.vr) return (int64_t)kf;  // squeeze: ~86 % of the draws end here
         if (kf < 0.0 || (us < 0.013 && V > us)) continue;
-        if ((log(V) + log(invalpha) - log(a / (us * us) + b)) <= (-mu + kf * loglam - lgamma(kf + 1.0)))
-            return (int64_t)kf;
+        const double loglam = FULL ? c.e_or_loglam : log(mu);
+        const double inv_alpha = FULL ? c.inv_alpha : 1.1239 + 1.1328 / (c.b - 3.4);
+        if (log(V * inv_alpha / (c.a / (us * us) + c.b)) <= (-mu + kf * loglam - log_factorial(kf))) return (int64_t)kf;
         if (attempt > 1000u) return (int64_t)kf;  // unreachable in practice; bounds the loop
     }
+}
+__device__ __forceinline__ int64_t poisson_mu(double mu, uint64_t key, uint32_t episode, int t) {
+    PoissonMu c = poisson_setup<false>(mu);
+    return poisson_draw<false>(c, key, episode, t);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -502,6 +502,9 @@ struct InvRolloutArgs {
     uint32_t episode;
     int policy;
     double target[MAXN];  // base-stock levels (L_i+1)*mu*sf as float64
+    long long target_int[MAXN];
+    int target_is_int;    // every level is an integer below 2^30: the policy is evaluated in integers (same result)
+    int rroff[MAXN], rslots;  // rollout ring layout: stage i owns max(L_i, 1) slots starting at rroff[i]
     const int64_t* actions;
     int64_t a_se, a_st;
     const int64_t* demand;
@@ -525,13 +528,15 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
     const int64_t e = (int64_t)blockIdx.x * ROLL_THREADS + tid;
     const bool valid = e < A.N;
     const bool need_aring = A.policy == ORGYM_POLICY_BASE_STOCK;
-    // shared: alias table | R rings [sumL][threads] | request rings [sumL][threads] (base-stock only)
+    // shared: alias table | R rings [rslots][threads] | request rings [rslots][threads] (base-stock only).
+    // Every stage owns max(L_i, 1) ring slots so that the ring traffic below is branch-free (a stage with L_i = 0
+    // reads and writes a dummy slot whose value is never used).
     uint2* tab = (uint2*)smem;
     const int K = (P.dem.kind == ORGYM_DIST_USER) ? 0 : (1 << P.dem.log2k);
     S* rring = (S*)(smem + (size_t)K * 8);
-    S* aring = rring + (size_t)P.sumL * ROLL_THREADS;
+    S* aring = rring + (size_t)A.rslots * ROLL_THREADS;
     for (int i = tid; i < K; i += ROLL_THREADS) tab[i] = P.dem.table[i];
-    for (int k = 0; k < P.sumL; k++) {
+    for (int k = 0; k < A.rslots; k++) {
         rring[k * ROLL_THREADS + tid] = 0;
         if (need_aring) aring[k * ROLL_THREADS + tid] = 0;
     }
@@ -539,12 +544,14 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
 
     const uint64_t key = A.seed + (uint64_t)(A.env_offset + e);
     S I[NS], B[NS + 1], psum[NS];
-    int rpos[NS];
+    int rbase[NS], rpos[NS], rlen[NS];  // ring base / position / length in elements of the [slot][thread] layout
 #pragma unroll
     for (int i = 0; i < NS; i++) {
         I[i] = (EXACT || i < n) ? (S)P.I0[i] : (S)0;
         psum[i] = 0;
+        rbase[i] = A.rroff[i] * ROLL_THREADS + tid;
         rpos[i] = 0;
+        rlen[i] = (P.L[i] > 0 ? P.L[i] : 1) * ROLL_THREADS;
     }
 #pragma unroll
     for (int j = 0; j <= NS; j++) B[j] = 0;
@@ -557,16 +564,28 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
         // ---- policy ---------------------------------------------------------------------------------------
         if (A.policy == ORGYM_POLICY_BASE_STOCK) {
             // benchmark_InvManagementBacklogEnv.py:152-198: position = on-hand + requested orders of the last L_i
-            // periods; q = clip(max(0, target - position), 0, c) in float64, truncated to int64
+            // periods; q = clip(max(0, target - position), 0, c) in float64, truncated to int64.  With an
+            // integer-valued target the float64 expression is exact, so it is evaluated in integers.
+            if (A.target_is_int) {
 #pragma unroll
-            for (int i = 0; i < NS; i++)
-                if (EXACT || i < n) {
-                    double q = A.target[i] - (double)(I[i] + psum[i]);
-                    q = q > 0.0 ? q : 0.0;
-                    double cap = (double)P.c[i];
-                    q = q < cap ? q : cap;
-                    req[i] = (S)(long long)q;
-                }
+                for (int i = 0; i < NS; i++)
+                    if (EXACT || i < n) {
+                        long long q = A.target_int[i] - (long long)(I[i] + psum[i]);
+                        q = q > 0 ? q : 0;
+                        q = q < P.c[i] ? q : P.c[i];
+                        req[i] = (S)q;
+                    }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NS; i++)
+                    if (EXACT || i < n) {
+                        double q = A.target[i] - (double)(I[i] + psum[i]);
+                        q = q > 0.0 ? q : 0.0;
+                        double cap = (double)P.c[i];
+                        q = q < cap ? q : cap;
+                        req[i] = (S)(long long)q;
+                    }
+            }
         } else if (A.policy == ORGYM_POLICY_RANDOM) {
             uint4 a4 = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -585,24 +604,19 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
                     req[i] = (S)a;
                 }
         }
-        // ---- lead-time rings --------------------------------------------------------------------------------
+        // ---- lead-time rings: slot rpos holds R[t - L_i] (zero before t = L_i) ----------------------------------
 #pragma unroll
         for (int i = 0; i < NS; i++)
-            if (EXACT || i < n) {
-                arr[i] = 0;
-                if (P.L[i] > 0) arr[i] = rring[(P.roff[i] + rpos[i]) * ROLL_THREADS + tid];
-            }
-        // ---- demand -----------------------------------------------------------------------------------------
+            if (EXACT || i < n) arr[i] = rring[rbase[i] + rpos[i]];
+        // ---- demand: one Philox block serves four periods ---------------------------------------------------------
         long long dl;
         if (A.demand)
             dl = valid ? A.demand[e * A.d_se + (int64_t)t * A.d_st] : 0;
         else if (P.dem.kind == ORGYM_DIST_USER)
             dl = t < P.dem.user_D_len ? P.dem.user_D[t] : 0;
         else {
-            // one Philox block serves two periods: (x,y) at even t, (z,w) at odd t
-            if ((t & 1) == 0) w = philox_block(key, (uint32_t)t >> 1, A.episode, STREAM_DEMAND, 0u);
-            dl = (t & 1) ? alias_draw(tab, P.dem.log2k, P.dem.base, w.z, w.w)
-                         : alias_draw(tab, P.dem.log2k, P.dem.base, w.x, w.y);
+            if ((t & 3) == 0) w = philox_block(key, (uint32_t)t >> 2, A.episode, STREAM_DEMAND, 0u);
+            dl = alias_draw(tab, P.dem.log2k, P.dem.base, pick_word(w, t & 3));
         }
         S s0;
         double profit = inv_period<NS, EXACT, S>(P, req, arr, (S)dl, I, B, Rf, s0, U);
@@ -615,19 +629,19 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < NS; i++)
             if (EXACT || i < n) s_inv += I[i] > 0 ? (long long)I[i] : 0;
-        // ---- ring updates -----------------------------------------------------------------------------------
+        // ---- ring updates (branch-free) ------------------------------------------------------------------------
 #pragma unroll
         for (int i = 0; i < NS; i++)
             if (EXACT || i < n) {
-                if (P.L[i] > 0) {
-                    int slot = (P.roff[i] + rpos[i]) * ROLL_THREADS + tid;
-                    rring[slot] = Rf[i];
-                    if (need_aring) {
-                        psum[i] += req[i] - aring[slot];
-                        aring[slot] = req[i];
-                    }
-                    rpos[i] = rpos[i] + 1 == P.L[i] ? 0 : rpos[i] + 1;
+                const int slot = rbase[i] + rpos[i];
+                rring[slot] = Rf[i];
+                if (need_aring) {
+                    S old = aring[slot];
+                    aring[slot] = req[i];
+                    psum[i] = P.L[i] > 0 ? psum[i] + req[i] - old : (S)0;
                 }
+                const int np1 = rpos[i] + ROLL_THREADS;
+                rpos[i] = np1 == rlen[i] ? 0 : np1;
             }
     }
     // ---- per-episode outputs --------------------------------------------------------------------------------------
@@ -964,8 +978,18 @@ extern "C" int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t en
     A.seed = seed;
     A.episode = episode;
     A.policy = in->policy;
-    if (in->policy == ORGYM_POLICY_BASE_STOCK)
-        for (int i = 0; i < P.n; i++) A.target[i] = ((double)(P.L[i] + 1) * in->param[1]) * in->param[0];
+    if (in->policy == ORGYM_POLICY_BASE_STOCK) {
+        A.target_is_int = 1;
+        for (int i = 0; i < P.n; i++) {
+            A.target[i] = ((double)(P.L[i] + 1) * in->param[1]) * in->param[0];  // (lead_times + 1) * mu * sf (:186)
+            if (!(A.target[i] == std::floor(A.target[i]) && std::fabs(A.target[i]) < 1073741824.0)) A.target_is_int = 0;
+            A.target_int[i] = A.target_is_int ? (long long)A.target[i] : 0;
+        }
+    }
+    for (int i = 0; i < P.n; i++) {
+        A.rroff[i] = A.rslots;
+        A.rslots += P.L[i] > 0 ? P.L[i] : 1;
+    }
     A.actions = in->actions_dev;
     A.a_se = in->act_stride_env;
     A.a_st = in->act_stride_t;
@@ -980,7 +1004,7 @@ extern "C" int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t en
     A.partials = out->summary_dev ? H->partials : nullptr;
     // pre-staged actions may be arbitrary int64 -> exact wide arithmetic; on-device policies stay inside [0, c]
     const bool wide = H->wide || in->policy == ORGYM_POLICY_ACTIONS;
-    size_t ring = (size_t)P.sumL * ROLL_THREADS * (wide ? 8 : 4);
+    size_t ring = (size_t)A.rslots * ROLL_THREADS * (wide ? 8 : 4);
     size_t smem = (P.dem.kind == ORGYM_DIST_USER ? 0 : (size_t(8) << P.dem.log2k)) +
                   ring * (in->policy == ORGYM_POLICY_BASE_STOCK ? 2 : 1);
     if (smem > 220 * 1024) {

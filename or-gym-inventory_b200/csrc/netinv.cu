@@ -26,6 +26,7 @@ struct NetDev {
     uint8_t is_factory[NJ], is_retail[NJ];
     int16_t sup[NE], pur[NE], L[NE];
     int32_t roff[NE];
+    uint32_t Lmagic[NE];  // ceil(2^32 / L): t % L by multiply-high (0 encodes L <= 1)
     double p[NE], g[NE];
     int16_t rt_node[NM];
     double rt_p[NM], rt_b[NM];
@@ -69,22 +70,39 @@ static int64_t net_state_bytes(const NetDev& P, int64_t npad) {
     return npad * (8 + 8 * (int64_t)(P.J + P.E + P.M + P.sumL) + 8);
 }
 
+// t % d for 0 <= t < 2^20, 1 <= d <= 64 (exact, see invmgmt.cu)
+__device__ __forceinline__ int net_mod(int t, int d, uint32_t magic) {
+    return magic ? t - (int)__umulhi((uint32_t)t, magic) * d : 0;
+}
+
 // observation (:334-413): [U (M), X (J), per link with L>0: R[t-L..t-1] zero-padded on the left] as float32.
 // ring slot s of a link holds the order of the latest period p with p % L == s (0 before any), so the window
-// element q (oldest first) of the observation at period t is ring[(t + q) % L].
-__device__ __forceinline__ void net_write_obs(const NetDev& P, const double* sU, const double* sX, int nthr, int tid,
+// element q (oldest first) of the observation at period t is ring[(t + q) % L].  Ring loads are issued in batches
+// of 8 before they are converted and stored, so that their latencies overlap.
+template <int NTHR>
+__device__ __forceinline__ void net_write_obs(const NetDev& P, const double* sU, const double* sX, int tid,
                                               const double* ring, int64_t npad, int64_t e, int t, float* o) {
     int k = 0;
-    for (int r = 0; r < P.M; r++) o[k++] = (float)sU[r * nthr + tid];
-    for (int j = 0; j < P.J; j++) o[k++] = (float)sX[j * nthr + tid];
+    for (int r = 0; r < P.M; r++) o[k++] = (float)sU[r * NTHR + tid];
+    for (int j = 0; j < P.J; j++) o[k++] = (float)sX[j * NTHR + tid];
     for (int i = 0; i < P.E; i++) {
-        int L = P.L[i];
+        const int L = P.L[i];
         if (L == 0) continue;  // :353
-        int s = t % L;
-        for (int q = 0; q < L; q++) {
-            o[k++] = (float)ring[(size_t)(P.roff[i] + s) * npad + e];
-            s = s + 1 == L ? 0 : s + 1;
+        int s = net_mod(t, L, P.Lmagic[i]);
+        const double* base = ring + (size_t)P.roff[i] * npad + e;
+        for (int q0 = 0; q0 < L; q0 += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                int sl = s + q0 + u;
+                sl = sl >= L ? sl - L : sl;
+                v[u] = (q0 + u < L) ? base[(size_t)sl * npad] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (q0 + u < L) o[k + q0 + u] = (float)v[u];
         }
+        k += L;
     }
 }
 
@@ -135,6 +153,7 @@ struct NetSimArgs {
     double* info_profit_total;
     float* final_obs;
     uint32_t* err;
+    int use_tile;  // STEP: stage the observation block in shared memory and store it coalesced
     // ROLLOUT outputs
     double* ep_return;
     double* stats;
@@ -145,19 +164,23 @@ struct NetSimArgs {
     double* partials;
 };
 
-__global__ void net_sim_kernel(const __grid_constant__ NetDev P, const __grid_constant__ NetSimArgs A) {
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR) net_sim_kernel(const __grid_constant__ NetDev P,
+                                                       const __grid_constant__ NetSimArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int nthr = blockDim.x, tid = threadIdx.x;
-    const int64_t e = (int64_t)blockIdx.x * nthr + tid;
+    const int tid = threadIdx.x;
+    const int64_t e0 = (int64_t)blockIdx.x * NTHR, e = e0 + tid;
     const bool valid = e < A.N;
     const int64_t ec = valid ? e : 0;  // clamp so that idle lanes stay in bounds
     const int J = P.J, E = P.E, M = P.M;
     double* sX = (double*)smem;      // [J]
-    double* sC = sX + J * nthr;      // [J] inventory consumed this period
-    double* sR = sC + J * nthr;      // [E] orders fulfilled this period
-    double* sY = sR + E * nthr;      // [E]
-    double* sU = sY + E * nthr;      // [M]
-    double* sS = sU + M * nthr;      // [M] retail sales this period
+    double* sC = sX + J * NTHR;      // [J] inventory consumed this period
+    double* sR = sC + J * NTHR;      // [E] orders fulfilled this period
+    double* sY = sR + E * NTHR;      // [E]
+    double* sU = sY + E * NTHR;      // [M]
+    double* sS = sU + M * NTHR;      // [M] retail sales this period
+    float* otile = (float*)(sS + M * NTHR);  // STEP mode, when it fits: [NTHR][obs_stride] staging tile
+    const int ostride = P.obs_dim | 1;       // odd row stride: conflict-free row writes
     NetState st(A.state, A.npad, P);
     double* ring = st.ring;
     const int64_t np_ = A.npad;
@@ -166,14 +189,15 @@ __global__ void net_sim_kernel(const __grid_constant__ NetDev P, const __grid_co
     uint32_t episode;
     int t0, t1;
     bool do_step = valid;
+    float* orow = A.use_tile ? otile + tid * ostride : (A.obs ? A.obs + ec * P.obs_dim : nullptr);
     if (A.rollout) {
         key = A.seed + (uint64_t)(A.env_offset + e);
         episode = A.episode;
         t0 = 0;
         t1 = P.T;
-        for (int j = 0; j < J; j++) sX[j * nthr + tid] = P.I0[j];
-        for (int i = 0; i < E; i++) sY[i * nthr + tid] = 0.0;
-        for (int r = 0; r < M; r++) sU[r * nthr + tid] = 0.0;
+        for (int j = 0; j < J; j++) sX[j * NTHR + tid] = P.I0[j];
+        for (int i = 0; i < E; i++) sY[i * NTHR + tid] = 0.0;
+        for (int r = 0; r < M; r++) sU[r * NTHR + tid] = 0.0;
         if (valid)
             for (int k = 0; k < P.sumL; k++) ring[(size_t)k * np_ + e] = 0.0;
     } else {
@@ -186,31 +210,33 @@ __global__ void net_sim_kernel(const __grid_constant__ NetDev P, const __grid_co
             if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {
                 for (int j = 0; j < J; j++) {
                     st.X[(size_t)j * np_ + e] = P.I0[j];
-                    sX[j * nthr + tid] = P.I0[j];
+                    sX[j * NTHR + tid] = P.I0[j];
                 }
                 for (int i = 0; i < E; i++) st.Y[(size_t)i * np_ + e] = 0.0;
                 for (int r = 0; r < M; r++) {
                     st.U[(size_t)r * np_ + e] = 0.0;
-                    sU[r * nthr + tid] = 0.0;
+                    sU[r * NTHR + tid] = 0.0;
                 }
                 for (int k = 0; k < P.sumL; k++) ring[(size_t)k * np_ + e] = 0.0;
                 st.period[e] = 0;
                 st.episode[e] = episode + 1;
-                net_write_obs(P, sU, sX, nthr, tid, ring, np_, e, 0, A.obs + e * P.obs_dim);
+                net_write_obs<NTHR>(P, sU, sX, tid, ring, np_, e, 0, orow);
                 A.reward[e] = 0.0;
                 A.terminated[e] = 0;
                 A.truncated[e] = 0;
             } else {
                 atomicOr(A.err, ORGYM_ERR_STEP_PAST_END);
+                if (A.use_tile)
+                    for (int z = 0; z < P.obs_dim; z++) orow[z] = A.obs[e * P.obs_dim + z];
                 A.reward[e] = 0.0;
                 A.terminated[e] = 0;
                 A.truncated[e] = 1;
             }
         }
         if (do_step) {
-            for (int j = 0; j < J; j++) sX[j * nthr + tid] = st.X[(size_t)j * np_ + e];
-            for (int i = 0; i < E; i++) sY[i * nthr + tid] = st.Y[(size_t)i * np_ + e];
-            for (int r = 0; r < M; r++) sU[r * nthr + tid] = st.U[(size_t)r * np_ + e];
+            for (int j = 0; j < J; j++) sX[j * NTHR + tid] = st.X[(size_t)j * np_ + e];
+            for (int i = 0; i < E; i++) sY[i * NTHR + tid] = st.Y[(size_t)i * np_ + e];
+            for (int r = 0; r < M; r++) sU[r * NTHR + tid] = st.U[(size_t)r * np_ + e];
         }
     }
     double ret = 0.0, s_sales = 0.0, s_dem = 0.0, s_unf = 0.0, s_inv = 0.0, last_reward = 0.0;
@@ -218,50 +244,56 @@ __global__ void net_sim_kernel(const __grid_constant__ NetDev P, const __grid_co
 
     for (int t = t0; t < t1; t++) {
         // ---- 0) place orders: sequential greedy allocation in sorted (supplier, purchaser) order (:448-490)
-        for (int j = 0; j < J; j++) sC[j * nthr + tid] = 0.0;
+        for (int j = 0; j < J; j++) sC[j * NTHR + tid] = 0.0;
         double cons_s = 0.0;
+        const float* arow = A.policy == ORGYM_NET_POLICY_CONSTANT
+                                ? A.actions
+                                : A.actions + ec * A.a_se + (int64_t)(A.rollout ? t : 0) * A.a_st;
         for (int i = 0; i < E; i++) {
-            float a;
-            if (A.policy == ORGYM_NET_POLICY_CONSTANT)
-                a = A.actions[i];
-            else
-                a = A.actions[ec * A.a_se + (int64_t)(A.rollout ? t : 0) * A.a_st + i];
-            double req = rint((double)a);  // Python round(): half to even
-            req = req > 0.0 ? req : 0.0;   // max(0, .)
+            double req = rint((double)arow[i]);  // Python round(): half to even
+            req = req > 0.0 ? req : 0.0;         // max(0, .)
             const int s = P.sup[i];
             double f = 0.0;
             if (s == -1)
                 f = req;  // raw material: unlimited (:453-455)
             else if (s >= 0) {
                 if (i == 0 || P.sup[i - 1] != s) cons_s = 0.0;
-                double avail = sX[s * nthr + tid] - cons_s;  // :459
+                double avail = sX[s * NTHR + tid] - cons_s;  // :459
                 avail = avail > 0.0 ? avail : 0.0;           // :460
                 double oa = avail;
+                const double vs = P.v[s];
                 if (P.is_factory[s]) {  // :464-478
-                    double mp = P.v[s] * avail;
+                    double mp = vs * avail;
                     double lim = mp < P.C[s] ? mp : P.C[s];
                     oa = lim < oa ? lim : oa;
                 }
-                f = oa < req ? oa : req;  // :481
-                cons_s += f / P.v[s];     // :484-485
-                if (i == E - 1 || P.sup[i + 1] != s) sC[s * nthr + tid] = cons_s;
+                f = oa < req ? oa : req;                 // :481
+                cons_s += vs == 1.0 ? f : f / vs;        // :484-485 (x / 1.0 == x)
+                if (i == E - 1 || P.sup[i + 1] != s) sC[s * NTHR + tid] = cons_s;
             }
-            sR[i * nthr + tid] = f;  // R[t] = S[t] = f (:488-490)
+            sR[i * NTHR + tid] = f;  // R[t] = S[t] = f (:488-490)
         }
-        // ---- 1) pipeline inventory (:494-511); arrivals are re-read from the rings in predecessor order below
-        for (int i = 0; i < E; i++) {
-            const int L = P.L[i];
-            double arriving = L == 0 ? sR[i * nthr + tid] : ring[(size_t)(P.roff[i] + t % L) * np_ + ec];
-            sY[i * nthr + tid] = (sY[i * nthr + tid] - arriving) + sR[i * nthr + tid];
-        }
-        // ---- on-hand inventory (:516-528)
+        // ---- on-hand inventory (:516-528): arrivals R[t-L] summed in predecessor (adjacency) order
         for (int j = 0; j < J; j++) {
             double arr = 0.0;
             for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
                 const int i = P.pred_idx[z], L = P.L[i];
-                arr += L == 0 ? sR[i * nthr + tid] : ring[(size_t)(P.roff[i] + t % L) * np_ + ec];
+                arr += L == 0 ? sR[i * NTHR + tid]
+                              : ring[(size_t)(P.roff[i] + net_mod(t, L, P.Lmagic[i])) * np_ + ec];
             }
-            sX[j * nthr + tid] = (sX[j * nthr + tid] + arr) - sC[j * nthr + tid];
+            sX[j * NTHR + tid] = (sX[j * NTHR + tid] + arr) - sC[j * NTHR + tid];
+        }
+        // ---- 1) pipeline inventory (:494-511) and ring commit: slot t % L held R[t-L] and now receives R[t]
+        for (int i = 0; i < E; i++) {
+            const int L = P.L[i];
+            const double rt = sR[i * NTHR + tid];
+            double arriving = rt;
+            if (L > 0) {
+                double* slot = ring + (size_t)(P.roff[i] + net_mod(t, L, P.Lmagic[i])) * np_ + ec;
+                arriving = *slot;
+                if (valid) *slot = rt;
+            }
+            sY[i * NTHR + tid] = (sY[i * NTHR + tid] - arriving) + rt;
         }
         // ---- 2-4) market demand, sales, backlog (:536-566)
         for (int r = 0; r < M; r++) {
@@ -272,15 +304,15 @@ __global__ void net_sim_kernel(const __grid_constant__ NetDev P, const __grid_co
                 d = (double)sample_fixed(P.dem[r], P.dem[r].table, key, episode, t, (uint32_t)r);
             d = d > 0.0 ? d : 0.0;  // max(0, int(round(.))) (:540)
             const int j = P.rt_node[r];
-            double fill = d + sU[r * nthr + tid];
-            double x = sX[j * nthr + tid];
+            double fill = d + sU[r * NTHR + tid];
+            double x = sX[j * NTHR + tid];
             double invr = x > 0.0 ? x : 0.0;
-            double s = invr < fill ? invr : fill;  // min(demand_to_fill, inv) (:548)
-            sS[r * nthr + tid] = s;
-            sX[j * nthr + tid] = x - s;
-            double un = fill - s;
-            sU[r * nthr + tid] = P.backlog ? un : 0.0;  // :560-563
-            s_sales += s;
+            double sl = invr < fill ? invr : fill;  // min(demand_to_fill, inv) (:548)
+            sS[r * NTHR + tid] = sl;
+            sX[j * NTHR + tid] = x - sl;
+            double un = fill - sl;
+            sU[r * NTHR + tid] = P.backlog ? un : 0.0;  // :560-563
+            s_sales += sl;
             s_dem += d;
             s_unf += P.backlog ? un : 0.0;
             if (!A.rollout && A.info_demand && do_step) A.info_demand[e * M + r] = d;
@@ -293,29 +325,32 @@ __global__ void net_sim_kernel(const __grid_constant__ NetDev P, const __grid_co
                 const int l = P.succ_idx[z];
                 double q, pr;
                 if (l < E) {
-                    q = sR[l * nthr + tid];
+                    q = sR[l * NTHR + tid];
                     pr = P.p[l];
                 } else {
-                    q = sS[(l - E) * nthr + tid];
+                    q = sS[(l - E) * NTHR + tid];
                     pr = P.rt_p[l - E];
-                    UP += P.rt_b[l - E] * sU[(l - E) * nthr + tid];  // :608
+                    UP += P.rt_b[l - E] * sU[(l - E) * NTHR + tid];  // :608
                 }
                 SR += pr * q;  // :582
                 sold += q;     // :599
             }
             for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
                 const int i = P.pred_idx[z];
-                PC += P.p[i] * sR[i * nthr + tid];  // :586
-                double y = sY[i * nthr + tid];
+                PC += P.p[i] * sR[i * NTHR + tid];  // :586
+                double y = sY[i * NTHR + tid];
                 HCp += P.g[i] * (y > 0.0 ? y : 0.0);  // :591
             }
-            double x = sX[j * nthr + tid];
+            double x = sX[j * NTHR + tid];
             double xp = x > 0.0 ? x : 0.0;
             double HC = P.h[j] * xp + HCp;  // :590-593
             double OC = 0.0;
-            if (P.is_factory[j]) OC = P.v[j] > 0.0 ? P.o[j] * (sold / P.v[j]) : 0.0;  // :597-601
-            if (!P.is_retail[j]) UP = 0.0;                                            // :605
-            double pj = (((SR - PC) - OC) - HC) - UP;                                 // :611
+            if (P.is_factory[j]) {  // :597-601
+                const double vj = P.v[j];
+                OC = vj > 0.0 ? P.o[j] * (vj == 1.0 ? sold : sold / vj) : 0.0;
+            }
+            if (!P.is_retail[j]) UP = 0.0;             // :605
+            double pj = (((SR - PC) - OC) - HC) - UP;  // :611
             total += pj;
             s_inv += xp;
             if (!A.rollout && A.info_profit && do_step) A.info_profit[e * J + j] = pj;
@@ -326,16 +361,10 @@ __global__ void net_sim_kernel(const __grid_constant__ NetDev P, const __grid_co
         if (!A.rollout && do_step) {
             if (A.info_profit_total) A.info_profit_total[e] = total;
             if (A.info_sales) {
-                for (int i = 0; i < E; i++) A.info_sales[e * (E + M) + i] = sR[i * nthr + tid];
-                for (int r = 0; r < M; r++) A.info_sales[e * (E + M) + E + r] = sS[r * nthr + tid];
+                for (int i = 0; i < E; i++) A.info_sales[e * (E + M) + i] = sR[i * NTHR + tid];
+                for (int r = 0; r < M; r++) A.info_sales[e * (E + M) + E + r] = sS[r * NTHR + tid];
             }
         }
-        // ---- commit the lead-time rings: slot t % L now holds R[t]
-        if (valid)
-            for (int i = 0; i < E; i++) {
-                const int L = P.L[i];
-                if (L > 0) ring[(size_t)(P.roff[i] + t % L) * np_ + e] = sR[i * nthr + tid];
-            }
     }
 
     if (A.rollout) {
@@ -344,9 +373,9 @@ __global__ void net_sim_kernel(const __grid_constant__ NetDev P, const __grid_co
             if (A.stats) {
                 A.stats[e * 4 + 0] = s_sales; A.stats[e * 4 + 1] = s_dem; A.stats[e * 4 + 2] = s_unf; A.stats[e * 4 + 3] = s_inv;
             }
-            if (A.final_X) for (int j = 0; j < J; j++) A.final_X[e * J + j] = sX[j * nthr + tid];
-            if (A.final_Y) for (int i = 0; i < E; i++) A.final_Y[e * E + i] = sY[i * nthr + tid];
-            if (A.final_U) for (int r = 0; r < M; r++) A.final_U[e * M + r] = sU[r * nthr + tid];
+            if (A.final_X) for (int j = 0; j < J; j++) A.final_X[e * J + j] = sX[j * NTHR + tid];
+            if (A.final_Y) for (int i = 0; i < E; i++) A.final_Y[e * E + i] = sY[i * NTHR + tid];
+            if (A.final_U) for (int r = 0; r < M; r++) A.final_U[e * M + r] = sU[r * NTHR + tid];
         }
         if (A.partials) {
             double v[7] = {valid ? 1.0 : 0.0, valid ? ret : 0.0, valid ? ret * ret : 0.0, valid ? s_sales : 0.0,
@@ -363,39 +392,54 @@ __global__ void net_sim_kernel(const __grid_constant__ NetDev P, const __grid_co
             __syncthreads();
             if (tid < 7) {
                 double x = 0.0;
-                for (int wv = 0; wv < nthr / 32; wv++) x += red[wv][tid];
+                for (int wv = 0; wv < NTHR / 32; wv++) x += red[wv][tid];
                 A.partials[(size_t)blockIdx.x * 8 + tid] = x;
             }
         }
-    } else if (do_step) {
+        return;
+    }
+    if (do_step) {
         const int tn = t0 + 1;
         const bool trunc = tn >= P.T;  // :624
         const bool reset_now = trunc && A.autoreset == ORGYM_AUTORESET_SAME_STEP;
         if (!reset_now) {
-            for (int j = 0; j < J; j++) st.X[(size_t)j * np_ + e] = sX[j * nthr + tid];
-            for (int i = 0; i < E; i++) st.Y[(size_t)i * np_ + e] = sY[i * nthr + tid];
-            for (int r = 0; r < M; r++) st.U[(size_t)r * np_ + e] = sU[r * nthr + tid];
+            for (int j = 0; j < J; j++) st.X[(size_t)j * np_ + e] = sX[j * NTHR + tid];
+            for (int i = 0; i < E; i++) st.Y[(size_t)i * np_ + e] = sY[i * NTHR + tid];
+            for (int r = 0; r < M; r++) st.U[(size_t)r * np_ + e] = sU[r * NTHR + tid];
             st.period[e] = tn;
-            net_write_obs(P, sU, sX, nthr, tid, ring, np_, e, tn, A.obs + e * P.obs_dim);
+            net_write_obs<NTHR>(P, sU, sX, tid, ring, np_, e, tn, orow);
         } else {
-            if (A.final_obs) net_write_obs(P, sU, sX, nthr, tid, ring, np_, e, tn, A.final_obs + e * P.obs_dim);
+            if (A.final_obs) net_write_obs<NTHR>(P, sU, sX, tid, ring, np_, e, tn, A.final_obs + e * P.obs_dim);
             for (int j = 0; j < J; j++) {
                 st.X[(size_t)j * np_ + e] = P.I0[j];
-                sX[j * nthr + tid] = P.I0[j];
+                sX[j * NTHR + tid] = P.I0[j];
             }
             for (int i = 0; i < E; i++) st.Y[(size_t)i * np_ + e] = 0.0;
             for (int r = 0; r < M; r++) {
                 st.U[(size_t)r * np_ + e] = 0.0;
-                sU[r * nthr + tid] = 0.0;
+                sU[r * NTHR + tid] = 0.0;
             }
             for (int k = 0; k < P.sumL; k++) ring[(size_t)k * np_ + e] = 0.0;
             st.period[e] = 0;
             st.episode[e] = episode + 1;
-            net_write_obs(P, sU, sX, nthr, tid, ring, np_, e, 0, A.obs + e * P.obs_dim);
+            net_write_obs<NTHR>(P, sU, sX, tid, ring, np_, e, 0, orow);
         }
         A.reward[e] = last_reward;
         A.terminated[e] = 0;
         A.truncated[e] = trunc ? 1 : 0;
+    }
+    if (A.use_tile) {  // coalesced copy-out of the [env][obs_dim] block
+        __syncthreads();
+        const int nvalid = (int)((A.N - e0) < NTHR ? (A.N - e0) : NTHR);
+        const int W = P.obs_dim, total = nvalid * W;
+        float* g = A.obs + (size_t)e0 * W;
+        int r = 0, c = tid;  // element i = tid + k*NTHR  ->  (row, col) tracked incrementally (no division)
+        while (c >= W) { c -= W; r++; }
+        for (int i = tid; i < total; i += NTHR) {
+            __stcs(g + i, otile[r * ostride + c]);
+            c += NTHR;
+            while (c >= W) { c -= W; r++; }
+        }
     }
 }
 
@@ -412,6 +456,16 @@ __global__ void net_export_kernel(const __grid_constant__ NetDev P, int64_t N, i
 }
 
 __global__ void orgym_reduce_partials_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out);
+
+static void net_launch(const NetHandle* H, const NetSimArgs& A, size_t smem, cudaStream_t s) {
+    unsigned grid = (unsigned)((A.N + H->threads - 1) / H->threads);
+    if (H->threads == 128)
+        net_sim_kernel<128><<<grid, 128, smem, s>>>(H->dev, A);
+    else if (H->threads == 64)
+        net_sim_kernel<64><<<grid, 64, smem, s>>>(H->dev, A);
+    else
+        net_sim_kernel<32><<<grid, 32, smem, s>>>(H->dev, A);
+}
 
 // ------------------------------------------------------------------------------------------------
 // host side of the C ABI
@@ -472,6 +526,7 @@ extern "C" int orgym_netinv_create(const orgym_netinv_config_t* c, int64_t num_e
             P.pur[i] = (int16_t)pu;
             P.L[i] = (int16_t)L;
             P.roff[i] = P.sumL;
+            P.Lmagic[i] = L > 1 ? (uint32_t)((0x100000000ULL + L - 1) / L) : 0u;
             P.sumL += L;
             P.p[i] = c->re_p[i];
             P.g[i] = c->re_g[i];
@@ -530,7 +585,10 @@ extern "C" int orgym_netinv_create(const orgym_netinv_config_t* c, int64_t num_e
             H->partials = nullptr;
             if (cudaMalloc(&H->partials, 64 * (size_t)nblocks) != cudaSuccess) FAIL(ORGYM_E_CUDA, "device allocation failed");
             H->allocs.push_back(H->partials);
-            cudaFuncSetAttribute(net_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+            if (P.T > (1 << 20)) FAIL(ORGYM_E_UNSUPPORTED, "num_periods above 2^20 is not supported");
+            cudaFuncSetAttribute(net_sim_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+            cudaFuncSetAttribute(net_sim_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+            cudaFuncSetAttribute(net_sim_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
         }
     }
 done:
@@ -620,7 +678,9 @@ extern "C" int orgym_netinv_step(orgym_handle_t h, void* state_dev, const float*
         A.final_obs = info->final_obs_dev;
     }
     A.err = H->base.err_dev;
-    net_sim_kernel<<<(unsigned)((A.N + H->threads - 1) / H->threads), H->threads, H->smem, (cudaStream_t)stream>>>(P, A);
+    size_t tile = (size_t)H->threads * (P.obs_dim | 1) * 4;
+    A.use_tile = (H->smem + tile <= 200 * 1024) ? 1 : 0;
+    net_launch(H, A, H->smem + (A.use_tile ? tile : 0), (cudaStream_t)stream);
     ORGYM_CUDA(cudaGetLastError());
     return ORGYM_OK;
 }
@@ -673,7 +733,7 @@ extern "C" int orgym_netinv_rollout(orgym_handle_t h, void* scratch_dev, uint64_
     A.final_U = out->final_U_dev;
     A.partials = out->summary_dev ? H->partials : nullptr;
     int nblocks = (int)((A.N + H->threads - 1) / H->threads);
-    net_sim_kernel<<<nblocks, H->threads, H->smem, (cudaStream_t)stream>>>(P, A);
+    net_launch(H, A, H->smem, (cudaStream_t)stream);
     ORGYM_CUDA(cudaGetLastError());
     if (out->summary_dev) {
         orgym_reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(H->partials, nblocks, out->summary_dev);
