@@ -334,6 +334,13 @@ typedef struct {
 int orgym_netinv_rollout(orgym_handle_t h, void* scratch_dev, uint64_t seed, int64_t env_offset, uint32_t episode,
                          const orgym_netinv_rollout_in_t* in, const orgym_netinv_rollout_out_t* out, void* stream);
 
+/* The network kernels are specialised per topology at create time: the flattened graph is emitted as straight-line
+ * CUDA source and compiled for sm_100a with NVRTC (fallback: a generic kernel that reads the topology from the
+ * constant bank; ORGYM_NET_JIT=0 forces it, =2 makes a failed specialisation an error).  This entry point returns
+ * that source for inspection and, with compile_check != 0, runs it through NVRTC; it needs no GPU. */
+int orgym_netinv_codegen(const orgym_netinv_config_t* cfg, int compile_check, char* buf, int64_t buflen,
+                         int64_t* needed);
+
 /* ------------------------------------------------------------------------- *
  * shared helpers
  * ------------------------------------------------------------------------- */

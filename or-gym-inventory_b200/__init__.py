@@ -20,6 +20,7 @@ from .newsvendor import NewsvendorEnv, NewsvendorParams  # noqa: F401
 from .network_management import (NetInvMgmtBacklogEnv, NetInvMgmtLostSalesEnv, NetInvMgmtMasterEnv,  # noqa: F401
                                  NetInvMgmtParams, default_graph, graph_from_spec, synthetic_graph)
 from . import network_management_custom  # noqa: F401
+from .adapters import SB3VecEnvAdapter, rllib_env_creator  # noqa: F401
 from .sampling import sample_demand, sample_poisson_mu  # noqa: F401
 from .sharding import allreduce_summary, describe_summary, shard_range  # noqa: F401
 

@@ -12,63 +12,7 @@
 //   net_sim_kernel     STEP mode: one period (:436-635) + observation;  ROLLOUT mode: fused reset + T periods
 //
 // float64 throughout, evaluated in the reference's operation order (Python sum order = adjacency order).
-#include "common.cuh"
-
-#define NJ ORGYM_NET_MAX_NODES
-#define NE ORGYM_NET_MAX_REORDER
-#define NM ORGYM_NET_MAX_RETAIL
-#define NSUCC (NE + NM)
-
-struct NetDev {
-    int T, backlog, J, E, M, obs_dim, sumL;
-    const double* disc;  // [T] alpha**t
-    double I0[NJ], h[NJ], C[NJ], v[NJ], o[NJ];
-    uint8_t is_factory[NJ], is_retail[NJ];
-    int16_t sup[NE], pur[NE], L[NE];
-    int32_t roff[NE];
-    uint32_t Lmagic[NE];  // ceil(2^32 / L): t % L by multiply-high (0 encodes L <= 1)
-    double p[NE], g[NE];
-    int16_t rt_node[NM];
-    double rt_p[NM], rt_b[NM];
-    int16_t succ_ptr[NJ + 1], pred_ptr[NJ + 1];
-    int16_t succ_idx[NSUCC], pred_idx[NE];
-    AliasDev dem[NM];
-};
-
-struct NetHandle {
-    HandleBase base;
-    NetDev dev;
-    int64_t npad;
-    int threads;  // threads per CTA that fit the shared-memory work vectors
-    size_t smem;
-    std::vector<void*> allocs;
-    double* partials;
-};
-
-// state (field[slot][env], stride npad): [key u64][X J][Y E][U M][ring sumL] f64, [period i32][episode u32]
-struct NetState {
-    uint64_t* key;
-    double *X, *Y, *U, *ring;
-    int32_t* period;
-    uint32_t* episode;
-    int64_t npad;
-    __host__ __device__ NetState(void* base, int64_t npad_, const NetDev& P) : npad(npad_) {
-        char* p = (char*)base;
-        key = (uint64_t*)p;
-        p += 8 * npad;
-        X = (double*)p;
-        Y = X + (size_t)P.J * npad;
-        U = Y + (size_t)P.E * npad;
-        ring = U + (size_t)P.M * npad;
-        p = (char*)(ring + (size_t)P.sumL * npad);
-        period = (int32_t*)p;
-        p += 4 * npad;
-        episode = (uint32_t*)p;
-    }
-};
-static int64_t net_state_bytes(const NetDev& P, int64_t npad) {
-    return npad * (8 + 8 * (int64_t)(P.J + P.E + P.M + P.sumL) + 8);
-}
+#include "netinv.cuh"
 
 // t % d for 0 <= t < 2^20, 1 <= d <= 64 (exact, see invmgmt.cu)
 __device__ __forceinline__ int net_mod(int t, int d, uint32_t magic) {
@@ -130,39 +74,7 @@ __global__ void net_reset_kernel(const __grid_constant__ NetDev P, int64_t N, in
     for (; k < P.obs_dim; k++) o[k] = 0.0f;
 }
 
-struct NetSimArgs {
-    int64_t N, npad, env_offset;
-    int rollout;  // 0 = one period from / to state (STEP), 1 = fused episode (ROLLOUT)
-    void* state;  // STEP: live state; ROLLOUT: scratch for the rings
-    uint64_t seed;
-    uint32_t episode;
-    int policy;
-    const float* actions;
-    int64_t a_se, a_st;
-    const double* demand;
-    int64_t d_se, d_st;
-    int autoreset;
-    // STEP outputs
-    float* obs;
-    double* reward;
-    uint8_t* terminated;
-    uint8_t* truncated;
-    double* info_demand;
-    double* info_sales;
-    double* info_profit;
-    double* info_profit_total;
-    float* final_obs;
-    uint32_t* err;
-    int use_tile;  // STEP: stage the observation block in shared memory and store it coalesced
-    // ROLLOUT outputs
-    double* ep_return;
-    double* stats;
-    double* reward_traj;
-    double* final_X;
-    double* final_Y;
-    double* final_U;
-    double* partials;
-};
+#include "netinv_args.cuh"
 
 template <int NTHR>
 __global__ void __launch_bounds__(NTHR) net_sim_kernel(const __grid_constant__ NetDev P,
@@ -470,8 +382,9 @@ static void net_launch(const NetHandle* H, const NetSimArgs& A, size_t smem, cud
 // ------------------------------------------------------------------------------------------------
 // host side of the C ABI
 // ------------------------------------------------------------------------------------------------
-extern "C" int orgym_netinv_create(const orgym_netinv_config_t* c, int64_t num_envs, int device, orgym_handle_t* out) {
-    ORGYM_REQUIRE(c && out, "null argument");
+// validate + flatten a config into NetDev (no CUDA calls)
+static int net_fill(const orgym_netinv_config_t* c, NetDev& P) {
+    ORGYM_REQUIRE(c, "null argument");
     // mirrors network_management.py:197-238
     ORGYM_REQUIRE(c->num_periods > 0, "num_periods must be positive");
     ORGYM_REQUIRE(c->alpha > 0 && c->alpha <= 1, "alpha must be in (0, 1]");
@@ -481,8 +394,6 @@ extern "C" int orgym_netinv_create(const orgym_netinv_config_t* c, int64_t num_e
                         c->num_main, NJ, c->num_reorder, NE, c->num_retail, NM);
         return ORGYM_E_UNSUPPORTED;
     }
-    NetHandle* H = new NetHandle();
-    NetDev& P = H->dev;
     memset(&P, 0, sizeof(P));
     P.T = c->num_periods;
     P.backlog = c->backlog ? 1 : 0;
@@ -493,8 +404,7 @@ extern "C" int orgym_netinv_create(const orgym_netinv_config_t* c, int64_t num_e
 #define FAIL(code, ...)            \
     do {                           \
         orgym_set_error(__VA_ARGS__); \
-        rc = code;                 \
-        goto done;                 \
+        return code;               \
     } while (0)
     {
         for (int j = 0; j < P.J; j++) {
@@ -558,6 +468,28 @@ extern "C" int orgym_netinv_create(const orgym_netinv_config_t* c, int64_t num_e
             P.pred_idx[z] = (int16_t)c->pred_idx[z];
         }
         P.obs_dim = P.M + P.J + P.sumL;  // :190
+    }
+#undef FAIL
+    (void)rc;
+    return ORGYM_OK;
+}
+
+extern "C" int orgym_netinv_create(const orgym_netinv_config_t* c, int64_t num_envs, int device, orgym_handle_t* out) {
+    ORGYM_REQUIRE(c && out, "null argument");
+    NetHandle* H = new NetHandle();
+    NetDev& P = H->dev;
+    int rc = net_fill(c, P);
+    if (rc != ORGYM_OK) {
+        delete H;
+        return rc;
+    }
+#define FAIL(code, ...)            \
+    do {                           \
+        orgym_set_error(__VA_ARGS__); \
+        rc = code;                 \
+        goto done;                 \
+    } while (0)
+    {
         rc = orgym_handle_base_init(&H->base, FAM_NETINV, device, num_envs);
         if (rc != ORGYM_OK) goto done;
         {
@@ -581,7 +513,7 @@ extern "C" int orgym_netinv_create(const orgym_netinv_config_t* c, int64_t num_e
             while (H->threads > 32 && per_thread * H->threads > 200 * 1024) H->threads /= 2;
             if (per_thread * H->threads > 200 * 1024) FAIL(ORGYM_E_UNSUPPORTED, "network work vectors do not fit in shared memory");
             H->smem = per_thread * H->threads;
-            int nblocks = (int)((num_envs + H->threads - 1) / H->threads);
+            int nblocks = (int)((num_envs + 31) / 32);  // enough for any block size
             H->partials = nullptr;
             if (cudaMalloc(&H->partials, 64 * (size_t)nblocks) != cudaSuccess) FAIL(ORGYM_E_CUDA, "device allocation failed");
             H->allocs.push_back(H->partials);
@@ -589,6 +521,21 @@ extern "C" int orgym_netinv_create(const orgym_netinv_config_t* c, int64_t num_e
             cudaFuncSetAttribute(net_sim_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
             cudaFuncSetAttribute(net_sim_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
             cudaFuncSetAttribute(net_sim_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+            // kernel specialised for this topology (NVRTC); any failure falls back to the generic kernel above
+            H->jit_threads = 0;
+            H->dem_dev = nullptr;
+            // auto: specialise graphs of up to 48 reorder links (larger ones take tens of seconds to compile);
+            // ORGYM_NET_JIT=0 never, =1 always, =2 always and fail loudly if it does not work
+            const char* jv = getenv("ORGYM_NET_JIT");
+            const bool want_jit = jv ? jv[0] != '0' : (P.E <= 48);
+            if (want_jit) {
+                std::string jerr;
+                if (net_jit_build(H, &jerr) != 0) {
+                    if (jv && jv[0] == '2') FAIL(ORGYM_E_CUDA, "ORGYM_NET_JIT=2 but specialisation failed: %s", jerr.c_str());
+                    fprintf(stderr, "[orgym_b200] network kernel specialisation unavailable (%s); using the generic kernel\n",
+                            jerr.substr(0, 600).c_str());
+                }
+            }
         }
     }
 done:
@@ -611,6 +558,7 @@ extern "C" int orgym_netinv_destroy(orgym_handle_t h) {
     NetHandle* H = (NetHandle*)h;
     {
         DeviceGuard g(H->base.device);
+        orgym_jit_release(&H->jit);
         for (void* p : H->allocs) cudaFree(p);
     }
     orgym_handle_base_free(&H->base);
@@ -678,6 +626,7 @@ extern "C" int orgym_netinv_step(orgym_handle_t h, void* state_dev, const float*
         A.final_obs = info->final_obs_dev;
     }
     A.err = H->base.err_dev;
+    if (H->jit.fn) return net_jit_launch(H, A, (cudaStream_t)stream);
     size_t tile = (size_t)H->threads * (P.obs_dim | 1) * 4;
     A.use_tile = (H->smem + tile <= 200 * 1024) ? 1 : 0;
     net_launch(H, A, H->smem + (A.use_tile ? tile : 0), (cudaStream_t)stream);
@@ -732,12 +681,46 @@ extern "C" int orgym_netinv_rollout(orgym_handle_t h, void* scratch_dev, uint64_
     A.final_Y = out->final_Y_dev;
     A.final_U = out->final_U_dev;
     A.partials = out->summary_dev ? H->partials : nullptr;
-    int nblocks = (int)((A.N + H->threads - 1) / H->threads);
-    net_launch(H, A, H->smem, (cudaStream_t)stream);
+    const int thr = H->jit.fn ? H->jit_threads : H->threads;
+    int nblocks = (int)((A.N + thr - 1) / thr);
+    if (H->jit.fn) {
+        int rc = net_jit_launch(H, A, (cudaStream_t)stream);
+        if (rc != ORGYM_OK) return rc;
+    } else
+        net_launch(H, A, H->smem, (cudaStream_t)stream);
     ORGYM_CUDA(cudaGetLastError());
     if (out->summary_dev) {
         orgym_reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(H->partials, nblocks, out->summary_dev);
         ORGYM_CUDA(cudaGetLastError());
+    }
+    return ORGYM_OK;
+}
+
+// debugging / test aid: the CUDA source the specialiser generates for a config (no GPU needed); compile_check != 0
+// also runs it through NVRTC.  Returns the source length (excluding the terminator) in *needed.
+extern "C" int orgym_netinv_codegen(const orgym_netinv_config_t* cfg, int compile_check, char* buf, int64_t buflen,
+                                    int64_t* needed) {
+    NetDev* P = new NetDev();
+    int rc = net_fill(cfg, *P);
+    if (rc != ORGYM_OK) {
+        delete P;
+        return rc;
+    }
+    std::string src = net_jit_source(*P, 128);
+    delete P;
+    if (needed) *needed = (int64_t)src.size();
+    if (buf && buflen > 0) {
+        size_t n = src.size() < (size_t)buflen - 1 ? src.size() : (size_t)buflen - 1;
+        memcpy(buf, src.data(), n);
+        buf[n] = 0;
+    }
+    if (compile_check) {
+        std::string err;
+        int jr = orgym_jit_compile_only(src, &err);
+        if (jr != 0) {
+            orgym_set_error("%s", err.substr(0, 900).c_str());
+            return ORGYM_E_UNSUPPORTED;
+        }
     }
     return ORGYM_OK;
 }

@@ -1,0 +1,70 @@
+// netinv.cuh -- declarations shared by the generic network kernel (netinv.cu) and the code generator (netinv_jit.cu)
+#pragma once
+#include "common.cuh"
+#include "jit.cuh"
+
+#define NJ ORGYM_NET_MAX_NODES
+#define NE ORGYM_NET_MAX_REORDER
+#define NM ORGYM_NET_MAX_RETAIL
+#define NSUCC (NE + NM)
+
+struct NetDev {
+    int T, backlog, J, E, M, obs_dim, sumL;
+    const double* disc;  // [T] alpha**t
+    double I0[NJ], h[NJ], C[NJ], v[NJ], o[NJ];
+    uint8_t is_factory[NJ], is_retail[NJ];
+    int16_t sup[NE], pur[NE], L[NE];
+    int32_t roff[NE];
+    uint32_t Lmagic[NE];  // ceil(2^32 / L): t % L by multiply-high (0 encodes L <= 1)
+    double p[NE], g[NE];
+    int16_t rt_node[NM];
+    double rt_p[NM], rt_b[NM];
+    int16_t succ_ptr[NJ + 1], pred_ptr[NJ + 1];
+    int16_t succ_idx[NSUCC], pred_idx[NE];
+    AliasDev dem[NM];
+};
+
+struct NetHandle {
+    HandleBase base;
+    NetDev dev;
+    int64_t npad;
+    int threads;  // threads per CTA that fit the shared-memory work vectors
+    size_t smem;
+    std::vector<void*> allocs;
+    double* partials;
+    // run-time specialised kernel (netinv_jit.cu); jit.fn == nullptr -> generic kernel
+    JitKernel jit;
+    int jit_threads;
+    AliasDev* dem_dev;  // device copy of dev.dem[] for the specialised kernel
+};
+
+// state (field[slot][env], stride npad): [key u64][X J][Y E][U M][ring sumL] f64, [period i32][episode u32]
+struct NetState {
+    uint64_t* key;
+    double *X, *Y, *U, *ring;
+    int32_t* period;
+    uint32_t* episode;
+    int64_t npad;
+    __host__ __device__ NetState(void* base, int64_t npad_, const NetDev& P) : npad(npad_) {
+        char* p = (char*)base;
+        key = (uint64_t*)p;
+        p += 8 * npad;
+        X = (double*)p;
+        Y = X + (size_t)P.J * npad;
+        U = Y + (size_t)P.E * npad;
+        ring = U + (size_t)P.M * npad;
+        p = (char*)(ring + (size_t)P.sumL * npad);
+        period = (int32_t*)p;
+        p += 4 * npad;
+        episode = (uint32_t*)p;
+    }
+};
+static int64_t net_state_bytes(const NetDev& P, int64_t npad) {
+    return npad * (8 + 8 * (int64_t)(P.J + P.E + P.M + P.sumL) + 8);
+}
+
+
+// netinv_jit.cu: generate + compile the kernel specialised for this topology (returns 0 on success)
+int net_jit_build(NetHandle* H, std::string* err);
+int net_jit_launch(const NetHandle* H, const struct NetSimArgs& A, cudaStream_t s);
+std::string net_jit_source(const NetDev& P, int nthr);

@@ -1,0 +1,326 @@
+// netinv_jit.cu -- network env: the topology compiled into the instruction stream.
+//
+// The generic kernel (netinv.cu) interprets the flattened graph from the constant bank: every link / node visit
+// pays for index loads, address arithmetic and loop control (ncu: ~3200 warp-instructions per warp-step on the
+// default 9-node graph, most of them bookkeeping).  Here the same period (network_management.py:436-635) is emitted as
+// straight-line CUDA source for ONE topology -- literal link / node indices, literal prices and lead times, per-
+// instance state in registers -- compiled for sm_100a with NVRTC when the env is created.  Evaluation order of every
+// floating-point expression is exactly the generic kernel's (= the reference's); the parity tests run both.
+#include <cstdarg>
+
+#include "netinv.cuh"
+#include "netinv_args.cuh"
+
+namespace {
+struct Src {
+    std::string s;
+    void operator()(const char* fmt, ...) {
+        char buf[2048];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        s += buf;
+        s += '\n';
+    }
+};
+// exact double literal (hexadecimal floating constant, C++17)
+std::string lit(double v) {
+    char buf[64];
+    if (v == 0.0) return "0.0";
+    snprintf(buf, sizeof(buf), "%a", v);
+    return buf;
+}
+}  // namespace
+
+std::string net_jit_source(const NetDev& P, int nthr) {
+    const int J = P.J, E = P.E, M = P.M;
+    Src o;
+    o.s += orgym_jit_device_rng_src();
+    o.s += orgym_jit_net_args_src();
+    o("#define NTHR %d", nthr);
+    o("#define NJ %d\n#define NE %d\n#define NM %d\n#define NOBS %d\n#define NSUML %d\n#define NT %d", J, E, M, P.obs_dim,
+      P.sumL, P.T);
+    o("#define OSTRIDE %d", P.obs_dim | 1);
+    // ---- observation writer (:334-413)
+    o("__device__ __forceinline__ void write_obs(const double (&X)[NJ > 0 ? NJ : 1], const double (&U)[NM > 0 ? NM : 1],");
+    o("    const double* __restrict__ ring, long long np, long long e, int t, float* o) {");
+    for (int r = 0; r < M; r++) o("  o[%d] = (float)U[%d];", r, r);
+    for (int j = 0; j < J; j++) o("  o[%d] = (float)X[%d];", M + j, j);
+    {
+        int k = M + J;
+        for (int i = 0; i < E; i++) {
+            const int L = P.L[i];
+            if (L == 0) continue;
+            o("  { const int s0 = t %% %d; const double* b = ring + (long long)%d * np + e;", L, P.roff[i]);
+            o("    double v[%d];", L);
+            o("    _Pragma(\"unroll\") for (int q = 0; q < %d; q++) { int sl = s0 + q; sl = sl >= %d ? sl - %d : sl; v[q] = b[(long long)sl * np]; }",
+              L, L, L);
+            o("    _Pragma(\"unroll\") for (int q = 0; q < %d; q++) o[%d + q] = (float)v[q]; }", L, k);
+            k += L;
+        }
+    }
+    o("}");
+    // ---- kernel
+    o("extern \"C\" __global__ void __launch_bounds__(NTHR) net_jit_kernel(const NetSimArgs A, const double* __restrict__ disc,");
+    o("    const AliasDev* __restrict__ dem) {");
+    o("  extern __shared__ __align__(16) unsigned char smem[];");
+    o("  float* otile = (float*)smem;");
+    o("  const int tid = threadIdx.x;");
+    o("  const long long e0 = (long long)blockIdx.x * NTHR, e = e0 + tid;");
+    o("  const bool valid = e < A.N;");
+    o("  const long long ec = valid ? e : 0, np = A.npad;");
+    o("  char* sb = (char*)A.state;");
+    o("  unsigned long long* s_key = (unsigned long long*)sb;");
+    o("  double* s_X = (double*)(sb + 8 * np); double* s_Y = s_X + (long long)NJ * np; double* s_U = s_Y + (long long)NE * np;");
+    o("  double* ring = s_U + (long long)NM * np;");
+    o("  int* s_period = (int*)(ring + (long long)NSUML * np); unsigned int* s_episode = (unsigned int*)(s_period + np);");
+    o("  double X[NJ > 0 ? NJ : 1], Y[NE > 0 ? NE : 1], U[NM > 0 ? NM : 1], R[NE > 0 ? NE : 1], S[NM > 0 ? NM : 1], Cn[NJ > 0 ? NJ : 1];");
+    o("  unsigned long long key; unsigned int episode; int t0, t1; bool do_step = valid;");
+    o("  float* orow = A.use_tile ? otile + tid * OSTRIDE : (A.obs ? A.obs + ec * NOBS : (float*)0);");
+    // initial state literals
+    auto emit_reset_regs = [&](const char* ind) {
+        for (int j = 0; j < J; j++) o("%sX[%d] = %s;", ind, j, lit(P.I0[j]).c_str());
+        for (int i = 0; i < E; i++) o("%sY[%d] = 0.0;", ind, i);
+        for (int r = 0; r < M; r++) o("%sU[%d] = 0.0;", ind, r);
+    };
+    auto emit_reset_state = [&](const char* ind) {
+        for (int j = 0; j < J; j++) o("%ss_X[(long long)%d * np + e] = %s;", ind, j, lit(P.I0[j]).c_str());
+        o("%sfor (int i = 0; i < NE; i++) s_Y[(long long)i * np + e] = 0.0;", ind);
+        o("%sfor (int r = 0; r < NM; r++) s_U[(long long)r * np + e] = 0.0;", ind);
+        o("%sfor (int k = 0; k < NSUML; k++) ring[(long long)k * np + e] = 0.0;", ind);
+        o("%ss_period[e] = 0;", ind);
+    };
+    o("  if (A.rollout) {");
+    o("    key = A.seed + (unsigned long long)(A.env_offset + e); episode = A.episode; t0 = 0; t1 = NT;");
+    emit_reset_regs("    ");
+    o("    if (valid) for (int k = 0; k < NSUML; k++) ring[(long long)k * np + e] = 0.0;");
+    o("  } else {");
+    o("    key = s_key[ec]; episode = s_episode[ec]; t0 = s_period[ec]; t1 = t0 + 1;");
+    o("    if (valid && t0 >= NT) {");
+    o("      do_step = false;");
+    o("      if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {");
+    emit_reset_state("        ");
+    emit_reset_regs("        ");
+    o("        s_episode[e] = episode + 1;");
+    o("        write_obs(X, U, ring, np, e, 0, orow);");
+    o("        A.reward[e] = 0.0; A.terminated[e] = 0; A.truncated[e] = 0;");
+    o("      } else {");
+    o("        atomicOr(A.err, ORGYM_ERR_STEP_PAST_END);");
+    o("        if (A.use_tile) for (int z = 0; z < NOBS; z++) orow[z] = A.obs[e * NOBS + z];");
+    o("        A.reward[e] = 0.0; A.terminated[e] = 0; A.truncated[e] = 1;");
+    o("      }");
+    o("    }");
+    o("    if (do_step) {");
+    for (int j = 0; j < J; j++) o("      X[%d] = s_X[(long long)%d * np + e];", j, j);
+    for (int i = 0; i < E; i++) o("      Y[%d] = s_Y[(long long)%d * np + e];", i, i);
+    for (int r = 0; r < M; r++) o("      U[%d] = s_U[(long long)%d * np + e];", r, r);
+    o("    }");
+    o("  }");
+    o("  double ret = 0.0, s_sales = 0.0, s_dem = 0.0, s_unf = 0.0, s_inv = 0.0, last_reward = 0.0;");
+    o("  if (!A.rollout && !do_step) t1 = t0;");
+    o("  for (int t = t0; t < t1; t++) {");
+    // arrivals: all ring loads up front (independent -> overlapped)
+    for (int i = 0; i < E; i++)
+        if (P.L[i] > 0) {
+            o("    const long long sl%d = (long long)(%d + t %% %d) * np + ec;", i, P.roff[i], P.L[i]);
+            o("    const double Ar%d = ring[sl%d];", i, i);
+        }
+    o("    const float* arow = A.policy == ORGYM_NET_POLICY_CONSTANT ? A.actions : A.actions + ec * A.a_se + (long long)(A.rollout ? t : 0) * A.a_st;");
+    // 0) orders (:448-490)
+    for (int j = 0; j < J; j++) o("    Cn[%d] = 0.0;", j);
+    o("    double cons = 0.0;");
+    for (int i = 0; i < E; i++) {
+        const int s = P.sup[i];
+        o("    { double req = rint((double)arow[%d]); req = req > 0.0 ? req : 0.0;", i);
+        if (s == -1)
+            o("      R[%d] = req; }", i);
+        else if (s < 0)
+            o("      R[%d] = 0.0; (void)req; }", i);
+        else {
+            if (i == 0 || P.sup[i - 1] != s) o("      cons = 0.0;");
+            o("      double avail = X[%d] - cons; avail = avail > 0.0 ? avail : 0.0; double oa = avail;", s);
+            if (P.is_factory[s]) {
+                o("      { double mp = %s * avail; double lim = mp < %s ? mp : %s; oa = lim < oa ? lim : oa; }", lit(P.v[s]).c_str(),
+                  lit(P.C[s]).c_str(), lit(P.C[s]).c_str());
+            }
+            o("      double f = oa < req ? oa : req;");
+            if (P.v[s] == 1.0)
+                o("      cons += f;");
+            else
+                o("      cons += f / %s;", lit(P.v[s]).c_str());
+            o("      R[%d] = f;", i);
+            if (i == E - 1 || P.sup[i + 1] != s) o("      Cn[%d] = cons;", s);
+            o("    }");
+        }
+    }
+    // on-hand (:516-528)
+    for (int j = 0; j < J; j++) {
+        o("    { double arr = 0.0;");
+        for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
+            const int i = P.pred_idx[z];
+            if (P.L[i] == 0)
+                o("      arr += R[%d];", i);
+            else
+                o("      arr += Ar%d;", i);
+        }
+        o("      X[%d] = (X[%d] + arr) - Cn[%d]; }", j, j, j);
+    }
+    // 1) pipeline (:494-511) + ring commit
+    for (int i = 0; i < E; i++) {
+        if (P.L[i] == 0)
+            o("    Y[%d] = (Y[%d] - R[%d]) + R[%d];", i, i, i, i);
+        else {
+            o("    Y[%d] = (Y[%d] - Ar%d) + R[%d];", i, i, i, i);
+            o("    if (valid) ring[sl%d] = R[%d];", i, i);
+        }
+    }
+    // 2-4) market (:536-566)
+    for (int r = 0; r < M; r++) {
+        const int j = P.rt_node[r];
+        o("    { double d;");
+        o("      if (A.demand) d = rint(A.demand[ec * A.d_se + (long long)(A.rollout ? t : 0) * A.d_st + %d]);", r);
+        o("      else d = (double)sample_fixed(dem[%d], dem[%d].table, key, episode, t, %du);", r, r, r);
+        o("      d = d > 0.0 ? d : 0.0;");
+        o("      double fill = d + U[%d]; double x = X[%d]; double invr = x > 0.0 ? x : 0.0;", r, j);
+        o("      double sl = invr < fill ? invr : fill; S[%d] = sl; X[%d] = x - sl; double un = fill - sl;", r, j);
+        o("      U[%d] = %s; s_sales += sl; s_dem += d; s_unf += %s;", r, P.backlog ? "un" : "0.0", P.backlog ? "un" : "0.0");
+        o("      if (!A.rollout && A.info_demand && do_step) A.info_demand[e * NM + %d] = d; }", r);
+    }
+    // 5) profit (:578-613)
+    o("    double total = 0.0;");
+    for (int j = 0; j < J; j++) {
+        o("    { double SR = 0.0, PC = 0.0, HCp = 0.0, sold = 0.0, UP = 0.0;");
+        for (int z = P.succ_ptr[j]; z < P.succ_ptr[j + 1]; z++) {
+            const int l = P.succ_idx[z];
+            if (l < E) {
+                o("      SR += %s * R[%d]; sold += R[%d];", lit(P.p[l]).c_str(), l, l);
+            } else {
+                const int r = l - E;
+                if (P.is_retail[j]) o("      UP += %s * U[%d];", lit(P.rt_b[r]).c_str(), r);
+                o("      SR += %s * S[%d]; sold += S[%d];", lit(P.rt_p[r]).c_str(), r, r);
+            }
+        }
+        for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
+            const int i = P.pred_idx[z];
+            o("      PC += %s * R[%d]; { double y = Y[%d]; HCp += %s * (y > 0.0 ? y : 0.0); }", lit(P.p[i]).c_str(), i, i,
+              lit(P.g[i]).c_str());
+        }
+        o("      double x = X[%d]; double xp = x > 0.0 ? x : 0.0; double HC = %s * xp + HCp; double OC = 0.0;", j, lit(P.h[j]).c_str());
+        if (P.is_factory[j]) {
+            if (!(P.v[j] > 0.0))
+                o("      OC = 0.0;");
+            else if (P.v[j] == 1.0)
+                o("      OC = %s * sold;", lit(P.o[j]).c_str());
+            else
+                o("      OC = %s * (sold / %s);", lit(P.o[j]).c_str(), lit(P.v[j]).c_str());
+        }
+        o("      (void)sold; double pj = (((SR - PC) - OC) - HC) - UP; total += pj; s_inv += xp;");
+        o("      if (!A.rollout && A.info_profit && do_step) A.info_profit[e * NJ + %d] = pj; }", j);
+    }
+    o("    last_reward = disc[t] * total; ret += last_reward;");
+    o("    if (A.rollout && A.reward_traj && valid) A.reward_traj[e * NT + t] = last_reward;");
+    o("    if (!A.rollout && do_step) {");
+    o("      if (A.info_profit_total) A.info_profit_total[e] = total;");
+    o("      if (A.info_sales) {");
+    for (int i = 0; i < E; i++) o("        A.info_sales[e * (NE + NM) + %d] = R[%d];", i, i);
+    for (int r = 0; r < M; r++) o("        A.info_sales[e * (NE + NM) + %d] = S[%d];", E + r, r);
+    o("      }");
+    o("    }");
+    o("  }");  // t loop
+    // ---- epilogue: ROLLOUT
+    o("  if (A.rollout) {");
+    o("    if (valid) {");
+    o("      if (A.ep_return) A.ep_return[e] = ret;");
+    o("      if (A.stats) { A.stats[e * 4 + 0] = s_sales; A.stats[e * 4 + 1] = s_dem; A.stats[e * 4 + 2] = s_unf; A.stats[e * 4 + 3] = s_inv; }");
+    o("      if (A.final_X) {");
+    for (int j = 0; j < J; j++) o("        A.final_X[e * NJ + %d] = X[%d];", j, j);
+    o("      }\n      if (A.final_Y) {");
+    for (int i = 0; i < E; i++) o("        A.final_Y[e * NE + %d] = Y[%d];", i, i);
+    o("      }\n      if (A.final_U) {");
+    for (int r = 0; r < M; r++) o("        A.final_U[e * NM + %d] = U[%d];", r, r);
+    o("      }");
+    o("    }");
+    o("    if (A.partials) {");
+    o("      double v[7] = {valid ? 1.0 : 0.0, valid ? ret : 0.0, valid ? ret * ret : 0.0, valid ? s_sales : 0.0, valid ? s_dem : 0.0, valid ? s_unf : 0.0, valid ? s_inv : 0.0};");
+    o("      __shared__ double red[NTHR / 32][7];");
+    o("      _Pragma(\"unroll\") for (int z = 0; z < 7; z++) { double x = v[z];");
+    o("        _Pragma(\"unroll\") for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);");
+    o("        if ((tid & 31) == 0) red[tid >> 5][z] = x; }");
+    o("      __syncthreads();");
+    o("      if (tid < 7) { double x = 0.0; for (int wv = 0; wv < NTHR / 32; wv++) x += red[wv][tid]; A.partials[(long long)blockIdx.x * 8 + tid] = x; }");
+    o("    }");
+    o("    return;");
+    o("  }");
+    // ---- epilogue: STEP
+    o("  if (do_step) {");
+    o("    const int tn = t0 + 1; const bool trunc = tn >= NT;");
+    o("    const bool reset_now = trunc && A.autoreset == ORGYM_AUTORESET_SAME_STEP;");
+    o("    if (!reset_now) {");
+    for (int j = 0; j < J; j++) o("      s_X[(long long)%d * np + e] = X[%d];", j, j);
+    for (int i = 0; i < E; i++) o("      s_Y[(long long)%d * np + e] = Y[%d];", i, i);
+    for (int r = 0; r < M; r++) o("      s_U[(long long)%d * np + e] = U[%d];", r, r);
+    o("      s_period[e] = tn;");
+    o("      write_obs(X, U, ring, np, e, tn, orow);");
+    o("    } else {");
+    o("      if (A.final_obs) write_obs(X, U, ring, np, e, tn, A.final_obs + e * NOBS);");
+    emit_reset_state("      ");
+    emit_reset_regs("      ");
+    o("      s_episode[e] = episode + 1;");
+    o("      write_obs(X, U, ring, np, e, 0, orow);");
+    o("    }");
+    o("    A.reward[e] = last_reward; A.terminated[e] = 0; A.truncated[e] = trunc ? 1 : 0;");
+    o("  }");
+    o("  if (A.use_tile) {");
+    o("    __syncthreads();");
+    o("    const int nvalid = (int)((A.N - e0) < NTHR ? (A.N - e0) : NTHR);");
+    o("    const int total = nvalid * NOBS;");
+    o("    float* g = A.obs + e0 * NOBS;");
+    o("    for (int i = tid; i < total; i += NTHR) { const int r = i / NOBS, c = i - r * NOBS; __stcs(g + i, otile[r * OSTRIDE + c]); }");
+    o("  }");
+    o("}");
+    return o.s;
+}
+
+int net_jit_build(NetHandle* H, std::string* err) {
+    const NetDev& P = H->dev;
+    H->jit_threads = 128;
+    std::string src = net_jit_source(P, H->jit_threads);
+    int rc = orgym_jit_compile(src, "net_jit_kernel", &H->jit, err);
+    if (rc != 0) return rc;
+    // device copy of the per-link demand descriptors
+    H->dem_dev = nullptr;
+    if (cudaMalloc(&H->dem_dev, sizeof(AliasDev) * (size_t)(P.M > 0 ? P.M : 1)) != cudaSuccess) {
+        *err = "device allocation failed";
+        orgym_jit_release(&H->jit);
+        return 10;
+    }
+    H->allocs.push_back(H->dem_dev);
+    if (P.M > 0) cudaMemcpy(H->dem_dev, P.dem, sizeof(AliasDev) * (size_t)P.M, cudaMemcpyHostToDevice);
+    cudaFuncSetAttribute((const void*)H->jit.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaGetLastError();
+    return 0;
+}
+
+int net_jit_launch(const NetHandle* H, const NetSimArgs& A_in, cudaStream_t s) {
+    const NetDev& P = H->dev;
+    NetSimArgs A = A_in;
+    const int nthr = H->jit_threads;
+    size_t tile = (size_t)nthr * (P.obs_dim | 1) * 4;
+    size_t smem = 16;
+    if (!A.rollout) {
+        A.use_tile = tile <= 160 * 1024 ? 1 : 0;
+        if (A.use_tile) smem = tile;
+    } else
+        A.use_tile = 0;
+    const double* disc = P.disc;
+    const AliasDev* dem = H->dem_dev;
+    void* args[] = {(void*)&A, (void*)&disc, (void*)&dem};
+    unsigned grid = (unsigned)((A.N + nthr - 1) / nthr);
+    cudaError_t e = cudaLaunchKernel((const void*)H->jit.fn, dim3(grid), dim3(nthr), args, smem, s);
+    if (e != cudaSuccess) {
+        orgym_set_error("specialised network kernel launch failed: %s", cudaGetErrorString(e));
+        return ORGYM_E_CUDA;
+    }
+    return ORGYM_OK;
+}

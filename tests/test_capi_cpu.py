@@ -68,3 +68,23 @@ def test_invmgmt_params_mirror_reference_defaults():
 def test_invmgmt_validation_matches_reference(bad, msg):
     with pytest.raises(AssertionError, match=msg):
         pkg.InvManagementParams(**bad)
+
+
+@pytest.mark.parametrize("kind", ["default", "custom", "yield"])
+def test_network_kernel_specialiser_compiles_without_gpu(lib, kind):
+    """The topology -> CUDA source generator (netinv_jit.cu) and NVRTC: compile check for sm_100a on the CPU box."""
+    import json
+    if kind == "yield":
+        g = np.load(os.path.join(ROOT, "tests", "golden", "net_yield_backlog_random.npz"))
+        meta = json.loads(str(g["meta"]))
+        P = pkg.NetInvMgmtParams(graph=meta["graph"], num_periods=meta["num_periods"], backlog=True, alpha=meta["alpha"])
+    else:
+        P = pkg.NetInvMgmtParams(default_graph_kind=kind)
+    keep = []
+    cfg = P.to_c(keep)
+    need = C.c_int64(0)
+    buf = C.create_string_buffer(1 << 20)
+    rc = lib.orgym_netinv_codegen(C.byref(cfg), 1, buf, len(buf), C.byref(need))
+    assert rc == 0, lib.orgym_last_error()
+    src = buf.value.decode()
+    assert len(src) == need.value and "net_jit_kernel" in src and f"#define NE {len(P.reorder_links)}" in src

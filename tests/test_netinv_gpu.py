@@ -14,13 +14,21 @@ def _torch():
     return torch
 
 
+@pytest.fixture(params=["specialised", "generic"])
+def kernel_mode(request, monkeypatch):
+    """Run the parity tests through both network kernels: the NVRTC-specialised one (must compile) and the
+    generic constant-bank interpreter."""
+    monkeypatch.setenv("ORGYM_NET_JIT", "2" if request.param == "specialised" else "0")
+    return request.param
+
+
 def _mk(meta, n, **kw):
     return pkg.NetInvMgmtMasterEnv(graph=meta["graph"], num_periods=meta["num_periods"], backlog=meta["backlog"],
                                    alpha=meta["alpha"], num_envs=n, device="cuda:0", **kw)
 
 
 @pytest.mark.parametrize("path", NET, ids=ids(NET))
-def test_step_matches_reference(path):
+def test_step_matches_reference(path, kernel_mode):
     torch = _torch()
     g, meta = load_golden(path)
     E = len(g["seeds"])
@@ -48,7 +56,7 @@ def test_step_matches_reference(path):
 
 
 @pytest.mark.parametrize("path", NET, ids=ids(NET))
-def test_rollout_replay_matches_reference(path):
+def test_rollout_replay_matches_reference(path, kernel_mode):
     g, meta = load_golden(path)
     E = len(g["seeds"])
     env = _mk(meta, E)
@@ -70,7 +78,7 @@ def test_rollout_replay_matches_reference(path):
     env.close()
 
 
-def test_class_surface_and_constant_policy():
+def test_class_surface_and_constant_policy(kernel_mode):
     """Class names / defaults of the reference, ConstantOrderAgent rollout vs oracle with device-sampled demand."""
     from oracle import oracle
     torch = _torch()
@@ -141,7 +149,7 @@ def test_synthetic_64_node_network_vs_oracle():
     env.close()
 
 
-def test_autoreset_next_step():
+def test_autoreset_next_step(kernel_mode):
     torch = _torch()
     env = pkg.NetInvMgmtBacklogEnv(num_envs=130, device="cuda:0", num_periods=3)
     obs0 = env.reset(seed=1)[0].clone()
