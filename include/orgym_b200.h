@@ -167,6 +167,7 @@ typedef struct {
     int64_t* final_I_dev;    /* [N,m-1] */
     int64_t* final_B_dev;    /* [N,m] */
     double* summary_dev;     /* [8] batch sums: n, sum ret, sum ret^2, sum sales, sum demand, sum stockout, sum end inv, 0 */
+    int32_t* stats32_dev;    /* [N,4] the same statistics as stats_dev, saturated to int32 (halves the result traffic) */
 } orgym_invmgmt_rollout_out_t;
 
 /* fused reset + `periods` steps of every env with state held on chip (no state_dev needed).

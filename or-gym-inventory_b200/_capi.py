@@ -47,7 +47,7 @@ class InvRolloutIn(C.Structure):
 
 class InvRolloutOut(C.Structure):
     _fields_ = [("ep_return", C.c_void_p), ("stats", C.c_void_p), ("reward_traj", C.c_void_p),
-                ("final_I", C.c_void_p), ("final_B", C.c_void_p), ("summary", C.c_void_p)]
+                ("final_I", C.c_void_p), ("final_B", C.c_void_p), ("summary", C.c_void_p), ("stats32", C.c_void_p)]
 
 
 class NvConfig(C.Structure):

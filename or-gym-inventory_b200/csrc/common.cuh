@@ -82,6 +82,14 @@ int orgym_build_alias(const orgym_dist_t* d, int user_clamp, AliasDev* out, std:
 // host pmf used by the builder
 int orgym_dist_pmf(const orgym_dist_t* d, std::vector<double>* pmf, int64_t* base);
 
+__device__ const double c_rcp_tab[65] = {
+    0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11, 1.0 / 12, 1.0 / 13,
+    1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25,
+    1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37,
+    1.0 / 38, 1.0 / 39, 1.0 / 40, 1.0 / 41, 1.0 / 42, 1.0 / 43, 1.0 / 44, 1.0 / 45, 1.0 / 46, 1.0 / 47, 1.0 / 48, 1.0 / 49,
+    1.0 / 50, 1.0 / 51, 1.0 / 52, 1.0 / 53, 1.0 / 54, 1.0 / 55, 1.0 / 56, 1.0 / 57, 1.0 / 58, 1.0 / 59, 1.0 / 60, 1.0 / 61,
+    1.0 / 62, 1.0 / 63, 1.0 / 64};
+
 // log(k!) for integer-valued k >= 0: exact table below 16, Stirling series above (error < 2e-12)
 __device__ __forceinline__ double log_factorial(double k) {
     if (k < 16.0) {
@@ -123,6 +131,10 @@ __device__ __forceinline__ PoissonMu poisson_setup(double mu) {
     }
     return c;
 }
+// reciprocals 1/x for the small-mean inversion loop (no division on the hot path)
+__device__ __forceinline__ double small_rcp(int x) {
+    return x <= 64 ? c_rcp_tab[x] : 1.0 / (double)x;
+}
 template <bool FULL>
 __device__ __forceinline__ int64_t poisson_draw(const PoissonMu& c, uint64_t key, uint32_t episode, int t) {
     const double mu = c.mu;
@@ -130,10 +142,10 @@ __device__ __forceinline__ int64_t poisson_draw(const PoissonMu& c, uint64_t key
     if (mu < 10.0) {
         uint4 w = philox_block(key, (uint32_t)t, episode, STREAM_POISSON_MU, 0);
         double u = u53(w.x, w.y), p = c.e_or_loglam, s = p;
-        int64_t x = 0;
+        int x = 0;
         while (u > s && x < 200) {
             x += 1;
-            p *= mu / (double)x;
+            p *= mu * small_rcp(x);
             s += p;
         }
         return x;
@@ -141,12 +153,27 @@ __device__ __forceinline__ int64_t poisson_draw(const PoissonMu& c, uint64_t key
     for (uint32_t attempt = 0;; attempt++) {
         uint4 w = philox_block(key, (uint32_t)t, episode, STREAM_POISSON_MU, attempt);
         double U = u53(w.x, w.y) - 0.5, V = u53(w.z, w.w), us = 0.5 - fabs(U);
-        double kf = floor((2.0 * c.a / us + c.b) * U + mu + 0.43);
+        double kf = floor((2.0 * c.a * __drcp_rn(us) + c.b) * U + mu + 0.43);
         if (us >= 0.07 && V <= c.vr) return (int64_t)kf;  // squeeze: ~86 % of the draws end here
         if (kf < 0.0 || (us < 0.013 && V > us)) continue;
+        // acceptance test  log(V*inv_alpha/(a/us^2+b)) <= -mu + k*log(mu) - log(k!).  It is first evaluated with
+        // single-precision logarithms (a few instructions each); only when the two sides are closer than a rigorous
+        // bound on that evaluation's error is the float64 expression computed, so the decision is always the float64 one.
+        const double inv_alpha = FULL ? c.inv_alpha : 1.1239 + 1.1328 * __drcp_rn(c.b - 3.4);
+        const double arg = V * inv_alpha * __drcp_rn(c.a * __drcp_rn(us * us) + c.b);
+        {
+            const double x1 = kf + 1.0;
+            const double lf = kf < 16.0 ? log_factorial(kf)
+                                        : (x1 - 0.5) * (double)__logf((float)x1) - x1 + 0.91893853320467274178 +
+                                              (1.0 / 12.0) * (double)__frcp_rn((float)x1);
+            const double lhs = (double)__logf((float)arg);
+            const double rhs = -mu + kf * (double)__logf((float)mu) - lf;
+            const double tol = 3.0e-5 * (kf + 16.0);  // >= 10x the worst-case error of the three __logf calls
+            if (lhs < rhs - tol) return (int64_t)kf;
+            if (lhs > rhs + tol) continue;
+        }
         const double loglam = FULL ? c.e_or_loglam : log(mu);
-        const double inv_alpha = FULL ? c.inv_alpha : 1.1239 + 1.1328 / (c.b - 3.4);
-        if (log(V * inv_alpha / (c.a / (us * us) + c.b)) <= (-mu + kf * loglam - log_factorial(kf))) return (int64_t)kf;
+        if (log(arg) <= (-mu + kf * loglam - log_factorial(kf))) return (int64_t)kf;
         if (attempt > 1000u) return (int64_t)kf;  // unreachable in practice; bounds the loop
     }
 }

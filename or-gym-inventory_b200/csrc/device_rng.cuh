@@ -69,10 +69,15 @@ __host__ __device__ __forceinline__ uint4 philox_block(uint64_t key, uint32_t c0
     return philox4x32_10(make_uint4(c0, episode, stream, c3), (uint32_t)key, (uint32_t)(key >> 32));
 }
 
-// 53-bit uniform in [0,1) from two 32-bit words (same construction as numpy's next_double)
+// uniform in [0,1) with 52 random bits from two 32-bit words: the bits become the mantissa of a double in [1,2)
+// (two logic ops and one subtraction instead of a 64-bit integer-to-double conversion)
 __host__ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)lo) - 1.0;
+#else
     uint64_t x = ((uint64_t)hi << 32) | lo;
-    return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+    return (double)(x >> 12) * (1.0 / 4503599627370496.0);
+#endif
 }
 
 // one alias-table draw from ONE 32-bit random word: the top log2k bits pick the bucket, the remaining bits

@@ -514,6 +514,7 @@ struct InvRolloutArgs {
     double* reward_traj;
     int64_t* final_I;
     int64_t* final_B;
+    int32_t* stats32;
     double* partials;  // [gridDim.x][8]
 };
 
@@ -650,6 +651,10 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
         if (A.stats) {
             longlong4 v = make_longlong4(s_sales, s_dem, s_stock, s_inv);
             *reinterpret_cast<longlong4*>(A.stats + e * 4) = v;
+        }
+        if (A.stats32) {
+            auto sat = [](long long v) { return (int)(v > 2147483647LL ? 2147483647LL : (v < -2147483648LL ? -2147483648LL : v)); };
+            *reinterpret_cast<int4*>(A.stats32 + e * 4) = make_int4(sat(s_sales), sat(s_dem), sat(s_stock), sat(s_inv));
         }
         if (A.final_I)
             for (int i = 0; i < n; i++) A.final_I[e * n + i] = (int64_t)I[i];
@@ -1001,6 +1006,7 @@ extern "C" int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t en
     A.reward_traj = out->reward_traj_dev;
     A.final_I = out->final_I_dev;
     A.final_B = out->final_B_dev;
+    A.stats32 = out->stats32_dev;
     A.partials = out->summary_dev ? H->partials : nullptr;
     // pre-staged actions may be arbitrary int64 -> exact wide arithmetic; on-device policies stay inside [0, c]
     const bool wide = H->wide || in->policy == ORGYM_POLICY_ACTIONS;

@@ -33,7 +33,8 @@ struct NetHandle {
     std::vector<void*> allocs;
     double* partials;
     // run-time specialised kernel (netinv_jit.cu); jit.fn == nullptr -> generic kernel
-    JitKernel jit;
+    JitKernel jit;             // module + STEP kernel
+    cudaKernel_t jit_rollout;  // ROLLOUT kernel of the same module
     int jit_threads;
     AliasDev* dem_dev;  // device copy of dev.dem[] for the specialised kernel
 };

@@ -61,8 +61,11 @@ std::string net_jit_source(const NetDev& P, int nthr) {
         }
     }
     o("}");
-    // ---- kernel
-    o("extern \"C\" __global__ void __launch_bounds__(NTHR) net_jit_kernel(const NetSimArgs A, const double* __restrict__ disc,");
+    // ---- kernels: the same period body is emitted twice, with the mode fixed at compile time.  STEP is bound by HBM
+    // latency and wants many resident warps (<= 102 registers -> 5 CTAs/SM); ROLLOUT is issue-bound and wants no spills.
+    auto emit_kernel = [&](const char* kname, int rollout, int min_blocks) {
+    o("#define ROLL %d", rollout);
+    o("extern \"C\" __global__ void __launch_bounds__(NTHR, %d) %s(const NetSimArgs A, const double* __restrict__ disc,", min_blocks, kname);
     o("    const AliasDev* __restrict__ dem) {");
     o("  extern __shared__ __align__(16) unsigned char smem[];");
     o("  float* otile = (float*)smem;");
@@ -91,7 +94,7 @@ std::string net_jit_source(const NetDev& P, int nthr) {
         o("%sfor (int k = 0; k < NSUML; k++) ring[(long long)k * np + e] = 0.0;", ind);
         o("%ss_period[e] = 0;", ind);
     };
-    o("  if (A.rollout) {");
+    o("  if (ROLL) {");
     o("    key = A.seed + (unsigned long long)(A.env_offset + e); episode = A.episode; t0 = 0; t1 = NT;");
     emit_reset_regs("    ");
     o("    if (valid) for (int k = 0; k < NSUML; k++) ring[(long long)k * np + e] = 0.0;");
@@ -118,7 +121,7 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     o("    }");
     o("  }");
     o("  double ret = 0.0, s_sales = 0.0, s_dem = 0.0, s_unf = 0.0, s_inv = 0.0, last_reward = 0.0;");
-    o("  if (!A.rollout && !do_step) t1 = t0;");
+    o("  if (!ROLL && !do_step) t1 = t0;");
     o("  for (int t = t0; t < t1; t++) {");
     // arrivals: all ring loads up front (independent -> overlapped)
     for (int i = 0; i < E; i++)
@@ -126,7 +129,7 @@ std::string net_jit_source(const NetDev& P, int nthr) {
             o("    const long long sl%d = (long long)(%d + t %% %d) * np + ec;", i, P.roff[i], P.L[i]);
             o("    const double Ar%d = ring[sl%d];", i, i);
         }
-    o("    const float* arow = A.policy == ORGYM_NET_POLICY_CONSTANT ? A.actions : A.actions + ec * A.a_se + (long long)(A.rollout ? t : 0) * A.a_st;");
+    o("    const float* arow = A.policy == ORGYM_NET_POLICY_CONSTANT ? A.actions : A.actions + ec * A.a_se + (long long)(ROLL ? t : 0) * A.a_st;");
     // 0) orders (:448-490)
     for (int j = 0; j < J; j++) o("    Cn[%d] = 0.0;", j);
     o("    double cons = 0.0;");
@@ -179,13 +182,13 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     for (int r = 0; r < M; r++) {
         const int j = P.rt_node[r];
         o("    { double d;");
-        o("      if (A.demand) d = rint(A.demand[ec * A.d_se + (long long)(A.rollout ? t : 0) * A.d_st + %d]);", r);
+        o("      if (A.demand) d = rint(A.demand[ec * A.d_se + (long long)(ROLL ? t : 0) * A.d_st + %d]);", r);
         o("      else d = (double)sample_fixed(dem[%d], dem[%d].table, key, episode, t, %du);", r, r, r);
         o("      d = d > 0.0 ? d : 0.0;");
         o("      double fill = d + U[%d]; double x = X[%d]; double invr = x > 0.0 ? x : 0.0;", r, j);
         o("      double sl = invr < fill ? invr : fill; S[%d] = sl; X[%d] = x - sl; double un = fill - sl;", r, j);
         o("      U[%d] = %s; s_sales += sl; s_dem += d; s_unf += %s;", r, P.backlog ? "un" : "0.0", P.backlog ? "un" : "0.0");
-        o("      if (!A.rollout && A.info_demand && do_step) A.info_demand[e * NM + %d] = d; }", r);
+        o("      if (!ROLL && A.info_demand && do_step) A.info_demand[e * NM + %d] = d; }", r);
     }
     // 5) profit (:578-613)
     o("    double total = 0.0;");
@@ -216,11 +219,11 @@ std::string net_jit_source(const NetDev& P, int nthr) {
                 o("      OC = %s * (sold / %s);", lit(P.o[j]).c_str(), lit(P.v[j]).c_str());
         }
         o("      (void)sold; double pj = (((SR - PC) - OC) - HC) - UP; total += pj; s_inv += xp;");
-        o("      if (!A.rollout && A.info_profit && do_step) A.info_profit[e * NJ + %d] = pj; }", j);
+        o("      if (!ROLL && A.info_profit && do_step) A.info_profit[e * NJ + %d] = pj; }", j);
     }
     o("    last_reward = disc[t] * total; ret += last_reward;");
-    o("    if (A.rollout && A.reward_traj && valid) A.reward_traj[e * NT + t] = last_reward;");
-    o("    if (!A.rollout && do_step) {");
+    o("    if (ROLL && A.reward_traj && valid) A.reward_traj[e * NT + t] = last_reward;");
+    o("    if (!ROLL && do_step) {");
     o("      if (A.info_profit_total) A.info_profit_total[e] = total;");
     o("      if (A.info_sales) {");
     for (int i = 0; i < E; i++) o("        A.info_sales[e * (NE + NM) + %d] = R[%d];", i, i);
@@ -229,7 +232,7 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     o("    }");
     o("  }");  // t loop
     // ---- epilogue: ROLLOUT
-    o("  if (A.rollout) {");
+    o("  if (ROLL) {");
     o("    if (valid) {");
     o("      if (A.ep_return) A.ep_return[e] = ret;");
     o("      if (A.stats) { A.stats[e * 4 + 0] = s_sales; A.stats[e * 4 + 1] = s_dem; A.stats[e * 4 + 2] = s_unf; A.stats[e * 4 + 3] = s_inv; }");
@@ -279,6 +282,13 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     o("    for (int i = tid; i < total; i += NTHR) { const int r = i / NOBS, c = i - r * NOBS; __stcs(g + i, otile[r * OSTRIDE + c]); }");
     o("  }");
     o("}");
+    o("#undef ROLL");
+    };
+    int mb_step = 5, mb_roll = 3;
+    if (const char* mb = getenv("ORGYM_NET_JIT_MINBLOCKS_STEP")) mb_step = atoi(mb) > 0 ? atoi(mb) : 1;
+    if (const char* mb = getenv("ORGYM_NET_JIT_MINBLOCKS_ROLLOUT")) mb_roll = atoi(mb) > 0 ? atoi(mb) : 1;
+    emit_kernel("net_jit_step", 0, mb_step);
+    emit_kernel("net_jit_rollout", 1, mb_roll);
     return o.s;
 }
 
@@ -286,8 +296,14 @@ int net_jit_build(NetHandle* H, std::string* err) {
     const NetDev& P = H->dev;
     H->jit_threads = 128;
     std::string src = net_jit_source(P, H->jit_threads);
-    int rc = orgym_jit_compile(src, "net_jit_kernel", &H->jit, err);
+    int rc = orgym_jit_compile(src, "net_jit_step", &H->jit, err);
     if (rc != 0) return rc;
+    if (cudaLibraryGetKernel(&H->jit_rollout, H->jit.lib, "net_jit_rollout") != cudaSuccess) {
+        *err = "net_jit_rollout missing from the specialised module";
+        cudaGetLastError();
+        orgym_jit_release(&H->jit);
+        return 11;
+    }
     // device copy of the per-link demand descriptors
     H->dem_dev = nullptr;
     if (cudaMalloc(&H->dem_dev, sizeof(AliasDev) * (size_t)(P.M > 0 ? P.M : 1)) != cudaSuccess) {
@@ -298,6 +314,7 @@ int net_jit_build(NetHandle* H, std::string* err) {
     H->allocs.push_back(H->dem_dev);
     if (P.M > 0) cudaMemcpy(H->dem_dev, P.dem, sizeof(AliasDev) * (size_t)P.M, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute((const void*)H->jit.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute((const void*)H->jit_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaGetLastError();
     return 0;
 }
@@ -317,7 +334,7 @@ int net_jit_launch(const NetHandle* H, const NetSimArgs& A_in, cudaStream_t s) {
     const AliasDev* dem = H->dem_dev;
     void* args[] = {(void*)&A, (void*)&disc, (void*)&dem};
     unsigned grid = (unsigned)((A.N + nthr - 1) / nthr);
-    cudaError_t e = cudaLaunchKernel((const void*)H->jit.fn, dim3(grid), dim3(nthr), args, smem, s);
+    cudaError_t e = cudaLaunchKernel((const void*)(A.rollout ? H->jit_rollout : H->jit.fn), dim3(grid), dim3(nthr), args, smem, s);
     if (e != cudaSuccess) {
         orgym_set_error("specialised network kernel launch failed: %s", cudaGetErrorString(e));
         return ORGYM_E_CUDA;

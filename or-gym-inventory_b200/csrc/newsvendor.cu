@@ -248,8 +248,18 @@ __global__ void __launch_bounds__(ORGYM_TILE) nv_step_kernel(const __grid_consta
         if (do_step) {
             const float* pp = st.pipe + e;
             const int64_t np_ = A.npad;
-            float psum = nv_pipe_sum(P.L, [&](int j) { return pp[(size_t)j * np_]; });
-            float pipe0 = P.L > 0 ? pp[0] : 0.0f;
+            // stage the pipeline in this env's row of the observation tile: loads are issued in batches of 8 so that
+            // their latencies overlap (a load-add chain would serialise them); the sum then runs out of shared memory
+            for (int j0 = 0; j0 < P.L; j0 += 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = (j0 + u < P.L) ? pp[(size_t)(j0 + u) * np_] : 0.0f;
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (j0 + u < P.L) row[5 + j0 + u] = v[u];
+            }
+            float psum = nv_pipe_sum(P.L, [&](int j) { return row[5 + j]; });
+            float pipe0 = P.L > 0 ? row[5] : 0.0f;
             long long d = A.demand ? A.demand[e] : poisson_mu(q.mu, key, ep, sc);
             float oq;
             double parts[4];
@@ -258,7 +268,7 @@ __global__ void __launch_bounds__(ORGYM_TILE) nv_step_kernel(const __grid_consta
             bool trunc = sc1 >= P.T;  // :190
             bool reset_now = trunc && A.autoreset == ORGYM_AUTORESET_SAME_STEP;
             for (int z = 0; z < 5; z++) row[z] = (float)(&q.price)[z];
-            for (int j = 0; j + 1 < P.L; j++) row[5 + j] = pp[(size_t)(j + 1) * np_];  // shift left (:177)
+            for (int j = 0; j + 1 < P.L; j++) row[5 + j] = row[5 + j + 1];  // shift left (:177)
             if (P.L > 0) row[5 + P.L - 1] = oq;
             if (!reset_now) {
                 float* pw = st.pipe + e;

@@ -249,7 +249,7 @@ class InvManagementMasterEnv(BatchedEnv):
 
     # -- fused rollout ------------------------------------------------------------------------------------------------
     def rollout(self, policy="base_stock", *, seed=None, episode=0, safety_factor=1.0, mu=None, actions=None,
-                demand=None, time_major=False, want=("ep_return", "stats", "summary")):
+                demand=None, time_major=False, want=("ep_return", "stats", "summary"), buffer_set=0):
         """Fused reset + `periods` steps with state held on chip (K4).
 
         policy: 'base_stock' (benchmark_InvManagementBacklogEnv.py:142-198), 'random' (a_i ~ U{0..c_i}),
@@ -257,7 +257,8 @@ class InvManagementMasterEnv(BatchedEnv):
         demand: optional int64 [N,T] ([T,N] if time_major) replayed demand; default = on-device Philox sampling.
         Returns a dict of device tensors: ep_return f64[N], stats i64[N,4] (sum sales[0], sum demand,
         sum unfulfilled[0], sum_t sum_i max(0,I_i)), summary f64[8], and on request reward_traj f64[N,T],
-        final_I, final_B.
+        final_I, final_B, stats32 (the statistics as int32).  The result tensors are owned by the env and reused by
+        the next rollout that uses the same `buffer_set`.
         """
         torch = _torch()
         P = self.params
@@ -289,10 +290,10 @@ class InvManagementMasterEnv(BatchedEnv):
         dev = self.device
         shapes = dict(ep_return=((N,), torch.float64), stats=((N, 4), torch.int64),
                       reward_traj=((N, T), torch.float64), final_I=((N, n), torch.int64),
-                      final_B=((N, m), torch.int64), summary=((8,), torch.float64))
+                      final_B=((N, m), torch.int64), summary=((8,), torch.float64), stats32=((N, 4), torch.int32))
+        cache = self.__dict__.setdefault("_rollout_buf", {}).setdefault(int(buffer_set), {})
         for name in want:
             shp, dt = shapes[name]
-            cache = self.__dict__.setdefault("_rollout_buf", {})
             if name not in cache:
                 cache[name] = torch.zeros(shp, dtype=dt, device=dev)
             out[name] = cache[name]

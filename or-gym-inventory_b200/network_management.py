@@ -413,7 +413,7 @@ class NetInvMgmtMasterEnv(BatchedEnv):
         return self.export_state()[3]
 
     def rollout(self, policy="constant", *, seed=None, episode=0, order_fraction=0.1, actions=None, demand=None,
-                time_major=False, want=("ep_return", "stats", "summary")):
+                time_major=False, want=("ep_return", "stats", "summary"), buffer_set=0):
         """Fused reset + num_periods steps (K5).  policy 'constant': the ConstantOrderAgent action
         (high * order_fraction as float32, benchmark_NetInvMgmtBacklogEnv.py:119-136) or an explicit float32[E]
         `actions` vector; policy 'actions': float32 [N,T,E] ([T,N,E] if time_major).  demand: optional float64
@@ -447,7 +447,7 @@ class NetInvMgmtMasterEnv(BatchedEnv):
                       final_Y=((N, E), torch.float64), final_U=((N, M), torch.float64), summary=((8,), torch.float64))
         out = {}
         rout = _capi.NetRolloutOut()
-        cache = self.__dict__.setdefault("_rollout_buf", {})
+        cache = self.__dict__.setdefault("_rollout_buf", {}).setdefault(int(buffer_set), {})
         for name in want:
             shp, dt = shapes[name]
             if name not in cache:

@@ -145,7 +145,7 @@ class NewsvendorEnv(BatchedEnv):
         return out
 
     def rollout(self, policy="classic", *, seed=None, episode=0, safety_factor=1.0, S_factor=1.2, actions=None,
-                demand=None, fixed_params=None, time_major=False, want=("ep_return", "stats", "summary")):
+                demand=None, fixed_params=None, time_major=False, want=("ep_return", "stats", "summary"), buffer_set=0):
         """Fused reset + step_limit periods (K1/K2).  policy: 'order_up_to' | 'classic' | 'sS' | 'actions'
         (float32 [N,T] or [T,N]).  Returns device tensors: ep_return f64[N], stats f64[N,4] (sum sales units,
         demand, lost units, excess units), summary f64[8]; on request reward_traj, action_traj, final_obs."""
@@ -175,7 +175,7 @@ class NewsvendorEnv(BatchedEnv):
                       final_obs=((N, P.obs_dim), torch.float32), summary=((8,), torch.float64))
         out = {}
         rout = _capi.NvRolloutOut()
-        cache = self.__dict__.setdefault("_rollout_buf", {})
+        cache = self.__dict__.setdefault("_rollout_buf", {}).setdefault(int(buffer_set), {})
         for name in want:
             shp, dt = shapes[name]
             if name not in cache:

@@ -131,6 +131,46 @@ class BatchedEnv(_VectorEnvBase):
         if bits & _capi.ERR_INT32_RANGE:
             raise OverflowError("a state value left the int32 range; construct the env with wide_state=True")
 
+    def evaluate(self, policy, episodes=1, *, seed=None, first_episode=0, want=("ep_return", "stats", "summary"),
+                 **policy_kwargs):
+        """The reference's `evaluate_agent` loop (e.g. benchmark_InvManagementLostSalesEnv.py:239-302) for the whole batch:
+        yields, per episode index, a dict of HOST (pinned) numpy-backed tensors with the per-instance results.
+        Rollout k+1 runs on the GPU while the results of rollout k are copied to the host on a second stream
+        (two device buffer sets + two pinned host buffer sets); a yielded dict stays valid until two more
+        episodes have been yielded."""
+        torch = _torch()
+        main = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._host_sets = {}
+        copy_done = [None, None]
+        pending = None
+        for k in range(int(episodes)):
+            b = k & 1
+            if copy_done[b] is not None:
+                main.wait_event(copy_done[b])          # device buffers of set b are free again
+            out = self.rollout(policy, seed=seed if k == 0 else None, episode=first_episode + k, want=want,
+                               buffer_set=b, **policy_kwargs)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            host = self._host_sets.setdefault(b, {})
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(ready)
+                for name, t in out.items():
+                    if name not in host:
+                        host[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                    host[name].copy_(t, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(self._copy_stream)
+            copy_done[b] = done
+            if pending is not None:
+                pending[1].synchronize()
+                yield pending[0]
+            pending = (host, done)
+        if pending is not None:
+            pending[1].synchronize()
+            yield pending[0]
+
     def close(self):
         if not getattr(self, "closed", True) and getattr(self, "_h", None):
             destroy = getattr(_capi.lib(), f"orgym_{self._family}_destroy")

@@ -87,4 +87,4 @@ def test_network_kernel_specialiser_compiles_without_gpu(lib, kind):
     rc = lib.orgym_netinv_codegen(C.byref(cfg), 1, buf, len(buf), C.byref(need))
     assert rc == 0, lib.orgym_last_error()
     src = buf.value.decode()
-    assert len(src) == need.value and "net_jit_kernel" in src and f"#define NE {len(P.reorder_links)}" in src
+    assert len(src) == need.value and "net_jit_step" in src and "net_jit_rollout" in src and f"#define NE {len(P.reorder_links)}" in src
