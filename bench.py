@@ -139,7 +139,7 @@ def cpu_port_rate(workload, seconds=10.0, threads=None):
                        f"Poisson demand, {dt:.1f} s on {threads} threads")
 
 
-def main_reference(args):
+def main_reference(args, emit):
     """--impl reference: the CPU implementation of the path on the box's host cores (oracle port; the Python
     reference itself cannot travel -- /root/reference does not exist on the GPU box)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -177,14 +177,21 @@ def main_reference(args):
             "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port",
                              "sample": f"{eps_per_step} episodes per step x {args.steps} steps, all {threads} host threads"},
             "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    # keep stdout clean for the ONE JSON line: libraries (e.g. NCCL's version banner) write to fd 1
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
-        return main_reference(args)
+        return main_reference(args, emit)
     import torch
     import torch.distributed as dist
     import or_gym_inventory_b200 as pkg
@@ -328,7 +335,8 @@ def main():
         c = counts.get(args.workload, {})
         roof = {"kernel": kernel, "bound": "issue", "unit": "warp-inst/s", "peak": issue_peak,
                 "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)",
-                "kernel_ms": kms, "achieved": None, "frac": None, "traffic": c.get("dram_bytes_per_launch"),
+                "kernel_ms": kms, "achieved": None, "frac": None,
+                "traffic": (c["dram_bytes_per_env_step"] * N * T) if c.get("dram_bytes_per_env_step") else None,
                 "hbm": {"achieved_gbs": alg_bytes / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                         "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": alg_bytes,
                         "peak_source": peak_src}}
@@ -365,7 +373,7 @@ def main():
         ach = N * ab / (sms * 1e-3) / 1e9
         line["roofline_step_api"] = {"kernel": sk, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                                      "frac": ach / hbm_peak,
-                                     "traffic": counts.get(args.workload + "_step", {}).get("dram_bytes_per_launch"),
+                                     "traffic": (counts.get(args.workload + "_step", {}).get("dram_bytes_per_env_step") or 0) * N or None,
                                      "kernel_ms": sms, "env_steps_per_s": N / (sms * 1e-3),
                                      "algorithmic_bytes_per_env_step": ab, "instances": N, "peak_source": peak_src,
                                      "note": "info tensors (demand/sales/unfulfilled/profit) are written too; they are "
@@ -376,7 +384,7 @@ def main():
         torch.cuda.empty_cache()
         line["cpu_baseline"] = cpu_port_rate(args.workload, seconds=10.0)
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

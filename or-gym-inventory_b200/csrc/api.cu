@@ -211,6 +211,25 @@ int orgym_build_alias(const orgym_dist_t* d, int user_clamp, AliasDev* out, std:
 }
 
 // ------------------------------------------------------------------------------------------------
+// reciprocal table used by the Poisson recurrences (common.cuh)
+// ------------------------------------------------------------------------------------------------
+int orgym_rcp_table(int device, const double** out) {
+    static double* tabs[64] = {nullptr};
+    ORGYM_REQUIRE(device >= 0 && device < 64, "device index out of range");
+    if (!tabs[device]) {
+        DeviceGuard g(device);
+        std::vector<double> h(ORGYM_RCP_N + 1, 0.0);
+        for (int k = 1; k <= ORGYM_RCP_N; k++) h[(size_t)k] = 1.0 / (double)k;
+        double* d = nullptr;
+        ORGYM_CUDA(cudaMalloc(&d, sizeof(double) * h.size()));
+        ORGYM_CUDA(cudaMemcpy(d, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+        tabs[device] = d;
+    }
+    *out = tabs[device];
+    return ORGYM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K6: stand-alone samplers for the statistical tests
 // ------------------------------------------------------------------------------------------------
 __global__ void sample_fixed_kernel(AliasDev A, uint64_t seed, int64_t env_offset, int64_t count, int per_env,
@@ -245,20 +264,77 @@ extern "C" int orgym_sample_demand(const orgym_dist_t* dist, uint64_t seed, int6
     return rc;
 }
 
-__global__ void sample_poisson_mu_kernel(const double* __restrict__ mu, uint64_t seed, int64_t env_offset, int64_t count,
-                                         int period, int64_t* __restrict__ out) {
+__global__ void sample_poisson_mu_kernel(const double* __restrict__ mu, const double* __restrict__ rcp, uint64_t seed,
+                                         int64_t env_offset, int64_t count, int period, int64_t* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    out[i] = poisson_mu(mu[i], seed + (uint64_t)(env_offset + i), 0u, period);
+    out[i] = poisson_mu(mu[i], rcp, seed + (uint64_t)(env_offset + i), 0u, period);
 }
 
 extern "C" int orgym_sample_poisson_mu(const double* mu_dev, uint64_t seed, int64_t env_offset, int64_t count,
                                        int32_t period, int device, int64_t* out_dev, void* stream) {
     ORGYM_REQUIRE(mu_dev && out_dev && count > 0, "bad arguments");
     ORGYM_REQUIRE(orgym_device_count() > 0, "no CUDA device");
+    const double* rcp = nullptr;
+    if (int rc = orgym_rcp_table(device, &rcp)) return rc;
     DeviceGuard g(device);
-    sample_poisson_mu_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mu_dev, seed, env_offset,
+    sample_poisson_mu_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mu_dev, rcp, seed, env_offset,
                                                                                               count, period, out_dev);
+    ORGYM_CUDA(cudaGetLastError());
+    return ORGYM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic summary reduction (see common.cuh)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) orgym_reduce_partials_kernel(const double* __restrict__ partials, int nrows,
+                                                                    double* __restrict__ scratch,
+                                                                    unsigned int* __restrict__ ticket,
+                                                                    double* __restrict__ out) {
+    const int tid = threadIdx.x, nb = gridDim.x;
+    const int rpb = (nrows + nb - 1) / nb;
+    const int r0 = blockIdx.x * rpb, r1 = min(nrows, r0 + rpb);
+    double v[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int r = r0 + tid; r < r1; r += 256) {
+        const double4 a = *reinterpret_cast<const double4*>(partials + (size_t)r * 8);
+        const double4 b = *reinterpret_cast<const double4*>(partials + (size_t)r * 8 + 4);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z;
+    }
+    __shared__ double red[8][7];
+    __shared__ int is_last;
+#pragma unroll
+    for (int q = 0; q < 7; q++) {
+        double x = v[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((tid & 31) == 0) red[tid >> 5][q] = x;
+    }
+    __syncthreads();
+    if (tid < 7) {
+        double x = 0.0;
+        for (int w = 0; w < 8; w++) x += red[w][tid];
+        scratch[(size_t)blockIdx.x * 8 + tid] = x;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicInc(ticket, (unsigned)nb - 1u) == (unsigned)nb - 1u);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (tid < 8) {
+            double x = 0.0;
+            if (tid < 7)
+                for (int b = 0; b < nb; b++) x += __ldcg(scratch + (size_t)b * 8 + tid);
+            out[tid] = x;
+        }
+    }
+}
+
+int orgym_launch_reduce(double* partials, int nrows, double* out_dev, cudaStream_t s) {
+    double* scratch = partials + (size_t)nrows * 8;
+    unsigned int* ticket = (unsigned int*)(scratch + ORGYM_REDUCE_CTAS * 8);
+    int nb = nrows < 4096 ? 1 : ORGYM_REDUCE_CTAS;
+    orgym_reduce_partials_kernel<<<nb, 256, 0, s>>>(partials, nrows, scratch, ticket, out_dev);
     ORGYM_CUDA(cudaGetLastError());
     return ORGYM_OK;
 }

@@ -82,6 +82,15 @@ int orgym_build_alias(const orgym_dist_t* d, int user_clamp, AliasDev* out, std:
 // host pmf used by the builder
 int orgym_dist_pmf(const orgym_dist_t* d, std::vector<double>* pmf, int64_t* base);
 
+// exact reciprocals 1/k for 1 <= k <= 2048 (16 KB, L1-resident): the Poisson recurrences p_k = p_{k-1} * mu / k use
+// a table load and a multiply instead of a float64 division.  Filled once per device by orgym_init_tables().
+#define ORGYM_RCP_N 2048
+// device pointer to the table of `device` (allocated and filled on first use, kept for the life of the process)
+int orgym_rcp_table(int device, const double** out);
+__device__ __forceinline__ double rcp_int(const double* __restrict__ tab, double k) {
+    return k <= (double)ORGYM_RCP_N ? tab[(int)k] : __drcp_rn(k);
+}
+
 __device__ const double c_rcp_tab[65] = {
     0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11, 1.0 / 12, 1.0 / 13,
     1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25,
@@ -110,12 +119,14 @@ __device__ __forceinline__ double log_factorial(double k) {
 // Keyed by (key, episode, t); rejection attempts advance counter word 3.
 struct PoissonMu {
     double mu, b, a, vr, e_or_loglam, inv_alpha;  // e_or_loglam: exp(-mu) for mu < 10, log(mu) otherwise
+    const double* rcp;                            // reciprocal table (orgym_rcp_table)
 };
 // full = false: only what the squeeze (fast acceptance) needs; the rest is computed on demand in the slow path
 template <bool FULL>
-__device__ __forceinline__ PoissonMu poisson_setup(double mu) {
+__device__ __forceinline__ PoissonMu poisson_setup(double mu, const double* rcp) {
     PoissonMu c;
     c.mu = mu;
+    c.rcp = rcp;
     c.b = c.a = c.vr = c.e_or_loglam = c.inv_alpha = 0.0;
     if (!(mu > 0.0)) return c;
     if (mu < 10.0) {
@@ -145,14 +156,19 @@ __device__ __forceinline__ int64_t poisson_draw(const PoissonMu& c, uint64_t key
         int x = 0;
         while (u > s && x < 200) {
             x += 1;
-            p *= mu * small_rcp(x);
+            p *= mu * c.rcp[x];
             s += p;
         }
         return x;
     }
+    // Each rejection attempt consumes two 32-bit uniforms (U and V are only compared / passed through smooth
+    // functions, so 2^-32 resolution is far below any statistical visibility); one Philox block feeds two attempts.
+    uint4 w = make_uint4(0, 0, 0, 0);
     for (uint32_t attempt = 0;; attempt++) {
-        uint4 w = philox_block(key, (uint32_t)t, episode, STREAM_POISSON_MU, attempt);
-        double U = u53(w.x, w.y) - 0.5, V = u53(w.z, w.w), us = 0.5 - fabs(U);
+        if ((attempt & 1u) == 0) w = philox_block(key, (uint32_t)t, episode, STREAM_POISSON_MU, attempt >> 1);
+        const uint32_t wu = (attempt & 1u) ? w.z : w.x, wv = (attempt & 1u) ? w.w : w.y;
+        const double U = ((double)wu + 0.5) * (1.0 / 4294967296.0) - 0.5, V = ((double)wv + 0.5) * (1.0 / 4294967296.0);
+        const double us = 0.5 - fabs(U);
         double kf = floor((2.0 * c.a * __drcp_rn(us) + c.b) * U + mu + 0.43);
         if (us >= 0.07 && V <= c.vr) return (int64_t)kf;  // squeeze: ~86 % of the draws end here
         if (kf < 0.0 || (us < 0.013 && V > us)) continue;
@@ -177,8 +193,8 @@ __device__ __forceinline__ int64_t poisson_draw(const PoissonMu& c, uint64_t key
         if (attempt > 1000u) return (int64_t)kf;  // unreachable in practice; bounds the loop
     }
 }
-__device__ __forceinline__ int64_t poisson_mu(double mu, uint64_t key, uint32_t episode, int t) {
-    PoissonMu c = poisson_setup<false>(mu);
+__device__ __forceinline__ int64_t poisson_mu(double mu, const double* rcp, uint64_t key, uint32_t episode, int t) {
+    PoissonMu c = poisson_setup<false>(mu, rcp);
     return poisson_draw<false>(c, key, episode, t);
 }
 
@@ -263,5 +279,12 @@ __device__ __forceinline__ void st_stream(T* p, T v) {
 }
 
 #define ORGYM_TILE 128  // env instances per CTA in the step kernels
+
+// Deterministic reduction of per-CTA partial sums ([nrows][8] float64, columns 0..6 used) into out[8]:
+// up to 128 CTAs reduce contiguous row ranges in a fixed order, the last CTA to finish (ticket) adds their results
+// in CTA order.  `partials` must have room for ORGYM_REDUCE_EXTRA more doubles after the nrows*8 entries.
+#define ORGYM_REDUCE_CTAS 128
+#define ORGYM_REDUCE_EXTRA (ORGYM_REDUCE_CTAS * 8 + 8)
+int orgym_launch_reduce(double* partials, int nrows, double* out_dev, cudaStream_t s);
 
 static inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }

@@ -570,11 +570,11 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
             if (A.target_is_int) {
 #pragma unroll
                 for (int i = 0; i < NS; i++)
-                    if (EXACT || i < n) {
-                        long long q = A.target_int[i] - (long long)(I[i] + psum[i]);
+                    if (EXACT || i < n) {  // |target|, |I + psum| < 2^30 (range guard): no overflow in S
+                        S q = (S)A.target_int[i] - (I[i] + psum[i]);
                         q = q > 0 ? q : 0;
-                        q = q < P.c[i] ? q : P.c[i];
-                        req[i] = (S)q;
+                        q = q < (S)P.c[i] ? q : (S)P.c[i];
+                        req[i] = q;
                     }
             } else {
 #pragma unroll
@@ -686,17 +686,6 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
             A.partials[(size_t)blockIdx.x * 8 + tid] = x;
         }
     }
-}
-
-__global__ void orgym_reduce_partials_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out) {
-    // one warp per column; fixed summation order -> run-to-run deterministic
-    int col = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (col >= 8) return;
-    double x = 0.0;
-    for (int b = lane; b < nblocks; b += 32) x += col < 7 ? partials[(size_t)b * 8 + col] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if (lane == 0) out[col] = x;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -826,8 +815,12 @@ extern "C" int orgym_invmgmt_create(const orgym_invmgmt_config_t* cfg, int64_t n
     H->max_blocks = (int)((num_envs + ROLL_THREADS - 1) / ROLL_THREADS);
     H->partials = nullptr;
     if (ce == cudaSuccess) {
-        ce = cudaMalloc(&H->partials, sizeof(double) * 8 * (size_t)H->max_blocks);
-        if (ce == cudaSuccess) H->allocs.push_back(H->partials);
+        size_t pbytes = sizeof(double) * (8 * (size_t)H->max_blocks + ORGYM_REDUCE_EXTRA);
+        ce = cudaMalloc(&H->partials, pbytes);
+        if (ce == cudaSuccess) {
+            H->allocs.push_back(H->partials);
+            ce = cudaMemset(H->partials, 0, pbytes);  // also zeroes the reduction ticket
+        }
     }
     if (ce != cudaSuccess) {
         orgym_set_error("device allocation failed: %s", cudaGetErrorString(ce));
@@ -1024,8 +1017,8 @@ extern "C" int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t en
     ORGYM_CUDA(cudaGetLastError());
     if (out->summary_dev) {
         int nblocks = (int)((A.N + ROLL_THREADS - 1) / ROLL_THREADS);
-        orgym_reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(H->partials, nblocks, out->summary_dev);
-        ORGYM_CUDA(cudaGetLastError());
+        int rr = orgym_launch_reduce(H->partials, nblocks, out->summary_dev, (cudaStream_t)stream);
+        if (rr != ORGYM_OK) return rr;
     }
     return ORGYM_OK;
 }

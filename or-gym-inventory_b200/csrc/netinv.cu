@@ -367,7 +367,6 @@ __global__ void net_export_kernel(const __grid_constant__ NetDev P, int64_t N, i
     if (period) period[e] = st.period[e];
 }
 
-__global__ void orgym_reduce_partials_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out);
 
 static void net_launch(const NetHandle* H, const NetSimArgs& A, size_t smem, cudaStream_t s) {
     unsigned grid = (unsigned)((A.N + H->threads - 1) / H->threads);
@@ -515,8 +514,10 @@ extern "C" int orgym_netinv_create(const orgym_netinv_config_t* c, int64_t num_e
             H->smem = per_thread * H->threads;
             int nblocks = (int)((num_envs + 31) / 32);  // enough for any block size
             H->partials = nullptr;
-            if (cudaMalloc(&H->partials, 64 * (size_t)nblocks) != cudaSuccess) FAIL(ORGYM_E_CUDA, "device allocation failed");
+            size_t pbytes = sizeof(double) * (8 * (size_t)nblocks + ORGYM_REDUCE_EXTRA);
+            if (cudaMalloc(&H->partials, pbytes) != cudaSuccess) FAIL(ORGYM_E_CUDA, "device allocation failed");
             H->allocs.push_back(H->partials);
+            cudaMemset(H->partials, 0, pbytes);
             if (P.T > (1 << 20)) FAIL(ORGYM_E_UNSUPPORTED, "num_periods above 2^20 is not supported");
             cudaFuncSetAttribute(net_sim_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
             cudaFuncSetAttribute(net_sim_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
@@ -690,8 +691,8 @@ extern "C" int orgym_netinv_rollout(orgym_handle_t h, void* scratch_dev, uint64_
         net_launch(H, A, H->smem, (cudaStream_t)stream);
     ORGYM_CUDA(cudaGetLastError());
     if (out->summary_dev) {
-        orgym_reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(H->partials, nblocks, out->summary_dev);
-        ORGYM_CUDA(cudaGetLastError());
+        int rr = orgym_launch_reduce(H->partials, nblocks, out->summary_dev, (cudaStream_t)stream);
+        if (rr != ORGYM_OK) return rr;
     }
     return ORGYM_OK;
 }

@@ -13,6 +13,7 @@
 #define NV_MAXL ORGYM_NV_MAX_LEAD
 
 struct NvDev {
+    const double* rcp;  // reciprocal table (orgym_rcp_table)
     int L, T, obs_dim;
     double max_inv, max_q, p_max, h_max, k_max, mu_max;
 };
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(ORGYM_TILE) nv_step_kernel(const __grid_consta
             }
             float psum = nv_pipe_sum(P.L, [&](int j) { return row[5 + j]; });
             float pipe0 = P.L > 0 ? row[5] : 0.0f;
-            long long d = A.demand ? A.demand[e] : poisson_mu(q.mu, key, ep, sc);
+            long long d = A.demand ? A.demand[e] : poisson_mu(q.mu, P.rcp, key, ep, sc);
             float oq;
             double parts[4];
             double r = nv_period(P, q, A.actions[e], d, pipe0, psum, &oq, parts, nullptr, nullptr, nullptr);
@@ -323,7 +324,7 @@ __global__ void nv_export_params_kernel(int64_t N, int64_t npad, int L, const vo
 // ---- Poisson quantile: smallest k with cdf(k) >= q (scipy.stats.poisson.ppf) ---------------------------------------
 // pmf recurrence summed in ascending order from 9 sigma below the mean (the mass below is < 3e-18); the per-term
 // division is a reciprocal-multiply (1 ulp), which can only matter when q sits within ~1e-13 of a CDF step.
-__device__ __forceinline__ double poisson_ppf_dev(double q, double mu) {
+__device__ __forceinline__ double poisson_ppf_dev(double q, double mu, const double* __restrict__ rcp) {
     if (!(q > 0.0)) return -1.0;
     if (q >= 1.0) return INFINITY;
     double lo = floor(mu - 9.0 * sqrt(mu) - 9.0);
@@ -333,7 +334,7 @@ __device__ __forceinline__ double poisson_ppf_dev(double q, double mu) {
         cdf += term;
         if (cdf >= q) return k;
         k += 1.0;
-        term *= mu * __drcp_rn(k);
+        term *= mu * rcp_int(rcp, k);
         if (term == 0.0 && k > mu) return k;
     }
 }
@@ -387,18 +388,18 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS) nv_rollout_kernel(const __gri
         if (!fallback) {
             float cr = fk / hk;
             float eff = (fmu * (float)(L + 1)) * (float)A.param0;
-            level = poisson_ppf_dev((double)cr, eff > 1e-6f ? (double)eff : 1e-6);
+            level = poisson_ppf_dev((double)cr, eff > 1e-6f ? (double)eff : 1e-6, P.rcp);
         }
     } else if (A.policy == ORGYM_NV_POLICY_SS) {  // benchmark_newsvendor_sb3_rllib.py:363-371
         if (fh + fk > 1e-6f) {
             float cr = fk / (fh + fk);
             cr = cr < 0.001f ? 0.001f : (cr > 0.999f ? 0.999f : cr);
             float eff = fmu * (float)(L + 1);
-            level = poisson_ppf_dev((double)cr, eff > 1e-6f ? (double)eff : 1e-6);
+            level = poisson_ppf_dev((double)cr, eff > 1e-6f ? (double)eff : 1e-6, P.rcp);
         }
         level = level > 0.0 ? level : 0.0;
     }
-    const PoissonMu pm = poisson_setup<true>(q.mu);  // per-episode constants of the demand sampler
+    const PoissonMu pm = poisson_setup<true>(q.mu, P.rcp);  // per-episode constants of the demand sampler
     int head = 0;
     double ret = 0.0, s_sales = 0.0, s_dem = 0.0, s_lost = 0.0, s_ex = 0.0;
     for (int t = 0; t < P.T; t++) {
@@ -484,7 +485,6 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS) nv_rollout_kernel(const __gri
     }
 }
 
-__global__ void orgym_reduce_partials_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out);
 
 // ------------------------------------------------------------------------------------------------
 // host side of the C ABI
@@ -507,6 +507,7 @@ extern "C" int orgym_newsvendor_create(const orgym_newsvendor_config_t* cfg, int
     P.max_q = cfg->max_order_quantity;
     P.p_max = cfg->p_max; P.h_max = cfg->h_max; P.k_max = cfg->k_max; P.mu_max = cfg->mu_max;
     int rc = orgym_handle_base_init(&H->base, FAM_NEWSVENDOR, device, num_envs);
+    if (rc == ORGYM_OK) rc = orgym_rcp_table(device, &P.rcp);
     if (rc != ORGYM_OK) {
         delete H;
         return rc;
@@ -515,7 +516,9 @@ extern "C" int orgym_newsvendor_create(const orgym_newsvendor_config_t* cfg, int
     H->npad = round_up(num_envs, 32);
     int nblocks = (int)((num_envs + NV_ROLL_THREADS - 1) / NV_ROLL_THREADS);
     H->partials = nullptr;
-    cudaError_t ce = cudaMalloc(&H->partials, sizeof(double) * 8 * (size_t)nblocks);
+    size_t pbytes = sizeof(double) * (8 * (size_t)nblocks + ORGYM_REDUCE_EXTRA);
+    cudaError_t ce = cudaMalloc(&H->partials, pbytes);
+    if (ce == cudaSuccess) ce = cudaMemset(H->partials, 0, pbytes);
     if (ce != cudaSuccess) {
         orgym_set_error("device allocation failed: %s", cudaGetErrorString(ce));
         orgym_handle_base_free(&H->base);
@@ -651,8 +654,8 @@ extern "C" int orgym_newsvendor_rollout(orgym_handle_t h, uint64_t seed, int64_t
     nv_rollout_kernel<<<nblocks, NV_ROLL_THREADS, smem, (cudaStream_t)stream>>>(H->dev, A);
     ORGYM_CUDA(cudaGetLastError());
     if (out->summary_dev) {
-        orgym_reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(H->partials, nblocks, out->summary_dev);
-        ORGYM_CUDA(cudaGetLastError());
+        int rr = orgym_launch_reduce(H->partials, nblocks, out->summary_dev, (cudaStream_t)stream);
+        if (rr != ORGYM_OK) return rr;
     }
     return ORGYM_OK;
 }

@@ -247,3 +247,25 @@ def test_no_bulk_path_matches(monkeypatch):
         obs, *_ = env.step(torch.from_numpy(acts[:, t]).cuda(), demand=torch.from_numpy(dem[:, t]).cuda())
         assert np.array_equal(obs.cpu().numpy(), ref_obs[:, t + 1])
     env.close()
+
+
+def test_evaluate_pipelined_host_results():
+    """env.evaluate(): double-buffered rollouts with results in pinned host memory == plain rollouts, episode by
+    episode; int32 statistics equal the int64 ones."""
+    torch = _torch()
+    N = 5000
+    env = pkg.InvManagementLostSalesEnv(num_envs=N, device="cuda:0")
+    ref = []
+    for ep in range(5):
+        o = env.rollout("base_stock", seed=5000, episode=ep, want=("ep_return", "stats", "summary"))
+        ref.append({k: v.cpu().clone() for k, v in o.items()})
+    got = []
+    for res in env.evaluate("base_stock", episodes=5, seed=5000, want=("ep_return", "stats32", "summary")):
+        assert res["ep_return"].is_pinned() and res["ep_return"].device.type == "cpu"
+        got.append({k: v.clone() for k, v in res.items()})
+    assert len(got) == 5
+    for a, b in zip(ref, got):
+        assert torch.equal(a["ep_return"], b["ep_return"]) and torch.equal(a["summary"], b["summary"])
+        assert torch.equal(a["stats"], b["stats32"].long())
+    assert not torch.equal(got[0]["ep_return"], got[1]["ep_return"])     # different episodes, different demand
+    env.close()

@@ -1,5 +1,6 @@
 """scratch: quick timing of all kernels (superseded by bench.py)"""
-import sys, time
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import or_gym_inventory_b200 as pkg
 

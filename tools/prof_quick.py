@@ -1,5 +1,6 @@
 """scratch: small launches for ncu (one family per invocation)"""
-import sys
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import or_gym_inventory_b200 as pkg
 which = sys.argv[1]
