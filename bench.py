@@ -36,7 +36,7 @@ SM_COUNT, SCHED_PER_SM = 148, 4
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="invmgmt", choices=["invmgmt", "newsvendor", "netinv"])
@@ -53,6 +53,20 @@ WORKLOADS = {
     "netinv": dict(name="NetInvMgmtBacklogEnv default 9-node network, fused 30-period rollout, constant-order 10% policy",
                    envs=1 << 22, seed=6000, periods=30),
 }
+
+
+KERNEL_SOURCES = {"invmgmt": ("invmgmt.cu", "common.cuh", "device_rng.cuh"),
+                  "newsvendor": ("newsvendor.cu", "common.cuh", "device_rng.cuh"),
+                  "netinv": ("netinv.cu", "netinv.cuh", "netinv_jit.cu", "netinv_args.cuh", "common.cuh", "device_rng.cuh")}
+
+
+def kernel_source_hash(workload):
+    """sha1 over the CUDA sources of one env family: ties profiles/inst_counts.json to the kernels it was captured from."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in KERNEL_SOURCES[workload]:
+        h.update(open(os.path.join(ROOT, "or-gym-inventory_b200", "csrc", f), "rb").read())
+    return h.hexdigest()
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -73,7 +87,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+                                          "-i", str(self.idx), "-lms", "20"], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
 
@@ -222,7 +236,7 @@ def main():
     else:
         env = pkg.NetInvMgmtBacklogEnv(num_envs=N, device=dev, env_offset=offset)
         roll = lambda ep, want: env.rollout("constant", order_fraction=0.1, seed=W["seed"], episode=ep, want=want)  # noqa: E731
-        kernel, dtype = "net_sim_kernel", "f64"
+        kernel, dtype = ("net_jit_rollout" if env.specialised else "net_sim_kernel<128> (generic)"), "f64"
     want = ("ep_return", "stats", "summary")
 
     def step(ep):
@@ -333,6 +347,8 @@ def main():
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         issue_peak = SM_COUNT * SCHED_PER_SM * sm_mhz * 1e6           # warp-instructions / s at the observed clock
         c = counts.get(args.workload, {})
+        src_now = kernel_source_hash(args.workload)
+        stale = bool(c) and c.get("src_sha1") not in (None, src_now)
         roof = {"kernel": kernel, "bound": "issue", "unit": "warp-inst/s", "peak": issue_peak,
                 "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)",
                 "kernel_ms": kms, "achieved": None, "frac": None,
@@ -340,7 +356,10 @@ def main():
                 "hbm": {"achieved_gbs": alg_bytes / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                         "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": alg_bytes,
                         "peak_source": peak_src}}
-        if c.get("warp_inst_per_env_step"):
+        if stale:
+            roof["note"] = ("instruction count in profiles/inst_counts.json was captured for different kernel sources "
+                            "(sha1 mismatch): issue-roofline fraction withheld until the capture is redone")
+        if c.get("warp_inst_per_env_step") and not stale:
             inst = c["warp_inst_per_env_step"] * N * T
             roof["achieved"] = inst / (kms * 1e-3)
             roof["frac"] = roof["achieved"] / issue_peak
@@ -357,7 +376,7 @@ def main():
             sk = "nv_step_kernel"
         else:
             a = torch.rand((N, len(env.reorder_links)), device=dev) * 100
-            sk = "net_jit_kernel (STEP)"
+            sk = "net_jit_step" if env.specialised else "net_sim_kernel<128> (generic, STEP)"
         env.reset(seed=W["seed"])
         for _ in range(3):
             env.step(a)

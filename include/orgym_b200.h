@@ -341,6 +341,8 @@ int orgym_netinv_rollout(orgym_handle_t h, void* scratch_dev, uint64_t seed, int
  * that source for inspection and, with compile_check != 0, runs it through NVRTC; it needs no GPU. */
 int orgym_netinv_codegen(const orgym_netinv_config_t* cfg, int compile_check, char* buf, int64_t buflen,
                          int64_t* needed);
+/* 1 if this handle runs the topology-specialised kernels, 0 if it runs the generic one */
+int orgym_netinv_is_specialised(orgym_handle_t h);
 
 /* ------------------------------------------------------------------------- *
  * shared helpers

@@ -725,3 +725,8 @@ extern "C" int orgym_netinv_codegen(const orgym_netinv_config_t* cfg, int compil
     }
     return ORGYM_OK;
 }
+
+extern "C" int orgym_netinv_is_specialised(orgym_handle_t h) {
+    if (orgym_check_handle(h, FAM_NETINV)) return ORGYM_E_INVALID;
+    return ((NetHandle*)h)->jit.fn ? 1 : 0;
+}

@@ -352,6 +352,7 @@ class NetInvMgmtMasterEnv(BatchedEnv):
             if specialise is not None and had is None:
                 os.environ.pop("ORGYM_NET_JIT", None)
         assert lib.orgym_netinv_obs_dim(self._h) == P.obs_dim
+        self.specialised = bool(lib.orgym_netinv_is_specialised(self._h))
         N, od, dev = self.num_envs, P.obs_dim, self.device
         J, E, M = len(P.main_nodes), len(P.reorder_links), len(P.retail_links)
         self._alloc_state(lib.orgym_netinv_state_bytes(self._h))
