@@ -329,14 +329,18 @@ __device__ __forceinline__ double poisson_ppf_dev(double q, double mu, const dou
     if (q >= 1.0) return INFINITY;
     double lo = floor(mu - 9.0 * sqrt(mu) - 9.0);
     if (lo < 0.0) lo = 0.0;
-    double term = exp(-mu + lo * log(mu) - lgamma(lo + 1.0)), cdf = 0.0, k = lo;
+    double term = exp(-mu + lo * log(mu) - lgamma(lo + 1.0)), cdf = 0.0;
+    int k = (int)lo;
+    const double* pr = rcp + k;  // pr[1] = 1/(k+1)
     for (;;) {
         cdf += term;
-        if (cdf >= q) return k;
-        k += 1.0;
-        term *= mu * rcp_int(rcp, k);
-        if (term == 0.0 && k > mu) return k;
+        if (cdf >= q) break;
+        ++k;
+        ++pr;
+        term *= mu * (k <= ORGYM_RCP_N ? *pr : __drcp_rn((double)k));
+        if (term == 0.0 && (double)k > mu) break;
     }
+    return (double)k;
 }
 
 // ---- fused rollout ----------------------------------------------------------------------------------------------
