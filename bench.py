@@ -397,11 +397,30 @@ def main():
                                      "algorithmic_bytes_per_env_step": ab, "instances": N, "peak_source": peak_src,
                                      "note": "info tensors (demand/sales/unfulfilled/profit) are written too; they are "
                                              "not part of the algorithmic byte count"}
-        del a
+        # the same kernel without the optional info tensors (they are not part of the algorithmic byte count)
         env.close()
         del env
         torch.cuda.empty_cache()
-        line["cpu_baseline"] = cpu_port_rate(args.workload, seconds=10.0)
+        cls0 = {"invmgmt": pkg.InvManagementLostSalesEnv, "newsvendor": pkg.NewsvendorEnv,
+                "netinv": pkg.NetInvMgmtBacklogEnv}[args.workload]
+        env0 = cls0(num_envs=N, device=dev, env_offset=offset, info_level=0)
+        env0.reset(seed=W["seed"])
+        for _ in range(3):
+            env0.step(a)
+        torch.cuda.synchronize()
+        s0.record()
+        for _ in range(20):
+            env0.step(a)
+        s1.record()
+        torch.cuda.synchronize()
+        sms0 = s0.elapsed_time(s1) / 20
+        line["roofline_step_api"]["info_off"] = {"kernel_ms": sms0, "achieved": N * ab / (sms0 * 1e-3) / 1e9,
+                                                 "frac": N * ab / (sms0 * 1e-3) / 1e9 / hbm_peak}
+        env0.close()
+        del a, env0
+        torch.cuda.empty_cache()
+        if world == 1:
+            line["cpu_baseline"] = cpu_port_rate(args.workload, seconds=10.0)
     if rank == 0:
         emit(line)
     if world > 1:
