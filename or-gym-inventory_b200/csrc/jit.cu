@@ -3,8 +3,12 @@
 
 #include <dlfcn.h>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -79,7 +83,88 @@ int orgym_jit_compile(const std::string& src, const char* name, JitKernel* out, 
     return 0;
 }
 
+// ---- cubin cache: in-process map + files under $ORGYM_JIT_CACHE (default ~/.cache/orgym_b200), keyed by a 64-bit
+// FNV-1a hash of the generated source (which embeds every constant of the config) and the NVRTC version ------------
+static std::mutex g_cache_mu;
+static std::map<std::string, std::vector<char>> g_cubin_cache;
+
+static std::string cache_key(const std::string& src) {
+    uint64_t h = 1469598103934665603ULL;
+    for (unsigned char c : src) {
+        h ^= c;
+        h *= 1099511628211ULL;
+    }
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%016llx_%zu_nvrtc12", (unsigned long long)h, src.size());
+    return buf;
+}
+static std::string cache_dir() {
+    const char* d = getenv("ORGYM_JIT_CACHE");
+    if (d && d[0]) return d[0] == '0' && d[1] == 0 ? std::string() : std::string(d);
+    const char* home = getenv("HOME");
+    if (!home || !home[0]) return std::string();
+    return std::string(home) + "/.cache/orgym_b200";
+}
+static bool cache_load(const std::string& key, std::vector<char>* out) {
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_cubin_cache.find(key);
+        if (it != g_cubin_cache.end()) {
+            *out = it->second;
+            return true;
+        }
+    }
+    std::string dir = cache_dir();
+    if (dir.empty()) return false;
+    FILE* f = fopen((dir + "/" + key + ".cubin").c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    bool ok = n > 0;
+    if (ok) {
+        out->resize((size_t)n);
+        ok = fread(out->data(), 1, (size_t)n, f) == (size_t)n;
+    }
+    fclose(f);
+    if (ok) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        g_cubin_cache[key] = *out;
+    }
+    return ok;
+}
+static void cache_store(const std::string& key, const std::vector<char>& cubin) {
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        g_cubin_cache[key] = cubin;
+    }
+    std::string dir = cache_dir();
+    if (dir.empty()) return;
+    std::string parent = dir.substr(0, dir.find_last_of('/'));
+    mkdir(parent.c_str(), 0755);
+    mkdir(dir.c_str(), 0755);
+    std::string tmp = dir + "/" + key + ".tmp" + std::to_string((long)getpid());
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    fclose(f);
+    if (ok)
+        rename(tmp.c_str(), (dir + "/" + key + ".cubin").c_str());  // atomic publish
+    else
+        unlink(tmp.c_str());
+}
+
+static int nvrtc_compile(const std::string& src, std::vector<char>* cubin_out, std::string* err);
+
 static int compile_to_cubin(const std::string& src, std::vector<char>* cubin_out, std::string* err) {
+    const std::string key = cache_key(src);
+    if (cache_load(key, cubin_out)) return 0;
+    int rc = nvrtc_compile(src, cubin_out, err);
+    if (rc == 0) cache_store(key, *cubin_out);
+    return rc;
+}
+
+static int nvrtc_compile(const std::string& src, std::vector<char>* cubin_out, std::string* err) {
     std::call_once(g_once, load_nvrtc);
     if (!g_nvrtc.ok) {
         *err = "NVRTC (libnvrtc.so.12) could not be loaded";

@@ -284,7 +284,10 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     o("}");
     o("#undef ROLL");
     };
-    int mb_step = 5, mb_roll = 3;
+    // small graphs: STEP 5 CTAs/SM (<= 102 registers), ROLLOUT 3; large graphs (hundreds of live float64 values per
+    // instance) spill either way and run best with all 255 registers (measured on the 64-node synthetic graph)
+    const bool big = 2 * J + 3 * E + 2 * M > 128;
+    int mb_step = big ? 2 : 5, mb_roll = big ? 1 : 3;
     if (const char* mb = getenv("ORGYM_NET_JIT_MINBLOCKS_STEP")) mb_step = atoi(mb) > 0 ? atoi(mb) : 1;
     if (const char* mb = getenv("ORGYM_NET_JIT_MINBLOCKS_ROLLOUT")) mb_roll = atoi(mb) > 0 ? atoi(mb) : 1;
     emit_kernel("net_jit_step", 0, mb_step);
