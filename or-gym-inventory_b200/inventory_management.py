@@ -146,8 +146,15 @@ class InvManagementMasterEnv(BatchedEnv):
     metadata = {"render_modes": [], "render_fps": 4}
 
     def __init__(self, *args, num_envs: int = 1, device="cuda", env_offset: int = 0,
-                 autoreset_mode: str = "next_step", wide_state: bool = False, info_level: int = 1, **kwargs):
+                 autoreset_mode: str = "next_step", wide_state: bool = False, info_level: int = 1,
+                 record_history: bool = False, **kwargs):
         torch = _torch()
+        self.record_history = bool(record_history)
+        if self.record_history:
+            if autoreset_mode != "disabled":
+                raise ValueError("record_history=True needs autoreset_mode='disabled' (episodes are reset explicitly, "
+                                 "like the reference's evaluators do)")
+            info_level = max(int(info_level), 1)
         self.params = InvManagementParams(*args, **kwargs)
         P = self.params
         # attributes the reference agents read (benchmark_InvManagementLostSalesEnv.py:142-153)
@@ -197,7 +204,37 @@ class InvManagementMasterEnv(BatchedEnv):
                                                     self.env_offset, self._ptr(mask), self._ptr(self._obs),
                                                     self._stream()))
         self._has_reset = True
+        if self.record_history:
+            if mask is not None:
+                raise NotImplementedError("record_history keeps all instances in lock-step: reset without a mask")
+            self._alloc_history()
         return self._obs, {}
+
+    # -- full-history buffers: the arrays the reference keeps per episode (:203-211), batched ----
+    def _alloc_history(self):
+        torch = _torch()
+        P = self.params
+        N, T, n, m, dev = self.num_envs, int(P.num_periods), P.num_stages - 1, P.num_stages, self.device
+        z = lambda *shape, dt=torch.int64: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731
+        self.I, self.B = z(N, T + 1, n), z(N, T + 1, m)
+        self.R, self.S, self.LS = z(N, T, n), z(N, T, m), z(N, T, m)
+        self.D, self.action_log = z(N, T), z(N, T, n)
+        self.P = z(N, T, dt=torch.float64)   # discounted profit (the reference stores it as float32, :210/:323)
+        self.I[:, 0] = torch.as_tensor(np.asarray(P.init_inv, np.int64), device=dev)
+        self._t_host = 0
+
+    def _record(self, a_req, reward, info):
+        t = self._t_host
+        if t >= int(self.params.num_periods):
+            return
+        I, B, _ = self.export_state()
+        self.I[:, t + 1], self.B[:, t + 1] = I, B
+        self.D[:, t], self.S[:, t], self.P[:, t] = info["demand_realized"], info["sales"], reward
+        self.R[:, t] = info["sales"][:, 1:]
+        if not self.params.backlog:
+            self.LS[:, t] = info["unfulfilled"]
+        self.action_log[:, t] = a_req
+        self._t_host = t + 1
 
     def step(self, actions, demand=None):
         """step (inventory_management.py:224-352) for all instances.
@@ -229,6 +266,8 @@ class InvManagementMasterEnv(BatchedEnv):
         info = dict(self._info_t)
         if self.autoreset_mode == "same_step":
             info["final_obs"] = self._final_obs
+        if self.record_history:
+            self._record(torch.clamp(a, min=0).to(torch.int64), self._reward, info)  # requested order (:250)
         return self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), info
 
     # -- batched views of the attributes the reference agents read ---------------------------------------------------

@@ -325,11 +325,17 @@ class NetInvMgmtMasterEnv(BatchedEnv):
     metadata = {"render_modes": ["human"], "render_fps": 4}
 
     def __init__(self, *args, num_envs: int = 1, device="cuda", env_offset: int = 0,
-                 autoreset_mode: str = "next_step", info_level: int = 1, specialise: Optional[bool] = None, **kwargs):
+                 autoreset_mode: str = "next_step", info_level: int = 1, specialise: Optional[bool] = None,
+                 record_history: bool = False, **kwargs):
         """specialise: True = compile kernels for this topology with NVRTC at construction (seconds for small graphs,
         ~20 s for a 64-node one; 2-5x faster stepping), False = generic kernel, None = automatic (graphs with up to
         48 reorder links).  The environment variable ORGYM_NET_JIT (0/1/2) takes precedence when set."""
         torch = _torch()
+        self.record_history = bool(record_history)
+        if self.record_history:
+            if autoreset_mode != "disabled":
+                raise ValueError("record_history=True needs autoreset_mode='disabled'")
+            info_level = max(int(info_level), 1)
         kwargs.setdefault("default_graph_kind", self._default_kind)
         self.params = NetInvMgmtParams(*args, **kwargs)
         P = self.params
@@ -387,7 +393,35 @@ class NetInvMgmtMasterEnv(BatchedEnv):
                                                    self.env_offset, self._ptr(mask), self._ptr(self._obs),
                                                    self._stream()))
         self._has_reset = True
+        if self.record_history:
+            if mask is not None:
+                raise NotImplementedError("record_history keeps all instances in lock-step: reset without a mask")
+            self._alloc_history()
         return self._obs, {}
+
+    # -- full-history buffers: the DataFrames the reference keeps (:315-321) as [N, T(+1), columns] tensors; columns in
+    # main_nodes / reorder_links / retail_links order, S = reorder links then retail links -----------------------------
+    def _alloc_history(self):
+        torch = _torch()
+        N, T, dev = self.num_envs, int(self.num_periods), self.device
+        J, E, M = len(self.main_nodes), len(self.reorder_links), len(self.retail_links)
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)  # noqa: E731
+        self.X, self.Y, self.U = z(N, T + 1, J), z(N, T + 1, E), z(N, T + 1, M)
+        self.R, self.S, self.D, self.P = z(N, T, E), z(N, T, E + M), z(N, T, M), z(N, T, J)
+        self.X[:, 0] = torch.as_tensor([float(self.graph.nodes[j].get("I0", 0)) for j in self.main_nodes],
+                                       dtype=torch.float64, device=dev)
+        self._t_host = 0
+
+    def _record(self, info):
+        t = self._t_host
+        if t >= int(self.num_periods):
+            return
+        E = len(self.reorder_links)
+        X, Y, U, _ = self.export_state()
+        self.X[:, t + 1], self.Y[:, t + 1], self.U[:, t + 1] = X, Y, U
+        self.S[:, t], self.R[:, t] = info["sales"], info["sales"][:, :E]
+        self.D[:, t], self.P[:, t] = info["demand"], info["profit_node"]
+        self._t_host = t + 1
 
     def step(self, actions, demand=None):
         """step (network_management.py:436-635): actions float32 [N, len(reorder_links)] in sorted link order;
@@ -405,6 +439,8 @@ class NetInvMgmtMasterEnv(BatchedEnv):
         info = dict(self._info_t)
         if self.autoreset_mode == "same_step":
             info["final_obs"] = self._final_obs
+        if self.record_history:
+            self._record(info)
         return self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), info
 
     def export_state(self):

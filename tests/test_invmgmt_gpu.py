@@ -269,3 +269,21 @@ def test_evaluate_pipelined_host_results():
         assert torch.equal(a["stats"], b["stats32"].long())
     assert not torch.equal(got[0]["ep_return"], got[1]["ep_return"])     # different episodes, different demand
     env.close()
+
+
+@pytest.mark.parametrize("path", [p for p in INV if "default_lost_random" in p or "zerolt_backlog_wild" in p],
+                         ids=lambda p: p.split("/")[-1][:-4])
+def test_history_buffers_match_reference_arrays(path):
+    """record_history=True: the batched I/B/R/S/LS/D/P/action_log arrays equal the reference's per-episode arrays."""
+    torch = _torch()
+    g, meta = load_golden(path)
+    env = _mk(meta, len(g["seeds"]), autoreset_mode="disabled", record_history=True)
+    env.reset(seed=0)
+    floats = meta["policy"] == "wild"
+    for t in range(env.num_periods):
+        a = g["actions"][:, t]
+        env.step(torch.from_numpy(a if floats else a.astype(np.int64)).cuda(), demand=torch.from_numpy(g["D"][:, t]).cuda())
+    for name in ("I", "B", "R", "S", "LS", "D", "action_log"):
+        assert np.array_equal(getattr(env, name).cpu().numpy(), g[name]), name
+    assert np.array_equal(env.P.cpu().numpy(), g["reward"])
+    env.close()

@@ -193,3 +193,19 @@ def test_mlp_policy_drives_step_api_zero_copy():
         assert np.array_equal(o["reward"], r_h[e])
         assert np.array_equal(o["obs"][-1], obs[e].cpu().numpy())
     env.close()
+
+
+def test_history_buffers_match_reference_frames():
+    """record_history=True: X/Y/U/R/S/D/P history tensors equal the reference's DataFrames."""
+    torch = _torch()
+    path = [p for p in NET if "yield_backlog_random" in p][0]
+    g, meta = load_golden(path)
+    env = _mk(meta, len(g["seeds"]), autoreset_mode="disabled", record_history=True)
+    cols = net_S_columns(meta)
+    env.reset(seed=0)
+    for t in range(env.num_periods):
+        env.step(torch.from_numpy(g["actions"][:, t]).cuda(), demand=torch.from_numpy(g["D"][:, t]).cuda())
+    for name in ("X", "Y", "U", "R", "D", "P"):
+        assert np.array_equal(getattr(env, name).cpu().numpy(), g[name]), name
+    assert np.array_equal(env.S.cpu().numpy(), g["S"][:, :, cols])
+    env.close()
