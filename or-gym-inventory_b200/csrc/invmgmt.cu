@@ -33,6 +33,10 @@ struct InvHandle {
     std::vector<void*> allocs;
     double* partials;  // [max_blocks][8] rollout block partial sums
     int max_blocks;
+    // lock-step period of the batch living in `hint_state` (host-side bookkeeping for speculative ring loads;
+    // a wrong hint only costs the speculation, never correctness): -1 = unknown
+    const void* hint_state;
+    int hint_t;
 };
 
 // ---- state layout: field[slot][env], env stride npad -------------------------------------------------------
@@ -86,6 +90,7 @@ struct InvStepArgs {
     int64_t* final_obs;
     uint32_t* err;
     int use_bulk;
+    int t_hint;  // period every env is expected to be in (lock-step batches), or -1
 };
 
 // ---- one period of one env: shared by the step and rollout kernels --------------------------------------------
@@ -200,7 +205,7 @@ __global__ void inv_reset_kernel(const __grid_constant__ InvDev P, int64_t N, in
 // ---- step ------------------------------------------------------------------------------------------------------
 // t % d for 0 <= t < 2^20 and 1 <= d <= 64 without a division: q = mulhi(t, ceil(2^32 / d)) is exact in that range
 #ifndef ORGYM_STEP_MIN_BLOCKS
-#define ORGYM_STEP_MIN_BLOCKS 8
+#define ORGYM_STEP_MIN_BLOCKS 6
 #endif
 __device__ __forceinline__ int mod_small(int t, int d, uint32_t magic) {
     return magic ? t - (int)__umulhi((uint32_t)t, magic) * d : 0;  // magic == 0 encodes d == 1
@@ -244,11 +249,56 @@ __device__ __forceinline__ void obs_tile_store(int64_t* __restrict__ g, const S*
     }
 }
 
+// Lead-time ring slots and the action window of one env for period t (the second group of loads of a step).
+// arr[i] = R[t - L_i] (ring slot t % L_i); window positions 0..k-2 of the observation at t+1 go straight into the
+// env's row of the staging tile (position k-1 is the current period's request, filled in by the caller).
+// All loads of up to CH periods are issued before the first store so that their latencies overlap.
+template <int NS, bool EXACT, typename S, int CH>
+__device__ __forceinline__ void inv_load_rings(const InvDev& P, const InvState<S>& st, int64_t e, int t, int n,
+                                               S (&arr)[NS], S* orow) {
+    const int Lm = P.lt_max;
+    const int tn = t + 1;
+    const int k = tn < Lm ? tn : Lm;  // window length at t+1 (:378)
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+        arr[i] = 0;
+        if ((EXACT || i < n) && P.L[i] > 0)
+            arr[i] = st.at(st.oR + P.roff[i] + mod_small(t, P.L[i], P.Lmagic[i]), e);  // slot holds R[t-L_i]
+    }
+    if (Lm > 0) {
+        const int slot = mod_small(tn - k, Lm, P.Lm_magic);
+        for (int q0 = 0; q0 < Lm; q0 += CH) {
+            S v[CH][NS];
+#pragma unroll
+            for (int u = 0; u < CH; u++) {
+                const int q = q0 + u;
+                const bool in = q < k - 1;
+                int sl = slot + q;
+                sl = sl >= Lm ? sl - Lm : sl;
+#pragma unroll
+                for (int i = 0; i < NS; i++) {
+                    v[u][i] = 0;
+                    if ((EXACT || i < n) && in) v[u][i] = st.at(st.oA + sl * n + i, e);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < CH; u++) {
+                const int q = q0 + u;
+                if (q < Lm && q != k - 1) {
+#pragma unroll
+                    for (int i = 0; i < NS; i++)
+                        if (EXACT || i < n) orow[n + q * n + i] = v[u][i];
+                }
+            }
+        }
+    }
+}
+
 template <int NS, bool EXACT, typename S>
 __global__ void __launch_bounds__(ORGYM_TILE, (NS <= 4 && sizeof(S) == 4) ? ORGYM_STEP_MIN_BLOCKS : 1)
     inv_step_kernel(const __grid_constant__ InvDev P, const InvStepArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int CH = NS <= 3 ? 8 : (NS <= 6 ? 4 : 2);  // window periods loaded per batch (CH*NS loads in flight)
+    constexpr int CH = NS <= 3 ? 12 : (NS <= 6 ? 6 : 3);  // window periods loaded per batch (<= 36 loads in flight)
     const int n = EXACT ? NS : P.n, m = n + 1;
     const int tid = threadIdx.x;
     const int64_t e0 = (int64_t)blockIdx.x * ORGYM_TILE, e = e0 + tid;
@@ -291,7 +341,14 @@ __global__ void __launch_bounds__(ORGYM_TILE, (NS <= 4 && sizeof(S) == 4) ? ORGY
     uint64_t key = 0;
     bool do_step = valid;
     S* orow = obs_tile + tid * ostride;
-    if (valid) {  // first round trip: everything that does not depend on the period
+    S arr[NS];
+    const int Lm = P.lt_max;
+    // The ring / window addresses depend on the env's period, which itself has to be loaded: two dependent round trips
+    // to HBM.  When the batch runs in lock-step the host-side handle knows the period (A.t_hint), so the second group
+    // of loads is issued speculatively together with the first; an env whose period differs simply reloads.
+    const int t_spec = A.t_hint;
+    const bool spec = valid && t_spec >= 0 && t_spec < P.T;
+    if (valid) {  // loads that do not depend on the period
         t = st.period[e];
         episode = st.episode[e];
         if (sample) key = st.key[e];
@@ -301,6 +358,9 @@ __global__ void __launch_bounds__(ORGYM_TILE, (NS <= 4 && sizeof(S) == 4) ? ORGY
 #pragma unroll
         for (int j = 0; j <= NS; j++)
             if (EXACT || j <= n) B[j] = st.at(st.oB + j, e);
+    }
+    if (spec) inv_load_rings<NS, EXACT, S, CH>(P, st, e, t_spec, n, arr, orow);
+    if (valid) {
         if (t >= P.T) {  // episode already over
             do_step = false;
             if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {
@@ -320,48 +380,9 @@ __global__ void __launch_bounds__(ORGYM_TILE, (NS <= 4 && sizeof(S) == 4) ? ORGY
             }
         }
     }
-    // second round trip: lead-time ring slots and the action window, all addressed by the period
-    S arr[NS];
-    const int Lm = P.lt_max;
+    if (do_step && !(spec && t == t_spec)) inv_load_rings<NS, EXACT, S, CH>(P, st, e, t, n, arr, orow);
     const int tn = t + 1;
     const int k = tn < Lm ? tn : Lm;  // window length at t+1 (:378)
-    if (do_step) {
-#pragma unroll
-        for (int i = 0; i < NS; i++) {
-            arr[i] = 0;
-            if ((EXACT || i < n) && P.L[i] > 0)
-                arr[i] = st.at(st.oR + P.roff[i] + mod_small(t, P.L[i], P.Lmagic[i]), e);  // slot holds R[t-L_i]
-        }
-        // observation window (:376-383): requested orders of periods tn-k .. tn-1, oldest first, left aligned.
-        // Period p lives in ring slot p % lt_max; the current period (window position k-1) is filled in below.
-        if (Lm > 0) {
-            int slot = mod_small(tn - k, Lm, P.Lm_magic);
-            for (int q0 = 0; q0 < Lm; q0 += CH) {
-                S v[CH][NS];
-#pragma unroll
-                for (int u = 0; u < CH; u++) {
-                    const int q = q0 + u;
-                    const bool in = q < k - 1;
-                    int sl = slot + q;
-                    sl = sl >= Lm ? sl - Lm : sl;
-#pragma unroll
-                    for (int i = 0; i < NS; i++) {
-                        v[u][i] = 0;
-                        if ((EXACT || i < n) && in) v[u][i] = st.at(st.oA + sl * n + i, e);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < CH; u++) {
-                    const int q = q0 + u;
-                    if (q < Lm && q != k - 1) {
-#pragma unroll
-                        for (int i = 0; i < NS; i++)
-                            if (EXACT || i < n) orow[n + q * n + i] = v[u][i];
-                    }
-                }
-            }
-        }
-    }
     if (bulk_in) mbar_wait(bar, 0);
     __syncthreads();  // action tile (cooperative path) and alias table visible
 
@@ -813,6 +834,8 @@ extern "C" int orgym_invmgmt_create(const orgym_invmgmt_config_t* cfg, int64_t n
     }
     P.disc = disc_dev;
     H->max_blocks = (int)((num_envs + ROLL_THREADS - 1) / ROLL_THREADS);
+    H->hint_state = nullptr;
+    H->hint_t = -1;
     H->partials = nullptr;
     if (ce == cudaSuccess) {
         size_t pbytes = sizeof(double) * (8 * (size_t)H->max_blocks + ORGYM_REDUCE_EXTRA);
@@ -878,6 +901,8 @@ extern "C" int orgym_invmgmt_reset(orgym_handle_t h, void* state_dev, int reseed
         inv_reset_kernel<int><<<grid, 256, 0, (cudaStream_t)stream>>>(H->dev, N, H->npad, state_dev, reseed, seed,
                                                                      env_offset, mask_dev, obs_dev);
     ORGYM_CUDA(cudaGetLastError());
+    H->hint_state = state_dev;
+    H->hint_t = mask_dev ? -1 : 0;
     return ORGYM_OK;
 }
 
@@ -922,6 +947,14 @@ extern "C" int orgym_invmgmt_step(orgym_handle_t h, void* state_dev, const void*
         A.final_obs = info->final_obs_dev;
     }
     A.err = H->base.err_dev;
+    A.t_hint = (H->hint_state == state_dev) ? H->hint_t : -1;
+    if (A.t_hint >= 0) {  // advance the host-side mirror of the lock-step period exactly like the kernel will
+        int t = A.t_hint;
+        if (t >= P.T)
+            H->hint_t = autoreset_mode == ORGYM_AUTORESET_NEXT_STEP ? 0 : t;
+        else
+            H->hint_t = (t + 1 >= P.T && autoreset_mode == ORGYM_AUTORESET_SAME_STEP) ? 0 : t + 1;
+    }
     A.use_bulk = use_bulk() && ((uintptr_t)actions_dev % 16 == 0) && ((uintptr_t)obs_dev % 16 == 0);
     int ostride = (P.obs_dim & 1) ? P.obs_dim : P.obs_dim + 1;
     size_t smem = (((size_t)ORGYM_TILE * ostride * (H->wide ? 8 : 4) + 15) & ~(size_t)15) + (size_t)ORGYM_TILE * P.n * 8 + 16 +
