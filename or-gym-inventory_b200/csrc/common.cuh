@@ -91,14 +91,6 @@ __device__ __forceinline__ double rcp_int(const double* __restrict__ tab, double
     return k <= (double)ORGYM_RCP_N ? tab[(int)k] : __drcp_rn(k);
 }
 
-__device__ const double c_rcp_tab[65] = {
-    0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11, 1.0 / 12, 1.0 / 13,
-    1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25,
-    1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37,
-    1.0 / 38, 1.0 / 39, 1.0 / 40, 1.0 / 41, 1.0 / 42, 1.0 / 43, 1.0 / 44, 1.0 / 45, 1.0 / 46, 1.0 / 47, 1.0 / 48, 1.0 / 49,
-    1.0 / 50, 1.0 / 51, 1.0 / 52, 1.0 / 53, 1.0 / 54, 1.0 / 55, 1.0 / 56, 1.0 / 57, 1.0 / 58, 1.0 / 59, 1.0 / 60, 1.0 / 61,
-    1.0 / 62, 1.0 / 63, 1.0 / 64};
-
 // log(k!) for integer-valued k >= 0: exact table below 16, Stirling series above (error < 2e-12)
 __device__ __forceinline__ double log_factorial(double k) {
     if (k < 16.0) {
@@ -141,10 +133,6 @@ __device__ __forceinline__ PoissonMu poisson_setup(double mu, const double* rcp)
         c.inv_alpha = 1.1239 + 1.1328 / (c.b - 3.4);
     }
     return c;
-}
-// reciprocals 1/x for the small-mean inversion loop (no division on the hot path)
-__device__ __forceinline__ double small_rcp(int x) {
-    return x <= 64 ? c_rcp_tab[x] : 1.0 / (double)x;
 }
 template <bool FULL>
 __device__ __forceinline__ int64_t poisson_draw(const PoissonMu& c, uint64_t key, uint32_t episode, int t) {
@@ -267,16 +255,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // make generic-proxy shared-memory writes visible to the async proxy before a bulk store reads them
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// streaming (evict-first) scalar accesses for state that is touched once per launch
-template <typename T>
-__device__ __forceinline__ T ld_stream(const T* p) {
-    return __ldcs(p);
-}
-template <typename T>
-__device__ __forceinline__ void st_stream(T* p, T v) {
-    __stcs(p, v);
-}
 
 #define ORGYM_TILE 128  // env instances per CTA in the step kernels
 

@@ -152,28 +152,6 @@ __device__ __forceinline__ double inv_period(const InvDev& P, const S (&req)[NS]
     return profit;
 }
 
-// ---- tile movers: row-major [TILE][width] tiles of the API tensors <-> shared memory --------------------------
-// dense tile (stride == width) + full tile + 16-byte multiples -> one bulk async copy; else cooperative loop.
-template <typename T>
-__device__ __forceinline__ void tile_store(T* __restrict__ g, const T* s, int width, int stride, int nvalid, bool bulk) {
-    if (bulk) {
-        fence_async_smem();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            bulk_s2g(g, s, (uint32_t)(nvalid * width * sizeof(T)));
-            bulk_commit();
-            bulk_wait_read0();
-        }
-    } else {
-        __syncthreads();
-        int total = nvalid * width;
-        for (int i = threadIdx.x; i < total; i += blockDim.x) {
-            int r = i / width, c = i - r * width;
-            g[i] = s[r * stride + c];
-        }
-    }
-}
-
 // ---- reset ------------------------------------------------------------------------------------------------------
 template <typename S>
 __device__ __forceinline__ void inv_reset_env(const InvDev& P, const InvState<S>& st, int64_t e) {

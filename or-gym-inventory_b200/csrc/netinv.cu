@@ -399,7 +399,6 @@ static int net_fill(const orgym_netinv_config_t* c, NetDev& P) {
     P.J = c->num_main;
     P.E = c->num_reorder;
     P.M = c->num_retail;
-    int rc = ORGYM_OK;
 #define FAIL(code, ...)            \
     do {                           \
         orgym_set_error(__VA_ARGS__); \
@@ -469,7 +468,6 @@ static int net_fill(const orgym_netinv_config_t* c, NetDev& P) {
         P.obs_dim = P.M + P.J + P.sumL;  // :190
     }
 #undef FAIL
-    (void)rc;
     return ORGYM_OK;
 }
 
@@ -658,7 +656,6 @@ extern "C" int orgym_netinv_rollout(orgym_handle_t h, void* scratch_dev, uint64_
                   in->policy);
     ORGYM_REQUIRE(in->actions_dev, "actions_dev is required");
     DeviceGuard g(H->base.device);
-    const NetDev& P = H->dev;
     NetSimArgs A;
     memset(&A, 0, sizeof(A));
     A.N = H->base.num_envs;
