@@ -421,6 +421,35 @@ def main():
         torch.cuda.empty_cache()
         if world == 1:
             line["cpu_baseline"] = cpu_port_rate(args.workload, seconds=10.0)
+            # the other BASELINE.json configs, measured briefly with the same method (fused rollout, CUDA events)
+            others = {}
+            for wname in ("newsvendor", "netinv"):
+                if wname == args.workload:
+                    continue
+                Wo = WORKLOADS[wname]
+                No, To = Wo["envs"], Wo["periods"]
+                if wname == "newsvendor":
+                    eo = pkg.NewsvendorEnv(num_envs=No, device=dev)
+                    ro = lambda ep: eo.rollout("classic", seed=Wo["seed"], episode=ep)  # noqa: E731
+                else:
+                    eo = pkg.NetInvMgmtBacklogEnv(num_envs=No, device=dev)
+                    ro = lambda ep: eo.rollout("constant", order_fraction=0.1, seed=Wo["seed"], episode=ep)  # noqa: E731
+                for k in range(3):
+                    ro(k)
+                torch.cuda.synchronize()
+                o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                o0.record()
+                for k in range(20):
+                    ro(10 + k)
+                o1.record()
+                torch.cuda.synchronize()
+                oms = o0.elapsed_time(o1) / 20
+                others[wname] = {"workload": Wo["name"], "instances": No, "periods": To, "ms_per_rollout": oms,
+                                 "env_steps_per_s": No * To / (oms * 1e-3)}
+                eo.close()
+                del eo
+                torch.cuda.empty_cache()
+            line["other_configs"] = others
     if rank == 0:
         emit(line)
     if world > 1:

@@ -11,6 +11,9 @@
 //
 // Integer state is exact (int64, or int32 with a range guard); rewards are float64 evaluated in the reference's
 // operation order (no FMA contraction: the library is built with --fmad=false).
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 #define MAXN ORGYM_INV_MAX_STAGES
@@ -37,6 +40,7 @@ struct InvHandle {
     // a wrong hint only costs the speculation, never correctness): -1 = unknown
     const void* hint_state;
     int hint_t;
+    long long user_dmax;  // largest value of a user_D trace (0 for sampled demand)
 };
 
 // ---- state layout: field[slot][env], env stride npad -------------------------------------------------------
@@ -136,8 +140,13 @@ __device__ __forceinline__ double inv_period(const InvDev& P, const S (&req)[NS]
             if (j < n) inv = Ic[j] > 0 ? Ic[j] : 0;
             double s = (double)sj;
             double rev = P.up[j] * s, pc = P.uc[j] * s;
-            double hold = P.hc[j] * (double)inv, pen = P.kc[j] * (double)U[j];
-            term[j] = ((rev - pc) - hold) - pen;
+            double pen = P.kc[j] * (double)U[j];
+            if (EXACT && j == NS)  // last stage holds no inventory: hc = 0 (:92), x - 0.0 == x
+                term[j] = (rev - pc) - pen;
+            else {
+                double hold = P.hc[j] * (double)inv;
+                term[j] = ((rev - pc) - hold) - pen;
+            }
         } else
             term[j] = 0.0;
     }
@@ -543,7 +552,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
     __syncthreads();
 
     const uint64_t key = A.seed + (uint64_t)(A.env_offset + e);
-    S I[NS], B[NS + 1], psum[NS];
+    S I[NS], B[NS + 1], psum[NS], lmask[NS];
     int rbase[NS], rpos[NS], rlen[NS];  // ring base / position / length in elements of the [slot][thread] layout
 #pragma unroll
     for (int i = 0; i < NS; i++) {
@@ -552,12 +561,16 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
         rbase[i] = A.rroff[i] * ROLL_THREADS + tid;
         rpos[i] = 0;
         rlen[i] = (P.L[i] > 0 ? P.L[i] : 1) * ROLL_THREADS;
+        lmask[i] = P.L[i] > 0 ? (S)-1 : (S)0;
     }
 #pragma unroll
     for (int j = 0; j <= NS; j++) B[j] = 0;
     double ret = 0.0;
-    long long s_sales = 0, s_dem = 0, s_stock = 0, s_inv = 0;
+    // episode statistics in the state type: the int32 instantiation is only launched when the host has bounded every
+    // per-episode sum below 2^31 (orgym_invmgmt_rollout), otherwise S = int64
+    S s_sales = 0, s_dem = 0, s_stock = 0, s_inv = 0;
     uint4 w = make_uint4(0, 0, 0, 0);
+    double* const rtraj = (A.reward_traj && valid) ? A.reward_traj + e * P.T : nullptr;
 
     for (int t = 0; t < P.T; t++) {
         S req[NS], arr[NS], Rf[NS], U[NS + 1];
@@ -622,13 +635,13 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
         double profit = inv_period<NS, EXACT, S>(P, req, arr, (S)dl, I, B, Rf, s0, U);
         double reward = P.disc[t] * profit;
         ret += reward;  // Python: total += reward, in period order
-        if (A.reward_traj && valid) A.reward_traj[e * P.T + t] = reward;
-        s_sales += (long long)s0;
-        s_dem += dl > 0 ? dl : 0;
-        s_stock += (long long)U[0];
+        if (rtraj) rtraj[t] = reward;
+        s_sales += s0;
+        s_dem += (S)dl > 0 ? (S)dl : (S)0;
+        s_stock += U[0];
 #pragma unroll
         for (int i = 0; i < NS; i++)
-            if (EXACT || i < n) s_inv += I[i] > 0 ? (long long)I[i] : 0;
+            if (EXACT || i < n) s_inv += I[i] > 0 ? I[i] : (S)0;
         // ---- ring updates (branch-free) ------------------------------------------------------------------------
 #pragma unroll
         for (int i = 0; i < NS; i++)
@@ -638,7 +651,7 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
                 if (need_aring) {
                     S old = aring[slot];
                     aring[slot] = req[i];
-                    psum[i] = P.L[i] > 0 ? psum[i] + req[i] - old : (S)0;
+                    psum[i] = (psum[i] + req[i] - old) & lmask[i];  // stays 0 for a stage without lead time
                 }
                 const int np1 = rpos[i] + ROLL_THREADS;
                 rpos[i] = np1 == rlen[i] ? 0 : np1;
@@ -648,12 +661,13 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
     if (valid) {
         if (A.ep_return) A.ep_return[e] = ret;
         if (A.stats) {
-            longlong4 v = make_longlong4(s_sales, s_dem, s_stock, s_inv);
+            longlong4 v = make_longlong4((long long)s_sales, (long long)s_dem, (long long)s_stock, (long long)s_inv);
             *reinterpret_cast<longlong4*>(A.stats + e * 4) = v;
         }
         if (A.stats32) {
             auto sat = [](long long v) { return (int)(v > 2147483647LL ? 2147483647LL : (v < -2147483648LL ? -2147483648LL : v)); };
-            *reinterpret_cast<int4*>(A.stats32 + e * 4) = make_int4(sat(s_sales), sat(s_dem), sat(s_stock), sat(s_inv));
+            *reinterpret_cast<int4*>(A.stats32 + e * 4) =
+                make_int4(sat((long long)s_sales), sat((long long)s_dem), sat((long long)s_stock), sat((long long)s_inv));
         }
         if (A.final_I)
             for (int i = 0; i < n; i++) A.final_I[e * n + i] = (int64_t)I[i];
@@ -814,6 +828,9 @@ extern "C" int orgym_invmgmt_create(const orgym_invmgmt_config_t* cfg, int64_t n
     H->max_blocks = (int)((num_envs + ROLL_THREADS - 1) / ROLL_THREADS);
     H->hint_state = nullptr;
     H->hint_t = -1;
+    H->user_dmax = 0;
+    if (cfg->dist.kind == ORGYM_DIST_USER)
+        for (int t = 0; t < cfg->dist.user_D_len; t++) H->user_dmax = std::max<long long>(H->user_dmax, std::llabs(cfg->dist.user_D[t]));
     H->partials = nullptr;
     if (ce == cudaSuccess) {
         size_t pbytes = sizeof(double) * (8 * (size_t)H->max_blocks + ORGYM_REDUCE_EXTRA);
@@ -1012,8 +1029,18 @@ extern "C" int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t en
     A.final_B = out->final_B_dev;
     A.stats32 = out->stats32_dev;
     A.partials = out->summary_dev ? H->partials : nullptr;
-    // pre-staged actions may be arbitrary int64 -> exact wide arithmetic; on-device policies stay inside [0, c]
-    const bool wide = H->wide || in->policy == ORGYM_POLICY_ACTIONS;
+    // int32 arithmetic only when every state value and per-episode sum is provably below 2^31: on-device policy
+    // (requests within [0, c]), sampled demand (bounded support) and (T+1) * n * (c_max + I0_max + d_max) * 4 < 2^31;
+    // pre-staged actions / replayed demand may be arbitrary int64 -> exact wide arithmetic
+    long long vmax = 0;
+    for (int i = 0; i < P.n; i++) vmax = std::max(vmax, std::max(P.c[i], P.I0[i]));
+    long long dmax = P.dem.kind == ORGYM_DIST_USER ? (1LL << 40) : (long long)P.dem.base + (1LL << P.dem.log2k);
+    if (P.dem.kind == ORGYM_DIST_USER && !in->demand_dev) {
+        dmax = 0;  // trace values were copied to the device at create; bound them through the config-time maximum
+        dmax = H->user_dmax;
+    }
+    const bool bounded = (double)(P.T + 1) * P.n * (double)(vmax + dmax) * 4.0 < 2147483648.0;
+    const bool wide = H->wide || in->policy == ORGYM_POLICY_ACTIONS || in->demand_dev != nullptr || !bounded;
     size_t ring = (size_t)A.rslots * ROLL_THREADS * (wide ? 8 : 4);
     size_t smem = (P.dem.kind == ORGYM_DIST_USER ? 0 : (size_t(8) << P.dem.log2k)) +
                   ring * (in->policy == ORGYM_POLICY_BASE_STOCK ? 2 : 1);
