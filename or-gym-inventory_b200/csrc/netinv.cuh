@@ -36,6 +36,7 @@ struct NetHandle {
     JitKernel jit;             // module + STEP kernel
     cudaKernel_t jit_rollout;  // ROLLOUT kernel of the same module
     int jit_threads;
+    int jit_stream;            // STEP kernel is the streaming variant (large graphs)
     AliasDev* dem_dev;  // device copy of dev.dem[] for the specialised kernel
 };
 
@@ -60,8 +61,9 @@ struct NetState {
         episode = (uint32_t*)p;
     }
 };
+// ... followed by a per-instance scratch area [R_t E][consumed J] float64 used by the streaming STEP kernel
 static int64_t net_state_bytes(const NetDev& P, int64_t npad) {
-    return npad * (8 + 8 * (int64_t)(P.J + P.E + P.M + P.sumL) + 8);
+    return npad * (8 + 8 * (int64_t)(P.J + P.E + P.M + P.sumL) + 8 + 8 * (int64_t)(P.E + P.J));
 }
 
 
@@ -69,3 +71,4 @@ static int64_t net_state_bytes(const NetDev& P, int64_t npad) {
 int net_jit_build(NetHandle* H, std::string* err);
 int net_jit_launch(const NetHandle* H, const struct NetSimArgs& A, cudaStream_t s);
 std::string net_jit_source(const NetDev& P, int nthr);
+int net_jit_uses_stream(const NetDev& P);

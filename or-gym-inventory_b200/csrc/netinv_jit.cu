@@ -6,7 +6,9 @@
 // straight-line CUDA source for ONE topology -- literal link / node indices, literal prices and lead times, per-
 // instance state in registers -- compiled for sm_100a with NVRTC when the env is created.  Evaluation order of every
 // floating-point expression is exactly the generic kernel's (= the reference's); the parity tests run both.
+#include <algorithm>
 #include <cstdarg>
+#include <vector>
 
 #include "netinv.cuh"
 #include "netinv_args.cuh"
@@ -31,7 +33,14 @@ std::string lit(double v) {
     snprintf(buf, sizeof(buf), "%a", v);
     return buf;
 }
+void emit_step_stream(Src& o, const NetDev& P, int min_blocks);
 }  // namespace
+
+int net_jit_uses_stream(const NetDev& P) {
+    int stream = 2 * P.J + 3 * P.E + 2 * P.M > 128 ? 1 : 0;
+    if (const char* sv = getenv("ORGYM_NET_JIT_STREAM")) stream = atoi(sv) ? 1 : 0;
+    return stream;
+}
 
 std::string net_jit_source(const NetDev& P, int nthr) {
     const int J = P.J, E = P.E, M = P.M;
@@ -290,15 +299,230 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     int mb_step = big ? 2 : 5, mb_roll = big ? 1 : 3;
     if (const char* mb = getenv("ORGYM_NET_JIT_MINBLOCKS_STEP")) mb_step = atoi(mb) > 0 ? atoi(mb) : 1;
     if (const char* mb = getenv("ORGYM_NET_JIT_MINBLOCKS_ROLLOUT")) mb_roll = atoi(mb) > 0 ? atoi(mb) : 1;
-    emit_kernel("net_jit_step", 0, mb_step);
+    const int stream = net_jit_uses_stream(P);  // large graphs: state stays in HBM, coalesced 32-column tiles
+    if (stream)
+        emit_step_stream(o, P, 4);
+    else
+        emit_kernel("net_jit_step", 0, mb_step);
     emit_kernel("net_jit_rollout", 1, mb_roll);
+    o("// step_kernel_kind=%s", stream ? "stream" : "register");
     return o.s;
 }
+
+
+// ---- streaming STEP kernel for large graphs --------------------------------------------------------------------------------
+// With hundreds of float64 values per instance the register-resident kernel above spills and runs at 2 CTAs/SM.  In
+// STEP mode the state lives in HBM anyway, so this variant never keeps it in registers: pass A walks the sorted links,
+// allocates orders and parks R_t / consumed in a per-instance scratch area of the state buffer; pass B walks the main
+// nodes, and for each one loads exactly what it needs (its X, consumed, the arrivals / pipeline entries of its
+// predecessor links, the backlog of its market links, the R_t of its successor links), updates state in place and
+// finishes the node's profit; pass C rebuilds the observation from the final state.  Same operations in the same
+// order as the other kernels; few live registers -> many resident warps -> the loads overlap.  The row-major action
+// and observation blocks move through 32-column shared-memory tiles, so every global access is coalesced whatever
+// the observation length.
+namespace {
+void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
+    const int J = P.J, E = P.E, M = P.M, W = P.obs_dim;
+    std::vector<int> has_seg(J, 0);
+    for (int i = 0; i < E; i++)
+        if (P.sup[i] >= 0) has_seg[P.sup[i]] = 1;
+    o("extern \"C\" __global__ void __launch_bounds__(NTHR, %d) net_jit_step(const NetSimArgs A, const double* __restrict__ disc,", min_blocks);
+    o("    const AliasDev* __restrict__ dem) {");
+    o("  __shared__ float tile[NTHR * 33];   // 32-column staging tile (+1 padding column: conflict-free)");
+    o("  const int tid = threadIdx.x;");
+    o("  const long long e0 = (long long)blockIdx.x * NTHR, e = e0 + tid, np = A.npad;");
+    o("  const int nvalid = (int)((A.N - e0) < NTHR ? (A.N - e0) : NTHR);");
+    o("  const bool valid = tid < nvalid;");
+    o("  char* sb = (char*)A.state;");
+    o("  unsigned long long* s_key = (unsigned long long*)sb;");
+    o("  double* s_X = (double*)(sb + 8 * np); double* s_Y = s_X + (long long)NJ * np; double* s_U = s_Y + (long long)NE * np;");
+    o("  double* ring = s_U + (long long)NM * np;");
+    o("  int* s_period = (int*)(ring + (long long)NSUML * np); unsigned int* s_episode = (unsigned int*)(s_period + np);");
+    o("  double* sc_R = (double*)(s_episode + np); double* sc_C = sc_R + (long long)NE * np;");
+    o("  float* trow = tile + tid * 33;");
+    o("  bool do_step = valid;");
+    o("  int t = 0; unsigned int episode = 0; unsigned long long key = 0;");
+    o("  if (valid) {");
+    o("    t = s_period[e]; episode = s_episode[e]; key = s_key[e];");
+    o("    if (t >= NT) {");
+    o("      do_step = false;");
+    o("      if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {");
+    for (int j = 0; j < J; j++) o("        s_X[(long long)%d * np + e] = %s;", j, lit(P.I0[j]).c_str());
+    o("        for (int i = 0; i < NE; i++) s_Y[(long long)i * np + e] = 0.0;");
+    o("        for (int r = 0; r < NM; r++) s_U[(long long)r * np + e] = 0.0;");
+    o("        for (int k = 0; k < NSUML; k++) ring[(long long)k * np + e] = 0.0;");
+    o("        s_period[e] = 0; s_episode[e] = episode + 1;");
+    o("        A.reward[e] = 0.0; A.terminated[e] = 0; A.truncated[e] = 0;");
+    o("      } else {");
+    o("        atomicOr(A.err, ORGYM_ERR_STEP_PAST_END);");
+    o("        A.reward[e] = 0.0; A.terminated[e] = 0; A.truncated[e] = 1;");
+    o("      }");
+    o("    }");
+    o("  }");
+    // ---- pass A: orders, 32 links per action chunk
+    o("  double cons = 0.0;");
+    for (int c0 = 0; c0 < E; c0 += 32) {
+        const int c1 = std::min(E, c0 + 32);
+        o("  __syncthreads();");
+        o("  for (int i = tid; i < nvalid * 32; i += NTHR) { const int r = i >> 5, c = i & 31;");
+        o("    if (%d + c < NE) tile[r * 33 + c] = A.actions[(e0 + r) * NE + %d + c]; }", c0, c0);
+        o("  __syncthreads();");
+        o("  if (do_step) {");
+        for (int i = c0; i < c1; i++) {
+            const int s = P.sup[i];
+            o("    { double req = rint((double)trow[%d]); req = req > 0.0 ? req : 0.0; double f;", i - c0);
+            if (s == -1)
+                o("      f = req;");
+            else if (s < 0)
+                o("      f = 0.0; (void)req;");
+            else {
+                if (i == 0 || P.sup[i - 1] != s) o("      cons = 0.0;");
+                o("      double avail = s_X[(long long)%d * np + e] - cons; avail = avail > 0.0 ? avail : 0.0; double oa = avail;", s);
+                if (P.is_factory[s])
+                    o("      { double mp = %s * avail; double lim = mp < %s ? mp : %s; oa = lim < oa ? lim : oa; }",
+                      lit(P.v[s]).c_str(), lit(P.C[s]).c_str(), lit(P.C[s]).c_str());
+                o("      f = oa < req ? oa : req;");
+                if (P.v[s] == 1.0)
+                    o("      cons += f;");
+                else
+                    o("      cons += f / %s;", lit(P.v[s]).c_str());
+                if (i == E - 1 || P.sup[i + 1] != s) o("      sc_C[(long long)%d * np + e] = cons;", s);
+            }
+            o("      sc_R[(long long)%d * np + e] = f;", i);
+            o("      if (A.info_sales) A.info_sales[e * (NE + NM) + %d] = f; }", i);
+        }
+        o("  }");
+    }
+    // ---- pass B: nodes
+    o("  if (do_step) {");
+    o("    double total = 0.0;");
+    std::vector<int> link_done(E, 0);
+    for (int j = 0; j < J; j++) {
+        o("    { double x = s_X[(long long)%d * np + e]; double arr = 0.0, PC = 0.0, HCp = 0.0;", j);
+        for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
+            const int i = P.pred_idx[z], L = P.L[i];
+            link_done[i] = 1;
+            o("      { const double rt = sc_R[(long long)%d * np + e];", i);
+            if (L == 0)
+                o("        const double ar = rt;");
+            else
+                o("        double* slot = ring + (long long)(%d + t %% %d) * np + e; const double ar = *slot; *slot = rt;", P.roff[i], L);
+            o("        arr += ar; const double yn = (s_Y[(long long)%d * np + e] - ar) + rt; s_Y[(long long)%d * np + e] = yn;", i, i);
+            o("        PC += %s * rt; HCp += %s * (yn > 0.0 ? yn : 0.0); }", lit(P.p[i]).c_str(), lit(P.g[i]).c_str());
+        }
+        if (has_seg[j])
+            o("      x = (x + arr) - sc_C[(long long)%d * np + e];", j);
+        else
+            o("      x = (x + arr) - 0.0;");
+        o("      double SR = 0.0, sold = 0.0, UP = 0.0;");
+        for (int r = 0; r < M; r++) {
+            if (P.rt_node[r] != j) continue;
+            o("      double S%d, U%d;", r, r);
+            o("      { double d;");
+            o("        if (A.demand) d = rint(A.demand[e * A.d_se + %d]);", r);
+            o("        else d = (double)sample_fixed(dem[%d], dem[%d].table, key, episode, t, %du);", r, r, r);
+            o("        d = d > 0.0 ? d : 0.0;");
+            o("        const double fill = d + s_U[(long long)%d * np + e]; const double invr = x > 0.0 ? x : 0.0;", r);
+            o("        S%d = invr < fill ? invr : fill; x = x - S%d; const double un = fill - S%d; U%d = %s;", r, r, r, r,
+              P.backlog ? "un" : "0.0");
+            o("        s_U[(long long)%d * np + e] = U%d;", r, r);
+            o("        if (A.info_demand) A.info_demand[e * NM + %d] = d;", r);
+            o("        if (A.info_sales) A.info_sales[e * (NE + NM) + %d] = S%d; }", E + r, r);
+        }
+        o("      s_X[(long long)%d * np + e] = x;", j);
+        for (int z = P.succ_ptr[j]; z < P.succ_ptr[j + 1]; z++) {
+            const int l = P.succ_idx[z];
+            if (l < E)
+                o("      { const double q = sc_R[(long long)%d * np + e]; SR += %s * q; sold += q; }", l, lit(P.p[l]).c_str());
+            else {
+                const int r = l - E;
+                if (P.is_retail[j]) o("      UP += %s * U%d;", lit(P.rt_b[r]).c_str(), r);
+                o("      SR += %s * S%d; sold += S%d;", lit(P.rt_p[r]).c_str(), r, r);
+            }
+        }
+        o("      const double xp = x > 0.0 ? x : 0.0; const double HC = %s * xp + HCp; double OC = 0.0;", lit(P.h[j]).c_str());
+        if (P.is_factory[j]) {
+            if (!(P.v[j] > 0.0))
+                o("      OC = 0.0;");
+            else if (P.v[j] == 1.0)
+                o("      OC = %s * sold;", lit(P.o[j]).c_str());
+            else
+                o("      OC = %s * (sold / %s);", lit(P.o[j]).c_str(), lit(P.v[j]).c_str());
+        }
+        o("      (void)sold; const double pj = (((SR - PC) - OC) - HC) - UP; total += pj;");
+        o("      if (A.info_profit) A.info_profit[e * NJ + %d] = pj; }", j);
+    }
+    for (int i = 0; i < E; i++) {  // reorder links whose purchaser holds no inventory: pipeline bookkeeping only
+        if (link_done[i]) continue;
+        const int L = P.L[i];
+        o("    { const double rt = sc_R[(long long)%d * np + e];", i);
+        if (L == 0)
+            o("      const double ar = rt;");
+        else
+            o("      double* slot = ring + (long long)(%d + t %% %d) * np + e; const double ar = *slot; *slot = rt;", P.roff[i], L);
+        o("      s_Y[(long long)%d * np + e] = (s_Y[(long long)%d * np + e] - ar) + rt; }", i, i);
+    }
+    o("    const int tn = t + 1; const bool trunc = tn >= NT;");
+    o("    if (A.info_profit_total) A.info_profit_total[e] = total;");
+    o("    A.reward[e] = disc[t] * total; A.terminated[e] = 0; A.truncated[e] = trunc ? 1 : 0;");
+    o("    if (trunc && A.autoreset == ORGYM_AUTORESET_SAME_STEP) {");
+    o("      if (A.final_obs) { double X[NJ], U[NM > 0 ? NM : 1];");
+    o("        for (int j = 0; j < NJ; j++) X[j] = s_X[(long long)j * np + e];");
+    o("        for (int r = 0; r < NM; r++) U[r] = s_U[(long long)r * np + e];");
+    o("        write_obs(X, U, ring, np, e, tn, A.final_obs + e * NOBS); }");
+    for (int j = 0; j < J; j++) o("      s_X[(long long)%d * np + e] = %s;", j, lit(P.I0[j]).c_str());
+    o("      for (int i = 0; i < NE; i++) s_Y[(long long)i * np + e] = 0.0;");
+    o("      for (int r = 0; r < NM; r++) s_U[(long long)r * np + e] = 0.0;");
+    o("      for (int k = 0; k < NSUML; k++) ring[(long long)k * np + e] = 0.0;");
+    o("      s_period[e] = 0; s_episode[e] = episode + 1;");
+    o("    } else s_period[e] = tn;");
+    o("  }");
+    // ---- pass C: observation of the final state, 32 columns at a time
+    o("  const int tobs = valid ? s_period[e] : 0;");
+    {
+        // column -> source expression
+        std::vector<std::string> col((size_t)W);
+        char buf[256];
+        for (int r = 0; r < M; r++) {
+            snprintf(buf, sizeof(buf), "s_U[(long long)%d * np + e]", r);
+            col[(size_t)r] = buf;
+        }
+        for (int j = 0; j < J; j++) {
+            snprintf(buf, sizeof(buf), "s_X[(long long)%d * np + e]", j);
+            col[(size_t)(M + j)] = buf;
+        }
+        int k = M + J;
+        for (int i = 0; i < E; i++) {
+            const int L = P.L[i];
+            if (L == 0) continue;
+            o("  const int w%d = tobs %% %d;", i, L);
+            for (int q = 0; q < L; q++) {
+                snprintf(buf, sizeof(buf), "ring[(long long)(%d + (w%d + %d >= %d ? w%d + %d - %d : w%d + %d)) * np + e]", P.roff[i], i, q, L,
+                         i, q, L, i, q);
+                col[(size_t)(k + q)] = buf;
+            }
+            k += L;
+        }
+        for (int c0 = 0; c0 < W; c0 += 32) {
+            const int c1 = std::min(W, c0 + 32);
+            o("  if (valid) {");
+            for (int c = c0; c < c1; c++) o("    trow[%d] = (float)%s;", c - c0, col[(size_t)c].c_str());
+            o("  }");
+            o("  __syncthreads();");
+            o("  for (int i = tid; i < nvalid * 32; i += NTHR) { const int r = i >> 5, c = i & 31;");
+            o("    if (%d + c < NOBS) __stcs(A.obs + (e0 + r) * NOBS + %d + c, tile[r * 33 + c]); }", c0, c0);
+            o("  __syncthreads();");
+        }
+    }
+    o("}");
+}
+}  // namespace
 
 int net_jit_build(NetHandle* H, std::string* err) {
     const NetDev& P = H->dev;
     H->jit_threads = 128;
     std::string src = net_jit_source(P, H->jit_threads);
+    H->jit_stream = net_jit_uses_stream(P);
     int rc = orgym_jit_compile(src, "net_jit_step", &H->jit, err);
     if (rc != 0) return rc;
     if (cudaLibraryGetKernel(&H->jit_rollout, H->jit.lib, "net_jit_rollout") != cudaSuccess) {
@@ -328,7 +552,9 @@ int net_jit_launch(const NetHandle* H, const NetSimArgs& A_in, cudaStream_t s) {
     const int nthr = H->jit_threads;
     size_t tile = (size_t)nthr * (P.obs_dim | 1) * 4;
     size_t smem = 16;
-    if (!A.rollout) {
+    if (!A.rollout && H->jit_stream) {
+        A.use_tile = 0;  // the streaming kernel stages through its own static 32-column tile
+    } else if (!A.rollout) {
         A.use_tile = tile <= 160 * 1024 ? 1 : 0;
         if (A.use_tile) smem = tile;
     } else

@@ -14,11 +14,13 @@ def _torch():
     return torch
 
 
-@pytest.fixture(params=["specialised", "generic"])
+@pytest.fixture(params=["specialised", "stream", "generic"])
 def kernel_mode(request, monkeypatch):
-    """Run the parity tests through both network kernels: the NVRTC-specialised one (must compile) and the
-    generic constant-bank interpreter."""
-    monkeypatch.setenv("ORGYM_NET_JIT", "2" if request.param == "specialised" else "0")
+    """Run the parity tests through all network kernels: the NVRTC-specialised register-resident one, the
+    NVRTC-specialised streaming STEP kernel (meant for large graphs, forced here), and the generic constant-bank
+    interpreter."""
+    monkeypatch.setenv("ORGYM_NET_JIT", "0" if request.param == "generic" else "2")
+    monkeypatch.setenv("ORGYM_NET_JIT_STREAM", "1" if request.param == "stream" else "0")
     return request.param
 
 

@@ -129,12 +129,13 @@ def _random_graph(rng):
     return g
 
 
-@pytest.mark.parametrize("mode", ["specialised", "generic"])
+@pytest.mark.parametrize("mode", ["specialised", "stream", "generic"])
 @pytest.mark.parametrize("case", range(6))
 def test_netinv_random_graph(case, mode, monkeypatch):
     from oracle import oracle
     torch = _torch()
-    monkeypatch.setenv("ORGYM_NET_JIT", "2" if mode == "specialised" else "0")
+    monkeypatch.setenv("ORGYM_NET_JIT", "0" if mode == "generic" else "2")
+    monkeypatch.setenv("ORGYM_NET_JIT_STREAM", "1" if mode == "stream" else "0")
     rng = np.random.default_rng(3000 + case)
     g = _random_graph(rng)
     T = int(rng.integers(4, 26))
