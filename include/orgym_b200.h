@@ -337,7 +337,9 @@ int orgym_netinv_rollout(orgym_handle_t h, void* scratch_dev, uint64_t seed, int
 
 /* The network kernels are specialised per topology at create time: the flattened graph is emitted as straight-line
  * CUDA source and compiled for sm_100a with NVRTC (fallback: a generic kernel that reads the topology from the
- * constant bank; ORGYM_NET_JIT=0 forces it, =2 makes a failed specialisation an error).  This entry point returns
+ * constant bank; automatic up to 128 reorder links, ORGYM_NET_JIT=0 forces the generic kernel, =1 specialises any
+ * size, =2 additionally makes a failed specialisation an error; cubins are cached under $ORGYM_JIT_CACHE or
+ * ~/.cache/orgym_b200).  This entry point returns
  * that source for inspection and, with compile_check != 0, runs it through NVRTC; it needs no GPU. */
 int orgym_netinv_codegen(const orgym_netinv_config_t* cfg, int compile_check, char* buf, int64_t buflen,
                          int64_t* needed);

@@ -300,8 +300,11 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     if (const char* mb = getenv("ORGYM_NET_JIT_MINBLOCKS_STEP")) mb_step = atoi(mb) > 0 ? atoi(mb) : 1;
     if (const char* mb = getenv("ORGYM_NET_JIT_MINBLOCKS_ROLLOUT")) mb_roll = atoi(mb) > 0 ? atoi(mb) : 1;
     const int stream = net_jit_uses_stream(P);  // large graphs: state stays in HBM, coalesced 32-column tiles
-    if (stream)
-        emit_step_stream(o, P, 4);
+    if (stream) {
+        int mb = 4;
+        if (const char* mbv = getenv("ORGYM_NET_JIT_MINBLOCKS_STEP")) mb = atoi(mbv) > 0 ? atoi(mbv) : 4;
+        emit_step_stream(o, P, mb);
+    }
     else
         emit_kernel("net_jit_step", 0, mb_step);
     emit_kernel("net_jit_rollout", 1, mb_roll);
@@ -361,6 +364,8 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
     o("  }");
     // ---- pass A: orders, 32 links per action chunk
     o("  double cons = 0.0;");
+    for (int j = 0; j < J; j++)
+        if (has_seg[j]) o("  double xs%d = 0.0;", j);
     for (int c0 = 0; c0 < E; c0 += 32) {
         const int c1 = std::min(E, c0 + 32);
         o("  __syncthreads();");
@@ -368,6 +373,11 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
         o("    if (%d + c < NE) tile[r * 33 + c] = A.actions[(e0 + r) * NE + %d + c]; }", c0, c0);
         o("  __syncthreads();");
         o("  if (do_step) {");
+        // independent loads first: the on-hand inventory of every supplier whose segment starts in this chunk
+        for (int i = c0; i < c1; i++) {
+            const int s = P.sup[i];
+            if (s >= 0 && (i == 0 || P.sup[i - 1] != s)) o("    xs%d = s_X[(long long)%d * np + e];", s, s);
+        }
         for (int i = c0; i < c1; i++) {
             const int s = P.sup[i];
             o("    { double req = rint((double)trow[%d]); req = req > 0.0 ? req : 0.0; double f;", i - c0);
@@ -377,7 +387,7 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
                 o("      f = 0.0; (void)req;");
             else {
                 if (i == 0 || P.sup[i - 1] != s) o("      cons = 0.0;");
-                o("      double avail = s_X[(long long)%d * np + e] - cons; avail = avail > 0.0 ? avail : 0.0; double oa = avail;", s);
+                o("      double avail = xs%d - cons; avail = avail > 0.0 ? avail : 0.0; double oa = avail;", s);
                 if (P.is_factory[s])
                     o("      { double mp = %s * avail; double lim = mp < %s ? mp : %s; oa = lim < oa ? lim : oa; }",
                       lit(P.v[s]).c_str(), lit(P.C[s]).c_str(), lit(P.C[s]).c_str());
@@ -397,60 +407,87 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
     o("  if (do_step) {");
     o("    double total = 0.0;");
     std::vector<int> link_done(E, 0);
-    for (int j = 0; j < J; j++) {
-        o("    { double x = s_X[(long long)%d * np + e]; double arr = 0.0, PC = 0.0, HCp = 0.0;", j);
-        for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
-            const int i = P.pred_idx[z], L = P.L[i];
-            link_done[i] = 1;
-            o("      { const double rt = sc_R[(long long)%d * np + e];", i);
-            if (L == 0)
-                o("        const double ar = rt;");
-            else
-                o("        double* slot = ring + (long long)(%d + t %% %d) * np + e; const double ar = *slot; *slot = rt;", P.roff[i], L);
-            o("        arr += ar; const double yn = (s_Y[(long long)%d * np + e] - ar) + rt; s_Y[(long long)%d * np + e] = yn;", i, i);
-            o("        PC += %s * rt; HCp += %s * (yn > 0.0 ? yn : 0.0); }", lit(P.p[i]).c_str(), lit(P.g[i]).c_str());
-        }
-        if (has_seg[j])
-            o("      x = (x + arr) - sc_C[(long long)%d * np + e];", j);
-        else
-            o("      x = (x + arr) - 0.0;");
-        o("      double SR = 0.0, sold = 0.0, UP = 0.0;");
-        for (int r = 0; r < M; r++) {
-            if (P.rt_node[r] != j) continue;
-            o("      double S%d, U%d;", r, r);
-            o("      { double d;");
-            o("        if (A.demand) d = rint(A.demand[e * A.d_se + %d]);", r);
-            o("        else d = (double)sample_fixed(dem[%d], dem[%d].table, key, episode, t, %du);", r, r, r);
-            o("        d = d > 0.0 ? d : 0.0;");
-            o("        const double fill = d + s_U[(long long)%d * np + e]; const double invr = x > 0.0 ? x : 0.0;", r);
-            o("        S%d = invr < fill ? invr : fill; x = x - S%d; const double un = fill - S%d; U%d = %s;", r, r, r, r,
-              P.backlog ? "un" : "0.0");
-            o("        s_U[(long long)%d * np + e] = U%d;", r, r);
-            o("        if (A.info_demand) A.info_demand[e * NM + %d] = d;", r);
-            o("        if (A.info_sales) A.info_sales[e * (NE + NM) + %d] = S%d; }", E + r, r);
-        }
-        o("      s_X[(long long)%d * np + e] = x;", j);
-        for (int z = P.succ_ptr[j]; z < P.succ_ptr[j + 1]; z++) {
-            const int l = P.succ_idx[z];
-            if (l < E)
-                o("      { const double q = sc_R[(long long)%d * np + e]; SR += %s * q; sold += q; }", l, lit(P.p[l]).c_str());
-            else {
-                const int r = l - E;
-                if (P.is_retail[j]) o("      UP += %s * U%d;", lit(P.rt_b[r]).c_str(), r);
-                o("      SR += %s * S%d; sold += S%d;", lit(P.rt_p[r]).c_str(), r, r);
+    // Nodes are independent of each other in this pass (every link has one purchaser, every market link one retailer;
+    // R_t / consumed are read-only here), so they are processed in groups: all loads of a group are issued first
+    // (dozens of independent loads in flight), then the group's arithmetic and stores.
+    int GROUP = 4;
+    if (const char* gv = getenv("ORGYM_NET_JIT_GROUP")) GROUP = atoi(gv) > 0 ? atoi(gv) : 4;
+    for (int j0 = 0; j0 < J; j0 += GROUP) {
+        const int j1 = std::min(J, j0 + GROUP);
+        o("    {");
+        for (int j = j0; j < j1; j++) {  // load phase
+            o("      double x%d = s_X[(long long)%d * np + e];", j, j);
+            if (has_seg[j]) o("      const double c%d = sc_C[(long long)%d * np + e];", j, j);
+            for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
+                const int i = P.pred_idx[z], L = P.L[i];
+                o("      const double rt%d = sc_R[(long long)%d * np + e]; const double y%d = s_Y[(long long)%d * np + e];", i, i, i, i);
+                if (L > 0) {
+                    o("      double* const slot%d = ring + (long long)(%d + t %% %d) * np + e; const double ar%d = *slot%d;", i, P.roff[i], L,
+                      i, i);
+                }
+            }
+            for (int r = 0; r < M; r++)
+                if (P.rt_node[r] == j) o("      const double u%d = s_U[(long long)%d * np + e];", r, r);
+            for (int z = P.succ_ptr[j]; z < P.succ_ptr[j + 1]; z++) {
+                const int l = P.succ_idx[z];
+                if (l < E) o("      const double qs%d_%d = sc_R[(long long)%d * np + e];", j, l, l);
             }
         }
-        o("      const double xp = x > 0.0 ? x : 0.0; const double HC = %s * xp + HCp; double OC = 0.0;", lit(P.h[j]).c_str());
-        if (P.is_factory[j]) {
-            if (!(P.v[j] > 0.0))
-                o("      OC = 0.0;");
-            else if (P.v[j] == 1.0)
-                o("      OC = %s * sold;", lit(P.o[j]).c_str());
+        for (int j = j0; j < j1; j++) {  // compute + store phase
+            o("      { double arr = 0.0, PC = 0.0, HCp = 0.0;");
+            for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
+                const int i = P.pred_idx[z], L = P.L[i];
+                link_done[i] = 1;
+                if (L == 0)
+                    o("        { const double ar = rt%d;", i);
+                else
+                    o("        { const double ar = ar%d; *slot%d = rt%d;", i, i, i);
+                o("          arr += ar; const double yn = (y%d - ar) + rt%d; s_Y[(long long)%d * np + e] = yn;", i, i, i);
+                o("          PC += %s * rt%d; HCp += %s * (yn > 0.0 ? yn : 0.0); }", lit(P.p[i]).c_str(), i, lit(P.g[i]).c_str());
+            }
+            if (has_seg[j])
+                o("        double x = (x%d + arr) - c%d;", j, j);
             else
-                o("      OC = %s * (sold / %s);", lit(P.o[j]).c_str(), lit(P.v[j]).c_str());
+                o("        double x = (x%d + arr) - 0.0;", j);
+            o("        double SR = 0.0, sold = 0.0, UP = 0.0;");
+            for (int r = 0; r < M; r++) {
+                if (P.rt_node[r] != j) continue;
+                o("        double S%d, U%d;", r, r);
+                o("        { double d;");
+                o("          if (A.demand) d = rint(A.demand[e * A.d_se + %d]);", r);
+                o("          else d = (double)sample_fixed(dem[%d], dem[%d].table, key, episode, t, %du);", r, r, r);
+                o("          d = d > 0.0 ? d : 0.0;");
+                o("          const double fill = d + u%d; const double invr = x > 0.0 ? x : 0.0;", r);
+                o("          S%d = invr < fill ? invr : fill; x = x - S%d; const double un = fill - S%d; U%d = %s;", r, r, r, r,
+                  P.backlog ? "un" : "0.0");
+                o("          s_U[(long long)%d * np + e] = U%d;", r, r);
+                o("          if (A.info_demand) A.info_demand[e * NM + %d] = d;", r);
+                o("          if (A.info_sales) A.info_sales[e * (NE + NM) + %d] = S%d; }", E + r, r);
+            }
+            o("        s_X[(long long)%d * np + e] = x;", j);
+            for (int z = P.succ_ptr[j]; z < P.succ_ptr[j + 1]; z++) {
+                const int l = P.succ_idx[z];
+                if (l < E)
+                    o("        SR += %s * qs%d_%d; sold += qs%d_%d;", lit(P.p[l]).c_str(), j, l, j, l);
+                else {
+                    const int r = l - E;
+                    if (P.is_retail[j]) o("        UP += %s * U%d;", lit(P.rt_b[r]).c_str(), r);
+                    o("        SR += %s * S%d; sold += S%d;", lit(P.rt_p[r]).c_str(), r, r);
+                }
+            }
+            o("        const double xp = x > 0.0 ? x : 0.0; const double HC = %s * xp + HCp; double OC = 0.0;", lit(P.h[j]).c_str());
+            if (P.is_factory[j]) {
+                if (!(P.v[j] > 0.0))
+                    o("        OC = 0.0;");
+                else if (P.v[j] == 1.0)
+                    o("        OC = %s * sold;", lit(P.o[j]).c_str());
+                else
+                    o("        OC = %s * (sold / %s);", lit(P.o[j]).c_str(), lit(P.v[j]).c_str());
+            }
+            o("        (void)sold; const double pj = (((SR - PC) - OC) - HC) - UP; total += pj;");
+            o("        if (A.info_profit) A.info_profit[e * NJ + %d] = pj; }", j);
         }
-        o("      (void)sold; const double pj = (((SR - PC) - OC) - HC) - UP; total += pj;");
-        o("      if (A.info_profit) A.info_profit[e * NJ + %d] = pj; }", j);
+        o("    }");
     }
     for (int i = 0; i < E; i++) {  // reorder links whose purchaser holds no inventory: pipeline bookkeeping only
         if (link_done[i]) continue;
@@ -503,15 +540,24 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
             }
             k += L;
         }
-        for (int c0 = 0; c0 < W; c0 += 32) {
+        // double-buffered: the loads of chunk c+1 are issued before chunk c is flushed, so their latency overlaps the flush
+        o("  float v[32], vn[32];");
+        auto emit_loads = [&](const char* dst, int c0) {
             const int c1 = std::min(W, c0 + 32);
             o("  if (valid) {");
-            for (int c = c0; c < c1; c++) o("    trow[%d] = (float)%s;", c - c0, col[(size_t)c].c_str());
+            for (int c = c0; c < c1; c++) o("    %s[%d] = (float)%s;", dst, c - c0, col[(size_t)c].c_str());
             o("  }");
+        };
+        emit_loads("v", 0);
+        for (int c0 = 0; c0 < W; c0 += 32) {
+            const int c1 = std::min(W, c0 + 32);
+            if (c0 + 32 < W) emit_loads("vn", c0 + 32);
+            o("  _Pragma(\"unroll\") for (int c = 0; c < %d; c++) trow[c] = v[c];", c1 - c0);
             o("  __syncthreads();");
             o("  for (int i = tid; i < nvalid * 32; i += NTHR) { const int r = i >> 5, c = i & 31;");
             o("    if (%d + c < NOBS) __stcs(A.obs + (e0 + r) * NOBS + %d + c, tile[r * 33 + c]); }", c0, c0);
             o("  __syncthreads();");
+            if (c0 + 32 < W) o("  _Pragma(\"unroll\") for (int c = 0; c < 32; c++) v[c] = vn[c];");
         }
     }
     o("}");

@@ -327,9 +327,10 @@ class NetInvMgmtMasterEnv(BatchedEnv):
     def __init__(self, *args, num_envs: int = 1, device="cuda", env_offset: int = 0,
                  autoreset_mode: str = "next_step", info_level: int = 1, specialise: Optional[bool] = None,
                  record_history: bool = False, **kwargs):
-        """specialise: True = compile kernels for this topology with NVRTC at construction (seconds for small graphs,
-        ~20 s for a 64-node one; 2-5x faster stepping), False = generic kernel, None = automatic (graphs with up to
-        48 reorder links).  The environment variable ORGYM_NET_JIT (0/1/2) takes precedence when set."""
+        """specialise: True = compile kernels for this topology with NVRTC at construction (1-2 s for small graphs,
+        10-15 s for the 64-node one, then cached on disk; 3-5x faster stepping), False = generic kernel, None =
+        automatic (graphs with up to 128 reorder links).  The environment variable ORGYM_NET_JIT (0/1/2) takes
+        precedence when set."""
         torch = _torch()
         self.record_history = bool(record_history)
         if self.record_history:

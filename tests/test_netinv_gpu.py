@@ -121,13 +121,16 @@ def test_class_surface_and_constant_policy(kernel_mode):
     env.close()
 
 
-def test_synthetic_64_node_network_vs_oracle():
-    """Config 5's synthetic 64-node network (lost sales): random actions, device demand, vs the oracle."""
+@pytest.mark.parametrize("spec", [True, False], ids=["specialised-streaming", "generic"])
+def test_synthetic_64_node_network_vs_oracle(spec):
+    """Config 5's synthetic 64-node network (lost sales): random actions, device demand, vs the oracle -- through the
+    specialised kernels (streaming STEP kernel for large graphs) and the generic one."""
     from oracle import oracle
     torch = _torch()
     G = pkg.synthetic_graph(64)
     N = 300
-    env = pkg.NetInvMgmtMasterEnv(graph=G, backlog=False, num_envs=N, device="cuda:0")
+    env = pkg.NetInvMgmtMasterEnv(graph=G, backlog=False, num_envs=N, device="cuda:0", specialise=spec)
+    assert env.specialised == spec
     P = env.params
     E, M, T = len(P.reorder_links), len(P.retail_links), env.num_periods
     assert len(G.nodes) == 64

@@ -3,7 +3,7 @@ sys.path.insert(0, "/root/repo")
 import torch
 import or_gym_inventory_b200 as pkg
 G = pkg.synthetic_graph(64)
-N = 1 << 17
+N = int(os.environ.get('N64', 1 << 17))
 t0 = time.time()
 env = pkg.NetInvMgmtMasterEnv(graph=G, backlog=False, num_envs=N, device="cuda:0")
 print("create s", round(time.time() - t0, 1), "E", len(env.reorder_links), "J", len(env.main_nodes), "M", len(env.retail_links), "obs", env.obs_dim)
