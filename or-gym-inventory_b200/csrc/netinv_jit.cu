@@ -541,23 +541,27 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
             k += L;
         }
         // double-buffered: the loads of chunk c+1 are issued before chunk c is flushed, so their latency overlaps the flush
-        o("  float v[32], vn[32];");
+        int dbuf = 1;
+        if (const char* dv = getenv("ORGYM_NET_JIT_DBUF")) dbuf = atoi(dv) ? 1 : 0;
+        o("  float v[32];");
+        if (dbuf) o("  float vn[32];");
         auto emit_loads = [&](const char* dst, int c0) {
             const int c1 = std::min(W, c0 + 32);
             o("  if (valid) {");
             for (int c = c0; c < c1; c++) o("    %s[%d] = (float)%s;", dst, c - c0, col[(size_t)c].c_str());
             o("  }");
         };
-        emit_loads("v", 0);
+        if (dbuf) emit_loads("v", 0);
         for (int c0 = 0; c0 < W; c0 += 32) {
             const int c1 = std::min(W, c0 + 32);
-            if (c0 + 32 < W) emit_loads("vn", c0 + 32);
+            if (!dbuf) emit_loads("v", c0);
+            if (dbuf && c0 + 32 < W) emit_loads("vn", c0 + 32);
             o("  _Pragma(\"unroll\") for (int c = 0; c < %d; c++) trow[c] = v[c];", c1 - c0);
             o("  __syncthreads();");
             o("  for (int i = tid; i < nvalid * 32; i += NTHR) { const int r = i >> 5, c = i & 31;");
             o("    if (%d + c < NOBS) __stcs(A.obs + (e0 + r) * NOBS + %d + c, tile[r * 33 + c]); }", c0, c0);
             o("  __syncthreads();");
-            if (c0 + 32 < W) o("  _Pragma(\"unroll\") for (int c = 0; c < 32; c++) v[c] = vn[c];");
+            if (dbuf && c0 + 32 < W) o("  _Pragma(\"unroll\") for (int c = 0; c < 32; c++) v[c] = vn[c];");
         }
     }
     o("}");
