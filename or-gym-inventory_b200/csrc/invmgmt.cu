@@ -172,21 +172,30 @@ __device__ __forceinline__ void inv_reset_env(const InvDev& P, const InvState<S>
 }
 
 template <typename S>
-__global__ void inv_reset_kernel(const __grid_constant__ InvDev P, int64_t N, int64_t npad, void* state, int reseed,
-                                 uint64_t seed, int64_t env_offset, const uint8_t* __restrict__ mask,
-                                 int64_t* __restrict__ obs) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= N) return;
-    if (mask && !mask[e]) return;
-    InvState<S> st(state, npad, P);
-    inv_reset_env(P, st, e);
-    if (reseed) {
-        st.key[e] = seed + (uint64_t)(env_offset + e);  // gymnasium vector convention: env i <- seed + i
-        st.episode[e] = 0;
-    } else
-        st.episode[e] += 1;
-    int64_t* o = obs + e * P.obs_dim;
-    for (int k = 0; k < P.obs_dim; k++) o[k] = k < P.n ? P.I0[k] : 0;
+__global__ void __launch_bounds__(256) inv_reset_kernel(const __grid_constant__ InvDev P, int64_t N, int64_t npad,
+                                                        void* state, int reseed, uint64_t seed, int64_t env_offset,
+                                                        const uint8_t* __restrict__ mask, int64_t* __restrict__ obs) {
+    const int64_t e0 = (int64_t)blockIdx.x * 256, e = e0 + threadIdx.x;
+    if (e < N && (!mask || mask[e])) {
+        InvState<S> st(state, npad, P);
+        inv_reset_env(P, st, e);
+        if (reseed) {
+            st.key[e] = seed + (uint64_t)(env_offset + e);  // gymnasium vector convention: env i <- seed + i
+            st.episode[e] = 0;
+        } else
+            st.episode[e] += 1;
+    }
+    // first observation [I0, 0, ...] (:354-391): the CTA fills its 256 rows of the row-major block cooperatively, so the
+    // stores are coalesced (a thread writing its own 264-byte row would touch 33 different cache lines per warp store)
+    const int W = P.obs_dim;
+    const int nrows = (int)((N - e0) < 256 ? (N - e0) : 256);
+    int r = 0, c = threadIdx.x;
+    while (c >= W) { c -= W; r++; }
+    for (int i = threadIdx.x; i < nrows * W; i += 256) {
+        if (!mask || mask[e0 + r]) obs[e0 * W + i] = c < P.n ? P.I0[c] : 0;
+        c += 256;
+        while (c >= W) { c -= W; r++; }
+    }
 }
 
 // ---- step ------------------------------------------------------------------------------------------------------

@@ -50,28 +50,33 @@ __device__ __forceinline__ void net_write_obs(const NetDev& P, const double* sU,
     }
 }
 
-__global__ void net_reset_kernel(const __grid_constant__ NetDev P, int64_t N, int64_t npad, void* state, int reseed,
-                                 uint64_t seed, int64_t env_offset, const uint8_t* __restrict__ mask,
-                                 float* __restrict__ obs) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= N) return;
-    if (mask && !mask[e]) return;
-    NetState st(state, npad, P);
-    for (int j = 0; j < P.J; j++) st.X[(size_t)j * npad + e] = P.I0[j];  // :326
-    for (int i = 0; i < P.E; i++) st.Y[(size_t)i * npad + e] = 0.0;
-    for (int r = 0; r < P.M; r++) st.U[(size_t)r * npad + e] = 0.0;
-    for (int k = 0; k < P.sumL; k++) st.ring[(size_t)k * npad + e] = 0.0;
-    st.period[e] = 0;
-    if (reseed) {
-        st.key[e] = seed + (uint64_t)(env_offset + e);
-        st.episode[e] = 0;
-    } else
-        st.episode[e] += 1;
-    float* o = obs + e * P.obs_dim;
-    int k = 0;
-    for (int r = 0; r < P.M; r++) o[k++] = 0.0f;
-    for (int j = 0; j < P.J; j++) o[k++] = (float)P.I0[j];
-    for (; k < P.obs_dim; k++) o[k] = 0.0f;
+__global__ void __launch_bounds__(128) net_reset_kernel(const __grid_constant__ NetDev P, int64_t N, int64_t npad,
+                                                        void* state, int reseed, uint64_t seed, int64_t env_offset,
+                                                        const uint8_t* __restrict__ mask, float* __restrict__ obs) {
+    const int64_t e0 = (int64_t)blockIdx.x * 128, e = e0 + threadIdx.x;
+    if (e < N && (!mask || mask[e])) {
+        NetState st(state, npad, P);
+        for (int j = 0; j < P.J; j++) st.X[(size_t)j * npad + e] = P.I0[j];  // :326
+        for (int i = 0; i < P.E; i++) st.Y[(size_t)i * npad + e] = 0.0;
+        for (int r = 0; r < P.M; r++) st.U[(size_t)r * npad + e] = 0.0;
+        for (int k = 0; k < P.sumL; k++) st.ring[(size_t)k * npad + e] = 0.0;
+        st.period[e] = 0;
+        if (reseed) {
+            st.key[e] = seed + (uint64_t)(env_offset + e);
+            st.episode[e] = 0;
+        } else
+            st.episode[e] += 1;
+    }
+    // first observation [0 (M), I0 (J), 0 ...] written cooperatively: coalesced stores over the CTA's 128 rows
+    const int W = P.obs_dim;
+    const int nrows = (int)((N - e0) < 128 ? (N - e0) : 128);
+    int r = 0, c = threadIdx.x;
+    while (c >= W) { c -= W; r++; }
+    for (int i = threadIdx.x; i < nrows * W; i += 128) {
+        if (!mask || mask[e0 + r]) obs[e0 * W + i] = (c >= P.M && c < P.M + P.J) ? (float)P.I0[c - P.M] : 0.0f;
+        c += 128;
+        while (c >= W) { c -= W; r++; }
+    }
 }
 
 #include "netinv_args.cuh"

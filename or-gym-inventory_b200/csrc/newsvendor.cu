@@ -153,40 +153,49 @@ __device__ __forceinline__ double nv_period(const NvDev& P, const NvParams& q, f
 }
 
 // ---- reset ------------------------------------------------------------------------------------------------------
-__global__ void nv_reset_kernel(const __grid_constant__ NvDev P, int64_t N, int64_t npad, void* state, int reseed,
-                                uint64_t seed, int64_t env_offset, const uint8_t* __restrict__ mask,
-                                const double* __restrict__ fixed, float* __restrict__ obs) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= N) return;
-    if (mask && !mask[e]) return;
-    NvState st(state, npad, P.L);
-    uint64_t key;
-    uint32_t ep;
-    if (reseed) {
-        key = seed + (uint64_t)(env_offset + e);
-        ep = 0;
-        st.key[e] = key;
-    } else {
-        key = st.key[e];
-        ep = st.episode[e] + 1;
+__global__ void __launch_bounds__(256) nv_reset_kernel(const __grid_constant__ NvDev P, int64_t N, int64_t npad,
+                                                       void* state, int reseed, uint64_t seed, int64_t env_offset,
+                                                       const uint8_t* __restrict__ mask, const double* __restrict__ fixed,
+                                                       float* __restrict__ obs) {
+    __shared__ float par32[256][5];
+    const int64_t e0 = (int64_t)blockIdx.x * 256, e = e0 + threadIdx.x;
+    if (e < N && (!mask || mask[e])) {
+        NvState st(state, npad, P.L);
+        uint64_t key;
+        uint32_t ep;
+        if (reseed) {
+            key = seed + (uint64_t)(env_offset + e);
+            ep = 0;
+            st.key[e] = key;
+        } else {
+            key = st.key[e];
+            ep = st.episode[e] + 1;
+        }
+        st.episode[e] = ep;
+        NvParams q;
+        if (fixed) {
+            q.price = fixed[e * 5 + 0]; q.cost = fixed[e * 5 + 1]; q.h = fixed[e * 5 + 2]; q.k = fixed[e * 5 + 3];
+            q.mu = fixed[e * 5 + 4];
+        } else
+            q = nv_draw_params(P, key, ep);
+        for (int z = 0; z < 5; z++) {
+            st.par[(size_t)z * npad + e] = (&q.price)[z];
+            par32[threadIdx.x][z] = (float)(&q.price)[z];  // :115
+        }
+        for (int j = 0; j < P.L; j++) st.pipe[(size_t)j * npad + e] = 0.0f;
+        st.step[e] = 0;
     }
-    st.episode[e] = ep;
-    NvParams q;
-    if (fixed) {
-        q.price = fixed[e * 5 + 0]; q.cost = fixed[e * 5 + 1]; q.h = fixed[e * 5 + 2]; q.k = fixed[e * 5 + 3];
-        q.mu = fixed[e * 5 + 4];
-    } else
-        q = nv_draw_params(P, key, ep);
-    st.par[0 * npad + e] = q.price;
-    st.par[1 * npad + e] = q.cost;
-    st.par[2 * npad + e] = q.h;
-    st.par[3 * npad + e] = q.k;
-    st.par[4 * npad + e] = q.mu;
-    for (int j = 0; j < P.L; j++) st.pipe[(size_t)j * npad + e] = 0.0f;
-    st.step[e] = 0;
-    float* o = obs + e * P.obs_dim;
-    o[0] = (float)q.price; o[1] = (float)q.cost; o[2] = (float)q.h; o[3] = (float)q.k; o[4] = (float)q.mu;  // :115
-    for (int j = 0; j < P.L; j++) o[5 + j] = 0.0f;
+    __syncthreads();
+    // first observation [price, cost, h, k, mu, 0 ...] written cooperatively (coalesced)
+    const int W = P.obs_dim;
+    const int nrows = (int)((N - e0) < 256 ? (N - e0) : 256);
+    int r = 0, c = threadIdx.x;
+    while (c >= W) { c -= W; r++; }
+    for (int i = threadIdx.x; i < nrows * W; i += 256) {
+        if (!mask || mask[e0 + r]) obs[e0 * W + i] = c < 5 ? par32[r][c] : 0.0f;
+        c += 256;
+        while (c >= W) { c -= W; r++; }
+    }
 }
 
 // ---- step ------------------------------------------------------------------------------------------------------
