@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liborgym_b200.so")
+# ORGYM_B200_LIB selects another build of the same library (kernel-tuning experiments: tools/build_variants.py)
+LIB_PATH = os.environ.get("ORGYM_B200_LIB") or os.path.join(_HERE, "csrc", "liborgym_b200.so")
 
 OK, E_INVALID, E_CUDA, E_UNSUPPORTED = 0, -1, -2, -3
 AUTORESET_DISABLED, AUTORESET_NEXT_STEP, AUTORESET_SAME_STEP = 0, 1, 2

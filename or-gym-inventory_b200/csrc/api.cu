@@ -1,6 +1,7 @@
 // api.cu -- family-independent part of the C ABI: error string, version, handle header, error bits,
 // alias-table construction for the fixed demand distributions, stand-alone samplers (K6).
 #include "common.cuh"
+#include <mutex>
 
 static thread_local std::string g_last_error;
 
@@ -157,7 +158,32 @@ int orgym_dist_pmf(const orgym_dist_t* d, std::vector<double>* pmf, int64_t* bas
     return ORGYM_OK;
 }
 
-// Walker/Vose alias table with 2^log2k buckets; thresholds are 32-bit fixed point
+// Walker/Vose alias construction over K >= pmf.size() buckets (the extra buckets have probability 0): bucket i gets
+// {threshold (32-bit fixed point, accept i if u < threshold), alias index}
+static void vose_alias(const std::vector<double>& pmf, size_t K, uint2* tab) {
+    std::vector<double> q(K, 0.0);
+    for (size_t i = 0; i < pmf.size(); i++) q[i] = pmf[i] * (double)K;
+    std::vector<uint32_t> small, large;
+    for (size_t i = 0; i < K; i++) (q[i] < 1.0 ? small : large).push_back((uint32_t)i);
+    auto thr = [](double x) {
+        double v = std::floor(x * 4294967296.0 + 0.5);
+        if (v < 0) v = 0;
+        if (v > 4294967295.0) v = 4294967295.0;
+        return (uint32_t)v;
+    };
+    for (size_t i = 0; i < K; i++) tab[i] = make_uint2(0xFFFFFFFFu, (uint32_t)i);
+    while (!small.empty() && !large.empty()) {
+        uint32_t s = small.back(), l = large.back();
+        small.pop_back();
+        large.pop_back();
+        tab[s] = make_uint2(thr(q[s]), l);
+        q[l] = (q[l] + q[s]) - 1.0;
+        (q[l] < 1.0 ? small : large).push_back(l);
+    }
+    // leftovers are 1.0 up to rounding: keep {0xFFFFFFFF, self}
+}
+
+// alias table with 2^log2k buckets for one of the fixed demand distributions
 int orgym_build_alias(const orgym_dist_t* d, int user_clamp, AliasDev* out, std::vector<void*>* allocs) {
     memset(out, 0, sizeof(*out));
     out->kind = d->kind;
@@ -179,27 +205,8 @@ int orgym_build_alias(const orgym_dist_t* d, int user_clamp, AliasDev* out, std:
     int log2k = 0;
     while ((size_t(1) << log2k) < pmf.size()) log2k++;
     size_t K = size_t(1) << log2k;
-    std::vector<double> q(K, 0.0);
-    for (size_t i = 0; i < pmf.size(); i++) q[i] = pmf[i] * (double)K;
     std::vector<uint2> tab(K);
-    std::vector<uint32_t> small, large;
-    for (size_t i = 0; i < K; i++) (q[i] < 1.0 ? small : large).push_back((uint32_t)i);
-    auto thr = [](double x) {
-        double v = std::floor(x * 4294967296.0 + 0.5);
-        if (v < 0) v = 0;
-        if (v > 4294967295.0) v = 4294967295.0;
-        return (uint32_t)v;
-    };
-    for (size_t i = 0; i < K; i++) tab[i] = make_uint2(0xFFFFFFFFu, (uint32_t)i);
-    while (!small.empty() && !large.empty()) {
-        uint32_t s = small.back(), l = large.back();
-        small.pop_back();
-        large.pop_back();
-        tab[s] = make_uint2(thr(q[s]), l);
-        q[l] = (q[l] + q[s]) - 1.0;
-        (q[l] < 1.0 ? small : large).push_back(l);
-    }
-    // leftovers are 1.0 up to rounding: keep {0xFFFFFFFF, self}
+    vose_alias(pmf, K, tab.data());
     uint2* dev = nullptr;
     ORGYM_CUDA(cudaMalloc(&dev, sizeof(uint2) * K));
     allocs->push_back(dev);
@@ -226,6 +233,62 @@ int orgym_rcp_table(int device, const double** out) {
         tabs[device] = d;
     }
     *out = tabs[device];
+    return ORGYM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// alias tables of Poisson(4 i), i = 0 .. ntab-1, for the per-env-mean sampler (common.cuh: poisson_tab_draw)
+// ------------------------------------------------------------------------------------------------
+int orgym_poisson_tables(int device, double mu_hi, PoisTabDev* out) {
+    struct Built {
+        int device;
+        PoisTabDev t;
+    };
+    static std::mutex mtx;
+    static std::vector<Built> cache;
+    ORGYM_REQUIRE(device >= 0, "device index out of range");
+    if (!(mu_hi > 256.0)) mu_hi = 256.0;  // default coverage: the reference's mu_max = 200 with margin
+    if (mu_hi > ORGYM_PT_MAX_MEAN) mu_hi = ORGYM_PT_MAX_MEAN;
+    const int ntab = (int)std::floor(mu_hi / ORGYM_PT_G) + 1;
+    std::lock_guard<std::mutex> lock(mtx);
+    for (const Built& b : cache)
+        if (b.device == device && b.t.ntab >= ntab) {
+            *out = b.t;
+            return ORGYM_OK;
+        }
+    std::vector<std::vector<double>> pmfs((size_t)ntab);
+    std::vector<int64_t> bases((size_t)ntab, 0);
+    size_t widest = 1;
+    for (int i = 0; i < ntab; i++) {
+        orgym_dist_t d;
+        memset(&d, 0, sizeof(d));
+        d.kind = ORGYM_DIST_POISSON;
+        d.p0 = (double)(ORGYM_PT_G * i);
+        if (int rc = orgym_dist_pmf(&d, &pmfs[(size_t)i], &bases[(size_t)i])) return rc;
+        widest = std::max(widest, pmfs[(size_t)i].size());
+    }
+    int log2k = 0;
+    while ((size_t(1) << log2k) < widest) log2k++;
+    const size_t K = size_t(1) << log2k;
+    std::vector<uint2> all((size_t)ntab * K), one(K);
+    for (int i = 0; i < ntab; i++) {
+        vose_alias(pmfs[(size_t)i], K, one.data());
+        const uint32_t base = (uint32_t)bases[(size_t)i];
+        ORGYM_REQUIRE(base + K <= 65536, "Poisson table values exceed 16 bits");
+        for (size_t j = 0; j < K; j++)
+            all[(size_t)i * K + j] = make_uint2(one[j].x, (base + (uint32_t)j) | ((base + one[j].y) << 16));
+    }
+    DeviceGuard g(device);
+    uint2* dev = nullptr;
+    ORGYM_CUDA(cudaMalloc(&dev, sizeof(uint2) * all.size()));
+    ORGYM_CUDA(cudaMemcpy(dev, all.data(), sizeof(uint2) * all.size(), cudaMemcpyHostToDevice));
+    Built b;
+    b.device = device;
+    b.t.tab = dev;
+    b.t.log2k = log2k;
+    b.t.ntab = ntab;
+    cache.push_back(b);
+    *out = b.t;
     return ORGYM_OK;
 }
 
@@ -264,11 +327,12 @@ extern "C" int orgym_sample_demand(const orgym_dist_t* dist, uint64_t seed, int6
     return rc;
 }
 
-__global__ void sample_poisson_mu_kernel(const double* __restrict__ mu, const double* __restrict__ rcp, uint64_t seed,
-                                         int64_t env_offset, int64_t count, int period, int64_t* __restrict__ out) {
+__global__ void sample_poisson_mu_kernel(const double* __restrict__ mu, PoisTabDev T, const double* __restrict__ rcp,
+                                         uint64_t seed, int64_t env_offset, int64_t count, int period,
+                                         int64_t* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    out[i] = poisson_mu(mu[i], rcp, seed + (uint64_t)(env_offset + i), 0u, period);
+    out[i] = poisson_mu(T, rcp, mu[i], seed + (uint64_t)(env_offset + i), 0u, period);
 }
 
 extern "C" int orgym_sample_poisson_mu(const double* mu_dev, uint64_t seed, int64_t env_offset, int64_t count,
@@ -277,9 +341,12 @@ extern "C" int orgym_sample_poisson_mu(const double* mu_dev, uint64_t seed, int6
     ORGYM_REQUIRE(orgym_device_count() > 0, "no CUDA device");
     const double* rcp = nullptr;
     if (int rc = orgym_rcp_table(device, &rcp)) return rc;
+    PoisTabDev T;  // default coverage (means below 260); larger means take the PTRS path
+    if (int rc = orgym_poisson_tables(device, 0.0, &T)) return rc;
     DeviceGuard g(device);
-    sample_poisson_mu_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mu_dev, rcp, seed, env_offset,
-                                                                                              count, period, out_dev);
+    sample_poisson_mu_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mu_dev, T, rcp, seed,
+                                                                                              env_offset, count, period,
+                                                                                              out_dev);
     ORGYM_CUDA(cudaGetLastError());
     return ORGYM_OK;
 }

@@ -105,50 +105,81 @@ __device__ __forceinline__ double log_factorial(double k) {
     return (x - 0.5) * log(x) - x + 0.91893853320467274178 + r * (1.0 / 12.0 - r2 * (1.0 / 360.0 - r2 * (1.0 / 1260.0)));
 }
 
-// Poisson with a per-call mean (Newsvendor: mu differs per env).  mu >= 10: Hoermann's PTRS transformed
-// rejection in float64 (the algorithm numpy uses, with the acceptance test folded into a single logarithm and a
-// Stirling log-factorial); mu < 10: CDF inversion by sequential search from one 53-bit uniform.
-// Keyed by (key, episode, t); rejection attempts advance counter word 3.
+// Poisson with a per-call mean (Newsvendor: mu differs per env).
+//
+// Main path, mu < 4 * ntab: Poisson(mu) = Poisson(mu0) + Poisson(r) with mu0 = 4*floor(mu/4) and r = mu - mu0 in [0, 4)
+// (a sum of independent Poisson variables is Poisson).  The first term is ONE draw from the Walker alias table of the
+// tabulated mean mu0 (tables built in float64 on the host for every multiple of 4, L2-resident: one 8-byte gather per
+// draw); the second is CDF inversion by chop-down search from one 32-bit uniform (p_k = p_{k-1} * r / k with a
+// reciprocal table; r < 4 keeps the search at ~2 iterations on average, <= ~10 for the slowest lane of a warp).  One
+// Philox block serves two periods.  Compared with a rejection sampler there is no float64 logarithm, no division and
+// no retry loop -- a warp no longer runs the slow path of its unluckiest lane.
+// Fallback, mu >= 4 * ntab (only reachable with fixed parameters beyond mu_max, or mu_max > 4096): Hoermann's PTRS
+// transformed rejection in float64 (the algorithm numpy uses), kept out of line.
+struct PoisTabDev {
+    const uint2* tab;  // [ntab][1 << log2k] {threshold (u32), value if accepted | alias value << 16}
+    int log2k, ntab;
+};
+#define ORGYM_PT_G 4
+#define ORGYM_PT_MAX_MEAN 4096.0
+// tables of `device` covering means up to at least mu_hi (built on first use, cached for the life of the process)
+int orgym_poisson_tables(int device, double mu_hi, PoisTabDev* out);
+
+struct PoisSplit {
+    int i0;     // table index: mu0 = 4 * i0 (-1: mean beyond the tables -> PTRS)
+    double r;   // mu - mu0
+    double p0;  // exp(-r)
+};
+__device__ __forceinline__ PoisSplit poisson_split(const PoisTabDev& T, double mu) {
+    PoisSplit s;
+    s.i0 = 0; s.r = 0.0; s.p0 = 1.0;
+    if (!(mu > 0.0)) return s;
+    if (!(mu < (double)(ORGYM_PT_G * T.ntab))) { s.i0 = -1; return s; }
+    s.i0 = (int)(mu * (1.0 / ORGYM_PT_G));
+    s.r = mu - (double)(ORGYM_PT_G * s.i0);  // exact: both operands are within a factor 2 or r == mu
+    s.p0 = exp(-s.r);
+    return s;
+}
+// wa: word for the alias draw, wi: word for the inversion
+__device__ __forceinline__ int poisson_tab_draw(const PoisTabDev& T, const double* __restrict__ rcp, const PoisSplit& s,
+                                                uint32_t wa, uint32_t wi) {
+    int x = 0;
+    if (s.i0 > 0) {
+        const uint2 e = T.tab[((size_t)s.i0 << T.log2k) + (wa >> (32 - T.log2k))];
+        x = (wa << T.log2k) < e.x ? (int)(e.y & 0xFFFFu) : (int)(e.y >> 16);
+    }
+    double u = ((double)wi + 0.5) * (1.0 / 4294967296.0), p = s.p0;
+    int k = 0;
+    while (u > p && k < 64) {  // P(k > 64 | r < 4) < 1e-50
+        u -= p;
+        k += 1;
+        p *= s.r * rcp[k];
+    }
+    return x + k;
+}
+
 struct PoissonMu {
-    double mu, b, a, vr, e_or_loglam, inv_alpha;  // e_or_loglam: exp(-mu) for mu < 10, log(mu) otherwise
-    const double* rcp;                            // reciprocal table (orgym_rcp_table)
+    double mu, b, a, vr, loglam, inv_alpha;
 };
 // full = false: only what the squeeze (fast acceptance) needs; the rest is computed on demand in the slow path
 template <bool FULL>
-__device__ __forceinline__ PoissonMu poisson_setup(double mu, const double* rcp) {
+__device__ __forceinline__ PoissonMu ptrs_setup(double mu) {
     PoissonMu c;
     c.mu = mu;
-    c.rcp = rcp;
-    c.b = c.a = c.vr = c.e_or_loglam = c.inv_alpha = 0.0;
-    if (!(mu > 0.0)) return c;
-    if (mu < 10.0) {
-        c.e_or_loglam = exp(-mu);
-        return c;
-    }
     c.b = 0.931 + 2.53 * sqrt(mu);
     c.a = -0.059 + 0.02483 * c.b;
     c.vr = 0.9277 - 3.6224 / (c.b - 2.0);
+    c.loglam = c.inv_alpha = 0.0;
     if (FULL) {
-        c.e_or_loglam = log(mu);
+        c.loglam = log(mu);
         c.inv_alpha = 1.1239 + 1.1328 / (c.b - 3.4);
     }
     return c;
 }
+// mu >= 10.  Keyed by (key, episode, t); rejection attempts advance counter word 3.
 template <bool FULL>
-__device__ __forceinline__ int64_t poisson_draw(const PoissonMu& c, uint64_t key, uint32_t episode, int t) {
+__device__ __forceinline__ int64_t ptrs_draw(const PoissonMu& c, uint64_t key, uint32_t episode, int t) {
     const double mu = c.mu;
-    if (!(mu > 0.0)) return 0;
-    if (mu < 10.0) {
-        uint4 w = philox_block(key, (uint32_t)t, episode, STREAM_POISSON_MU, 0);
-        double u = u53(w.x, w.y), p = c.e_or_loglam, s = p;
-        int x = 0;
-        while (u > s && x < 200) {
-            x += 1;
-            p *= mu * c.rcp[x];
-            s += p;
-        }
-        return x;
-    }
     // Each rejection attempt consumes two 32-bit uniforms (U and V are only compared / passed through smooth
     // functions, so 2^-32 resolution is far below any statistical visibility); one Philox block feeds two attempts.
     uint4 w = make_uint4(0, 0, 0, 0);
@@ -176,14 +207,26 @@ __device__ __forceinline__ int64_t poisson_draw(const PoissonMu& c, uint64_t key
             if (lhs < rhs - tol) return (int64_t)kf;
             if (lhs > rhs + tol) continue;
         }
-        const double loglam = FULL ? c.e_or_loglam : log(mu);
+        const double loglam = FULL ? c.loglam : log(mu);
         if (log(arg) <= (-mu + kf * loglam - log_factorial(kf))) return (int64_t)kf;
         if (attempt > 1000u) return (int64_t)kf;  // unreachable in practice; bounds the loop
     }
 }
-__device__ __forceinline__ int64_t poisson_mu(double mu, const double* rcp, uint64_t key, uint32_t episode, int t) {
-    PoissonMu c = poisson_setup<false>(mu, rcp);
-    return poisson_draw<false>(c, key, episode, t);
+static __device__ __noinline__ int64_t poisson_ptrs(double mu, uint64_t key, uint32_t episode, int t) {
+    PoissonMu c = ptrs_setup<false>(mu);
+    return ptrs_draw<false>(c, key, episode, t);
+}
+// demand of (key, episode, period t) for mean mu -- the same value through every API (step, rollout, sampler)
+__device__ __forceinline__ uint2 poisson_words(uint64_t key, uint32_t episode, int t) {
+    const uint4 w = philox_block(key, (uint32_t)t >> 1, episode, STREAM_POISSON_TAB, 0);
+    return (t & 1) ? make_uint2(w.z, w.w) : make_uint2(w.x, w.y);
+}
+__device__ __forceinline__ int64_t poisson_mu(const PoisTabDev& T, const double* __restrict__ rcp, double mu, uint64_t key,
+                                              uint32_t episode, int t) {
+    const PoisSplit s = poisson_split(T, mu);
+    if (s.i0 < 0) return poisson_ptrs(mu, key, episode, t);
+    const uint2 w = poisson_words(key, episode, t);
+    return poisson_tab_draw(T, rcp, s, w.x, w.y);
 }
 
 // ------------------------------------------------------------------------------------------------

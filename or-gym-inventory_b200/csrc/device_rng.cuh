@@ -41,7 +41,8 @@ enum {
     STREAM_DEMAND = 0,    // c0 = period >> 2 (four alias samples per block), c3 = demand source (retail link) index
     STREAM_ACTION = 1,    // random-action policy: c0 = period, c3 = stage group (4 stages per block)
     STREAM_PARAMS = 2,    // newsvendor reset uniforms: c0 = 0..2
-    STREAM_POISSON_MU = 3 // per-env-mean Poisson: c0 = period, c3 = attempt
+    STREAM_POISSON_MU = 3,  // per-env-mean Poisson, PTRS fallback: c0 = period, c3 = attempt pair
+    STREAM_POISSON_TAB = 4  // per-env-mean Poisson, table + inversion: c0 = period >> 1 (two words per period)
 };
 
 __host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {

@@ -571,6 +571,10 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
 int net_jit_build(NetHandle* H, std::string* err) {
     const NetDev& P = H->dev;
     H->jit_threads = 128;
+    if (const char* tv = getenv("ORGYM_NET_JIT_THREADS")) {  // tuning knob: 64 / 128 / 256 threads per CTA
+        const int t = atoi(tv);
+        if (t == 64 || t == 128 || t == 256) H->jit_threads = t;
+    }
     std::string src = net_jit_source(P, H->jit_threads);
     H->jit_stream = net_jit_uses_stream(P);
     int rc = orgym_jit_compile(src, "net_jit_step", &H->jit, err);

@@ -11,9 +11,16 @@
 #include "common.cuh"
 
 #define NV_MAXL ORGYM_NV_MAX_LEAD
+#ifndef NV_STEP_MINB
+#define NV_STEP_MINB 8
+#endif
+#ifndef NV_ROLL_MINB
+#define NV_ROLL_MINB 6
+#endif
 
 struct NvDev {
     const double* rcp;  // reciprocal table (orgym_rcp_table)
+    PoisTabDev pt;      // alias tables of the demand sampler (orgym_poisson_tables)
     int L, T, obs_dim;
     double max_inv, max_q, p_max, h_max, k_max, mu_max;
 };
@@ -216,7 +223,7 @@ struct NvStepArgs {
     int use_bulk;
 };
 
-__global__ void __launch_bounds__(ORGYM_TILE) nv_step_kernel(const __grid_constant__ NvDev P, const NvStepArgs A) {
+__global__ void __launch_bounds__(ORGYM_TILE, NV_STEP_MINB) nv_step_kernel(const __grid_constant__ NvDev P, const NvStepArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* tile = (float*)smem;
     const int tid = threadIdx.x, W = P.obs_dim;
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(ORGYM_TILE) nv_step_kernel(const __grid_consta
             }
             float psum = nv_pipe_sum(P.L, [&](int j) { return row[5 + j]; });
             float pipe0 = P.L > 0 ? row[5] : 0.0f;
-            long long d = A.demand ? A.demand[e] : poisson_mu(q.mu, P.rcp, key, ep, sc);
+            long long d = A.demand ? A.demand[e] : poisson_mu(P.pt, P.rcp, q.mu, key, ep, sc);
             float oq;
             double parts[4];
             double r = nv_period(P, q, A.actions[e], d, pipe0, psum, &oq, parts, nullptr, nullptr, nullptr);
@@ -376,7 +383,7 @@ struct NvRolloutArgs {
 
 __device__ __forceinline__ float clipf(float q, float hi) { return q < 0.0f ? 0.0f : (q > hi ? hi : q); }
 
-__global__ void __launch_bounds__(NV_ROLL_THREADS) nv_rollout_kernel(const __grid_constant__ NvDev P,
+__global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kernel(const __grid_constant__ NvDev P,
                                                                      const __grid_constant__ NvRolloutArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* ring = (float*)smem;  // [L][threads], logical index j lives at slot (head + j) % L
@@ -412,7 +419,8 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS) nv_rollout_kernel(const __gri
         }
         level = level > 0.0 ? level : 0.0;
     }
-    const PoissonMu pm = poisson_setup<true>(q.mu, P.rcp);  // per-episode constants of the demand sampler
+    const PoisSplit ps = poisson_split(P.pt, q.mu);  // per-episode constants of the demand sampler
+    uint4 dw = make_uint4(0, 0, 0, 0);
     int head = 0;
     double ret = 0.0, s_sales = 0.0, s_dem = 0.0, s_lost = 0.0, s_ex = 0.0;
     for (int t = 0; t < P.T; t++) {
@@ -449,8 +457,12 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS) nv_rollout_kernel(const __gri
         long long d;
         if (A.demand)
             d = valid ? A.demand[e * A.d_se + (int64_t)t * A.d_st] : 0;
-        else
-            d = poisson_draw<true>(pm, key, A.episode, t);
+        else if (ps.i0 < 0)
+            d = poisson_ptrs(q.mu, key, A.episode, t);
+        else {  // one Philox block per two periods (same words as poisson_mu)
+            if ((t & 1) == 0) dw = philox_block(key, (uint32_t)t >> 1, A.episode, STREAM_POISSON_TAB, 0);
+            d = poisson_tab_draw(P.pt, P.rcp, ps, (t & 1) ? dw.z : dw.x, (t & 1) ? dw.w : dw.y);
+        }
         float oq;
         double su, ex, sh;
         double r = nv_period(P, q, act, d, pipe0, psum, &oq, nullptr, &su, &ex, &sh);
@@ -521,6 +533,7 @@ extern "C" int orgym_newsvendor_create(const orgym_newsvendor_config_t* cfg, int
     P.p_max = cfg->p_max; P.h_max = cfg->h_max; P.k_max = cfg->k_max; P.mu_max = cfg->mu_max;
     int rc = orgym_handle_base_init(&H->base, FAM_NEWSVENDOR, device, num_envs);
     if (rc == ORGYM_OK) rc = orgym_rcp_table(device, &P.rcp);
+    if (rc == ORGYM_OK) rc = orgym_poisson_tables(device, cfg->mu_max, &P.pt);
     if (rc != ORGYM_OK) {
         delete H;
         return rc;

@@ -71,11 +71,15 @@ def test_alias_other_distributions(kind, p0, p1, dist):
     assert ks_randomised(x, dist) > P_MIN
 
 
-@pytest.mark.parametrize("mu", [0.5, 5.0, 9.99, 10.0, 20.0, 37.3, 199.9])
-def test_per_env_mean_poisson_matches_scipy(mu):
+# table + inversion path: means below 260 (3.999 / 4.0 / 255.5 / 259.99 sit on table-grid edges);
+# PTRS fallback: 260 and above
+@pytest.mark.parametrize("mu,period", [(0.5, 3), (3.999, 2), (4.0, 3), (5.0, 3), (9.99, 2), (10.0, 3), (20.0, 3),
+                                       (37.3, 4), (199.9, 3), (255.5, 6), (259.99, 3), (260.0, 3), (300.0, 2),
+                                       (1000.5, 3)])
+def test_per_env_mean_poisson_matches_scipy(mu, period):
     import torch
     m = torch.full((2_000_000,), mu, dtype=torch.float64, device="cuda")
-    x = pkg.sample_poisson_mu(m, seed=2000, period=3).cpu().numpy()
+    x = pkg.sample_poisson_mu(m, seed=2000, period=period).cpu().numpy()
     d = stats.poisson(mu)
     assert chi_square(x, d) > P_MIN
     assert ks_randomised(x, d) > P_MIN
@@ -92,6 +96,55 @@ def test_per_env_mean_poisson_mixture():
     assert stats.kstest(u, "uniform").pvalue > P_MIN
     z = (x - mu)[mu > 1] / np.sqrt(mu[mu > 1])
     assert abs(z.mean()) < 5 / np.sqrt(z.size) and abs(z.var() - 1) < 0.01
+
+
+def test_per_env_mean_poisson_degenerate_means():
+    import torch
+    m = torch.tensor([0.0, -1.0, float("nan"), 1e-300], dtype=torch.float64, device="cuda")
+    assert (pkg.sample_poisson_mu(m, seed=1, period=0).cpu().numpy() == 0).all()
+
+
+def test_per_env_mean_poisson_periods_are_independent():
+    """Two consecutive periods share one Philox block (words x,y / z,w): their draws must be uncorrelated, and so
+    must the two terms of the decomposition (alias word vs inversion word)."""
+    import torch
+    rng = np.random.default_rng(1)
+    mu = rng.random(1_000_000) * 200.0
+    m = torch.from_numpy(mu).cuda()
+    a = pkg.sample_poisson_mu(m, seed=9, period=2).cpu().numpy()
+    b = pkg.sample_poisson_mu(m, seed=9, period=3).cpu().numpy()
+    c = pkg.sample_poisson_mu(m, seed=9, period=4).cpu().numpy()
+    keep = mu > 1
+    za, zb, zc = ((x - mu)[keep] / np.sqrt(mu[keep]) for x in (a, b, c))
+    assert abs(np.corrcoef(za, zb)[0, 1]) < 5e-3 and abs(np.corrcoef(zb, zc)[0, 1]) < 5e-3
+    # neighbouring envs (key = seed + id)
+    assert abs(np.corrcoef(za[:-1], za[1:])[0, 1]) < 5e-3
+
+
+def test_newsvendor_env_demand_large_mu_max():
+    """mu_max = 1500 makes the env build its own (larger) table set; demand reported by step() must follow
+    Poisson(mu_i) for every instance, and fixed means beyond the tables take the rejection path."""
+    import torch
+    N = 400_000
+    env = pkg.NewsvendorEnv(num_envs=N, device="cuda:0", mu_max=1500, step_limit=4)
+    env.reset(seed=11)
+    mu = env.export_params().cpu().numpy()[:, 4]
+    assert mu.max() > 1400
+    z = torch.zeros(N, dtype=torch.float32, device="cuda")
+    rng = np.random.default_rng(2)
+    for t in range(3):
+        x = env.step(z)[4]["demand"].cpu().numpy()
+        u = stats.poisson.cdf(x - 1, mu) + rng.random(N) * stats.poisson.pmf(x, mu)
+        assert stats.kstest(u, "uniform").pvalue > P_MIN
+    env.close()
+    env = pkg.NewsvendorEnv(num_envs=N, device="cuda:0", step_limit=4)
+    fixed = np.tile(np.array([10.0, 5.0, 1.0, 2.0, 0.0]), (N, 1))
+    fixed[:, 4] = rng.random(N) * 5000.0            # default tables end at 260
+    env.reset(seed=12, options={"fixed_params": fixed})
+    x = env.step(z)[4]["demand"].cpu().numpy()
+    u = stats.poisson.cdf(x - 1, fixed[:, 4]) + rng.random(N) * stats.poisson.pmf(x, fixed[:, 4])
+    assert stats.kstest(u, "uniform").pvalue > P_MIN
+    env.close()
 
 
 def test_stream_independence_and_keying():
