@@ -236,6 +236,12 @@ __global__ void __launch_bounds__(ORGYM_TILE, NV_STEP_MINB) nv_step_kernel(const
     NvState st(A.state, A.npad, P.L);
     if (valid) {
         float* row = tile + tid * stride;
+        // the pipeline goes straight into this env's row of the observation tile with asynchronous copies issued
+        // before anything else: they overlap the scalar loads, the demand draw and its table gather
+        {
+            const float* pp = st.pipe + e;
+            for (int j = 0; j < P.L; j++) cp_async4(row + 5 + j, pp + (size_t)j * A.npad);
+        }
         int sc = st.step[e];
         uint32_t ep = st.episode[e];
         uint64_t key = st.key[e];
@@ -245,6 +251,7 @@ __global__ void __launch_bounds__(ORGYM_TILE, NV_STEP_MINB) nv_step_kernel(const
         bool do_step = true;
         if (sc >= P.T) {
             do_step = false;
+            cp_async_wait_all();
             if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {
                 ep += 1;
                 q = nv_draw_params(P, key, ep);
@@ -263,21 +270,11 @@ __global__ void __launch_bounds__(ORGYM_TILE, NV_STEP_MINB) nv_step_kernel(const
             }
         }
         if (do_step) {
-            const float* pp = st.pipe + e;
             const int64_t np_ = A.npad;
-            // stage the pipeline in this env's row of the observation tile: loads are issued in batches of 8 so that
-            // their latencies overlap (a load-add chain would serialise them); the sum then runs out of shared memory
-            for (int j0 = 0; j0 < P.L; j0 += 8) {
-                float v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) v[u] = (j0 + u < P.L) ? pp[(size_t)(j0 + u) * np_] : 0.0f;
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (j0 + u < P.L) row[5 + j0 + u] = v[u];
-            }
+            long long d = A.demand ? A.demand[e] : poisson_mu(P.pt, P.rcp, q.mu, key, ep, sc);
+            cp_async_wait_all();
             float psum = nv_pipe_sum(P.L, [&](int j) { return row[5 + j]; });
             float pipe0 = P.L > 0 ? row[5] : 0.0f;
-            long long d = A.demand ? A.demand[e] : poisson_mu(P.pt, P.rcp, q.mu, key, ep, sc);
             float oq;
             double parts[4];
             double r = nv_period(P, q, A.actions[e], d, pipe0, psum, &oq, parts, nullptr, nullptr, nullptr);
@@ -285,11 +282,15 @@ __global__ void __launch_bounds__(ORGYM_TILE, NV_STEP_MINB) nv_step_kernel(const
             bool trunc = sc1 >= P.T;  // :190
             bool reset_now = trunc && A.autoreset == ORGYM_AUTORESET_SAME_STEP;
             for (int z = 0; z < 5; z++) row[z] = (float)(&q.price)[z];
-            for (int j = 0; j + 1 < P.L; j++) row[5 + j] = row[5 + j + 1];  // shift left (:177)
-            if (P.L > 0) row[5 + P.L - 1] = oq;
-            if (!reset_now) {
+            {
                 float* pw = st.pipe + e;
-                for (int j = 0; j < P.L; j++) pw[(size_t)j * np_] = row[5 + j];
+                for (int j = 0; j < P.L; j++) {  // shift left, append the new order (:177); one pass for tile and state
+                    const float x = j + 1 < P.L ? row[5 + j + 1] : oq;
+                    row[5 + j] = x;
+                    if (!reset_now) pw[(size_t)j * np_] = x;
+                }
+            }
+            if (!reset_now) {
                 st.step[e] = sc1;
             } else {
                 if (A.final_obs)
@@ -340,20 +341,38 @@ __global__ void nv_export_params_kernel(int64_t N, int64_t npad, int L, const vo
 // ---- Poisson quantile: smallest k with cdf(k) >= q (scipy.stats.poisson.ppf) ---------------------------------------
 // pmf recurrence summed in ascending order from 9 sigma below the mean (the mass below is < 3e-18); the per-term
 // division is a reciprocal-multiply (1 ulp), which can only matter when q sits within ~1e-13 of a CDF step.
+// The search advances four terms per trip: the partial sums are formed in the same order as a term-by-term loop
+// (identical floating-point values), but only the last one is compared with q -- the CDF is non-decreasing, so the
+// quantile lies in the block iff its last partial sum reaches q.
 __device__ __forceinline__ double poisson_ppf_dev(double q, double mu, const double* __restrict__ rcp) {
     if (!(q > 0.0)) return -1.0;
     if (q >= 1.0) return INFINITY;
     double lo = floor(mu - 9.0 * sqrt(mu) - 9.0);
     if (lo < 0.0) lo = 0.0;
-    double term = exp(-mu + lo * log(mu) - lgamma(lo + 1.0)), cdf = 0.0;
+    double term = exp(-mu + lo * log(mu) - lgamma(lo + 1.0)), cdf = 0.0;  // term = pmf(k), cdf = P(X < k)
     int k = (int)lo;
-    const double* pr = rcp + k;  // pr[1] = 1/(k+1)
-    for (;;) {
+    const int kmu = mu < 1e9 ? (int)mu : 1000000000;  // for integer k: k > mu <=> k > floor(mu)
+    while (k + 4 <= ORGYM_RCP_N) {
+        const double* pr = rcp + k;
+        const double t0 = term, t1 = t0 * (mu * pr[1]), t2 = t1 * (mu * pr[2]), t3 = t2 * (mu * pr[3]),
+                     t4 = t3 * (mu * pr[4]);
+        const double c0 = cdf + t0, c1 = c0 + t1, c2 = c1 + t2, c3 = c2 + t3;
+        if (c3 >= q) return (double)(k + (c0 >= q ? 0 : (c1 >= q ? 1 : (c2 >= q ? 2 : 3))));
+        if (t4 == 0.0) {  // underflow beyond the mean: q is within rounding of 1
+            if (t1 == 0.0 && k + 1 > kmu) return (double)(k + 1);
+            if (t2 == 0.0 && k + 2 > kmu) return (double)(k + 2);
+            if (t3 == 0.0 && k + 3 > kmu) return (double)(k + 3);
+            if (k + 4 > kmu) return (double)(k + 4);
+        }
+        cdf = c3;
+        term = t4;
+        k += 4;
+    }
+    for (;;) {  // beyond the reciprocal table (means in the thousands)
         cdf += term;
         if (cdf >= q) break;
         ++k;
-        ++pr;
-        term *= mu * (k <= ORGYM_RCP_N ? *pr : __drcp_rn((double)k));
+        term *= mu * (k <= ORGYM_RCP_N ? rcp[k] : __drcp_rn((double)k));
         if (term == 0.0 && (double)k > mu) break;
     }
     return (double)k;
