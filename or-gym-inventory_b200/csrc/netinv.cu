@@ -25,7 +25,7 @@ __device__ __forceinline__ int net_mod(int t, int d, uint32_t magic) {
 // of 8 before they are converted and stored, so that their latencies overlap.
 template <int NTHR>
 __device__ __forceinline__ void net_write_obs(const NetDev& P, const double* sU, const double* sX, int tid,
-                                              const double* ring, int64_t npad, int64_t e, int t, float* o) {
+                                              const double* ring, int el, int t, float* o) {
     int k = 0;
     for (int r = 0; r < P.M; r++) o[k++] = (float)sU[r * NTHR + tid];
     for (int j = 0; j < P.J; j++) o[k++] = (float)sX[j * NTHR + tid];
@@ -33,14 +33,14 @@ __device__ __forceinline__ void net_write_obs(const NetDev& P, const double* sU,
         const int L = P.L[i];
         if (L == 0) continue;  // :353
         int s = net_mod(t, L, P.Lmagic[i]);
-        const double* base = ring + (size_t)P.roff[i] * npad + e;
+        const double* base = ring + (size_t)P.roff[i] * NET_TILE + el;
         for (int q0 = 0; q0 < L; q0 += 8) {
             double v[8];
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 int sl = s + q0 + u;
                 sl = sl >= L ? sl - L : sl;
-                v[u] = (q0 + u < L) ? base[(size_t)sl * npad] : 0.0;
+                v[u] = (q0 + u < L) ? base[(size_t)sl * NET_TILE] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 8; u++)
@@ -50,22 +50,23 @@ __device__ __forceinline__ void net_write_obs(const NetDev& P, const double* sU,
     }
 }
 
-__global__ void __launch_bounds__(128) net_reset_kernel(const __grid_constant__ NetDev P, int64_t N, int64_t npad,
-                                                        void* state, int reseed, uint64_t seed, int64_t env_offset,
+__global__ void __launch_bounds__(NET_TILE) net_reset_kernel(const __grid_constant__ NetDev P, int64_t N, void* state,
+                                                             int reseed, uint64_t seed, int64_t env_offset,
                                                         const uint8_t* __restrict__ mask, float* __restrict__ obs) {
     const int64_t e0 = (int64_t)blockIdx.x * 128, e = e0 + threadIdx.x;
     if (e < N && (!mask || mask[e])) {
-        NetState st(state, npad, P);
-        for (int j = 0; j < P.J; j++) st.X[(size_t)j * npad + e] = P.I0[j];  // :326
-        for (int i = 0; i < P.E; i++) st.Y[(size_t)i * npad + e] = 0.0;
-        for (int r = 0; r < P.M; r++) st.U[(size_t)r * npad + e] = 0.0;
-        for (int k = 0; k < P.sumL; k++) st.ring[(size_t)k * npad + e] = 0.0;
-        st.period[e] = 0;
+        NetState st((char*)state + (int64_t)blockIdx.x * net_tile_bytes(P), P);  // one CTA per state tile
+        const int el = threadIdx.x;
+        for (int j = 0; j < P.J; j++) st.X[j * NET_TILE + el] = P.I0[j];  // :326
+        for (int i = 0; i < P.E; i++) st.Y[i * NET_TILE + el] = 0.0;
+        for (int r = 0; r < P.M; r++) st.U[r * NET_TILE + el] = 0.0;
+        for (int k = 0; k < P.sumL; k++) st.ring[k * NET_TILE + el] = 0.0;
+        st.period[el] = 0;
         if (reseed) {
-            st.key[e] = seed + (uint64_t)(env_offset + e);
-            st.episode[e] = 0;
+            st.key[el] = seed + (uint64_t)(env_offset + e);
+            st.episode[el] = 0;
         } else
-            st.episode[e] += 1;
+            st.episode[el] += 1;
     }
     // first observation [0 (M), I0 (J), 0 ...] written cooperatively: coalesced stores over the CTA's 128 rows
     const int W = P.obs_dim;
@@ -98,9 +99,10 @@ __global__ void __launch_bounds__(NTHR) net_sim_kernel(const __grid_constant__ N
     double* sS = sU + M * NTHR;      // [M] retail sales this period
     float* otile = (float*)(sS + M * NTHR);  // STEP mode, when it fits: [NTHR][obs_stride] staging tile
     const int ostride = P.obs_dim | 1;       // odd row stride: conflict-free row writes
-    NetState st(A.state, A.npad, P);
+    NetState st((char*)A.state + (ec / NET_TILE) * net_tile_bytes(P), P);
+    const int el = (int)(ec % NET_TILE);  // position inside the state tile
     double* ring = st.ring;
-    const int64_t np_ = A.npad;
+    constexpr int np_ = NET_TILE;
 
     uint64_t key;
     uint32_t episode;
@@ -116,28 +118,28 @@ __global__ void __launch_bounds__(NTHR) net_sim_kernel(const __grid_constant__ N
         for (int i = 0; i < E; i++) sY[i * NTHR + tid] = 0.0;
         for (int r = 0; r < M; r++) sU[r * NTHR + tid] = 0.0;
         if (valid)
-            for (int k = 0; k < P.sumL; k++) ring[(size_t)k * np_ + e] = 0.0;
+            for (int k = 0; k < P.sumL; k++) ring[k * np_ + el] = 0.0;
     } else {
-        key = st.key[ec];
-        episode = st.episode[ec];
-        t0 = st.period[ec];
+        key = st.key[el];
+        episode = st.episode[el];
+        t0 = st.period[el];
         t1 = t0 + 1;
         if (valid && t0 >= P.T) {  // episode already over
             do_step = false;
             if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {
                 for (int j = 0; j < J; j++) {
-                    st.X[(size_t)j * np_ + e] = P.I0[j];
+                    st.X[j * np_ + el] = P.I0[j];
                     sX[j * NTHR + tid] = P.I0[j];
                 }
-                for (int i = 0; i < E; i++) st.Y[(size_t)i * np_ + e] = 0.0;
+                for (int i = 0; i < E; i++) st.Y[i * np_ + el] = 0.0;
                 for (int r = 0; r < M; r++) {
-                    st.U[(size_t)r * np_ + e] = 0.0;
+                    st.U[r * np_ + el] = 0.0;
                     sU[r * NTHR + tid] = 0.0;
                 }
-                for (int k = 0; k < P.sumL; k++) ring[(size_t)k * np_ + e] = 0.0;
-                st.period[e] = 0;
-                st.episode[e] = episode + 1;
-                net_write_obs<NTHR>(P, sU, sX, tid, ring, np_, e, 0, orow);
+                for (int k = 0; k < P.sumL; k++) ring[k * np_ + el] = 0.0;
+                st.period[el] = 0;
+                st.episode[el] = episode + 1;
+                net_write_obs<NTHR>(P, sU, sX, tid, ring, el, 0, orow);
                 A.reward[e] = 0.0;
                 A.terminated[e] = 0;
                 A.truncated[e] = 0;
@@ -151,9 +153,9 @@ __global__ void __launch_bounds__(NTHR) net_sim_kernel(const __grid_constant__ N
             }
         }
         if (do_step) {
-            for (int j = 0; j < J; j++) sX[j * NTHR + tid] = st.X[(size_t)j * np_ + e];
-            for (int i = 0; i < E; i++) sY[i * NTHR + tid] = st.Y[(size_t)i * np_ + e];
-            for (int r = 0; r < M; r++) sU[r * NTHR + tid] = st.U[(size_t)r * np_ + e];
+            for (int j = 0; j < J; j++) sX[j * NTHR + tid] = st.X[j * np_ + el];
+            for (int i = 0; i < E; i++) sY[i * NTHR + tid] = st.Y[i * np_ + el];
+            for (int r = 0; r < M; r++) sU[r * NTHR + tid] = st.U[r * np_ + el];
         }
     }
     double ret = 0.0, s_sales = 0.0, s_dem = 0.0, s_unf = 0.0, s_inv = 0.0, last_reward = 0.0;
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(NTHR) net_sim_kernel(const __grid_constant__ N
             for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
                 const int i = P.pred_idx[z], L = P.L[i];
                 arr += L == 0 ? sR[i * NTHR + tid]
-                              : ring[(size_t)(P.roff[i] + net_mod(t, L, P.Lmagic[i])) * np_ + ec];
+                              : ring[(P.roff[i] + net_mod(t, L, P.Lmagic[i])) * np_ + el];
             }
             sX[j * NTHR + tid] = (sX[j * NTHR + tid] + arr) - sC[j * NTHR + tid];
         }
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(NTHR) net_sim_kernel(const __grid_constant__ N
             const double rt = sR[i * NTHR + tid];
             double arriving = rt;
             if (L > 0) {
-                double* slot = ring + (size_t)(P.roff[i] + net_mod(t, L, P.Lmagic[i])) * np_ + ec;
+                double* slot = ring + (P.roff[i] + net_mod(t, L, P.Lmagic[i])) * np_ + el;
                 arriving = *slot;
                 if (valid) *slot = rt;
             }
@@ -320,26 +322,26 @@ __global__ void __launch_bounds__(NTHR) net_sim_kernel(const __grid_constant__ N
         const bool trunc = tn >= P.T;  // :624
         const bool reset_now = trunc && A.autoreset == ORGYM_AUTORESET_SAME_STEP;
         if (!reset_now) {
-            for (int j = 0; j < J; j++) st.X[(size_t)j * np_ + e] = sX[j * NTHR + tid];
-            for (int i = 0; i < E; i++) st.Y[(size_t)i * np_ + e] = sY[i * NTHR + tid];
-            for (int r = 0; r < M; r++) st.U[(size_t)r * np_ + e] = sU[r * NTHR + tid];
-            st.period[e] = tn;
-            net_write_obs<NTHR>(P, sU, sX, tid, ring, np_, e, tn, orow);
+            for (int j = 0; j < J; j++) st.X[j * np_ + el] = sX[j * NTHR + tid];
+            for (int i = 0; i < E; i++) st.Y[i * np_ + el] = sY[i * NTHR + tid];
+            for (int r = 0; r < M; r++) st.U[r * np_ + el] = sU[r * NTHR + tid];
+            st.period[el] = tn;
+            net_write_obs<NTHR>(P, sU, sX, tid, ring, el, tn, orow);
         } else {
-            if (A.final_obs) net_write_obs<NTHR>(P, sU, sX, tid, ring, np_, e, tn, A.final_obs + e * P.obs_dim);
+            if (A.final_obs) net_write_obs<NTHR>(P, sU, sX, tid, ring, el, tn, A.final_obs + e * P.obs_dim);
             for (int j = 0; j < J; j++) {
-                st.X[(size_t)j * np_ + e] = P.I0[j];
+                st.X[j * np_ + el] = P.I0[j];
                 sX[j * NTHR + tid] = P.I0[j];
             }
-            for (int i = 0; i < E; i++) st.Y[(size_t)i * np_ + e] = 0.0;
+            for (int i = 0; i < E; i++) st.Y[i * np_ + el] = 0.0;
             for (int r = 0; r < M; r++) {
-                st.U[(size_t)r * np_ + e] = 0.0;
+                st.U[r * np_ + el] = 0.0;
                 sU[r * NTHR + tid] = 0.0;
             }
-            for (int k = 0; k < P.sumL; k++) ring[(size_t)k * np_ + e] = 0.0;
-            st.period[e] = 0;
-            st.episode[e] = episode + 1;
-            net_write_obs<NTHR>(P, sU, sX, tid, ring, np_, e, 0, orow);
+            for (int k = 0; k < P.sumL; k++) ring[k * np_ + el] = 0.0;
+            st.period[el] = 0;
+            st.episode[el] = episode + 1;
+            net_write_obs<NTHR>(P, sU, sX, tid, ring, el, 0, orow);
         }
         A.reward[e] = last_reward;
         A.terminated[e] = 0;
@@ -360,16 +362,17 @@ __global__ void __launch_bounds__(NTHR) net_sim_kernel(const __grid_constant__ N
     }
 }
 
-__global__ void net_export_kernel(const __grid_constant__ NetDev P, int64_t N, int64_t npad, const void* state,
+__global__ void net_export_kernel(const __grid_constant__ NetDev P, int64_t N, const void* state,
                                   double* __restrict__ X, double* __restrict__ Y, double* __restrict__ U,
                                   int32_t* __restrict__ period) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= N) return;
-    NetState st((void*)state, npad, P);
-    if (X) for (int j = 0; j < P.J; j++) X[e * P.J + j] = st.X[(size_t)j * npad + e];
-    if (Y) for (int i = 0; i < P.E; i++) Y[e * P.E + i] = st.Y[(size_t)i * npad + e];
-    if (U) for (int r = 0; r < P.M; r++) U[e * P.M + r] = st.U[(size_t)r * npad + e];
-    if (period) period[e] = st.period[e];
+    NetState st((char*)state + (e / NET_TILE) * net_tile_bytes(P), P);
+    const int el = (int)(e % NET_TILE);
+    if (X) for (int j = 0; j < P.J; j++) X[e * P.J + j] = st.X[j * NET_TILE + el];
+    if (Y) for (int i = 0; i < P.E; i++) Y[e * P.E + i] = st.Y[i * NET_TILE + el];
+    if (U) for (int r = 0; r < P.M; r++) U[e * P.M + r] = st.U[r * NET_TILE + el];
+    if (period) period[e] = st.period[el];
 }
 
 
@@ -496,7 +499,6 @@ extern "C" int orgym_netinv_create(const orgym_netinv_config_t* c, int64_t num_e
         if (rc != ORGYM_OK) goto done;
         {
             DeviceGuard g(device);
-            H->npad = round_up(num_envs, 32);
             std::vector<double> disc((size_t)P.T);
             for (int t = 0; t < P.T; t++) disc[(size_t)t] = std::pow(c->alpha, (double)t);
             double* dd = nullptr;
@@ -573,7 +575,7 @@ extern "C" int orgym_netinv_destroy(orgym_handle_t h) {
 extern "C" int64_t orgym_netinv_state_bytes(orgym_handle_t h) {
     if (orgym_check_handle(h, FAM_NETINV)) return -1;
     NetHandle* H = (NetHandle*)h;
-    return net_state_bytes(H->dev, H->npad);
+    return net_state_bytes(H->dev, H->base.num_envs);
 }
 extern "C" int32_t orgym_netinv_obs_dim(orgym_handle_t h) {
     if (orgym_check_handle(h, FAM_NETINV)) return -1;
@@ -587,7 +589,7 @@ extern "C" int orgym_netinv_reset(orgym_handle_t h, void* state_dev, int reseed,
     ORGYM_REQUIRE(state_dev && obs_dev, "state_dev and obs_dev are required");
     DeviceGuard g(H->base.device);
     int64_t N = H->base.num_envs;
-    net_reset_kernel<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(H->dev, N, H->npad, state_dev, reseed,
+    net_reset_kernel<<<(unsigned)((N + NET_TILE - 1) / NET_TILE), NET_TILE, 0, (cudaStream_t)stream>>>(H->dev, N, state_dev, reseed,
                                                                                   seed, env_offset, mask_dev, obs_dev);
     ORGYM_CUDA(cudaGetLastError());
     return ORGYM_OK;
@@ -607,7 +609,6 @@ extern "C" int orgym_netinv_step(orgym_handle_t h, void* state_dev, const float*
     NetSimArgs A;
     memset(&A, 0, sizeof(A));
     A.N = H->base.num_envs;
-    A.npad = H->npad;
     A.rollout = 0;
     A.state = state_dev;
     A.policy = ORGYM_NET_POLICY_ACTIONS;
@@ -645,7 +646,7 @@ extern "C" int orgym_netinv_export_state(orgym_handle_t h, const void* state_dev
     ORGYM_REQUIRE(state_dev, "state_dev is required");
     DeviceGuard g(H->base.device);
     int64_t N = H->base.num_envs;
-    net_export_kernel<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(H->dev, N, H->npad, state_dev, X_dev,
+    net_export_kernel<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(H->dev, N, state_dev, X_dev,
                                                                                    Y_dev, U_dev, period_dev);
     ORGYM_CUDA(cudaGetLastError());
     return ORGYM_OK;
@@ -664,7 +665,6 @@ extern "C" int orgym_netinv_rollout(orgym_handle_t h, void* scratch_dev, uint64_
     NetSimArgs A;
     memset(&A, 0, sizeof(A));
     A.N = H->base.num_envs;
-    A.npad = H->npad;
     A.env_offset = env_offset;
     A.rollout = 1;
     A.state = scratch_dev;

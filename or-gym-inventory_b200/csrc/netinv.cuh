@@ -27,7 +27,6 @@ struct NetDev {
 struct NetHandle {
     HandleBase base;
     NetDev dev;
-    int64_t npad;
     int threads;  // threads per CTA that fit the shared-memory work vectors
     size_t smem;
     std::vector<void*> allocs;
@@ -40,30 +39,40 @@ struct NetHandle {
     AliasDev* dem_dev;  // device copy of dev.dem[] for the specialised kernel
 };
 
-// state (field[slot][env], stride npad): [key u64][X J][Y E][U M][ring sumL] f64, [period i32][episode u32]
+// State layout: tiles of NET_TILE = 128 instances; inside a tile every field is slot-major,
+//   [key u64][X J][Y E][U M][ring sumL] f64, [period i32][episode u32], [scratch: R_t E, consumed J] f64
+// each slot a contiguous row of 128 values (1 KB).  A warp still reads a slot with fully coalesced 256-byte
+// transactions, but -- unlike one global field[slot][env] array with a stride of round_up(N) elements -- the stride
+// between slots is a compile-time constant (every access of the specialised kernels becomes base + immediate, no
+// 64-bit index arithmetic) and the ~1700 slots of a 64-node graph that one CTA touches per period lie in one
+// contiguous 1.7 MB region instead of being spread over as many distinct 1 MB-apart rows (TLB reach, DRAM pages).
+#define NET_TILE 128
 struct NetState {
     uint64_t* key;
     double *X, *Y, *U, *ring;
     int32_t* period;
     uint32_t* episode;
-    int64_t npad;
-    __host__ __device__ NetState(void* base, int64_t npad_, const NetDev& P) : npad(npad_) {
-        char* p = (char*)base;
+    // tile_base = state + (env / NET_TILE) * net_tile_bytes(P); index the fields with [slot * NET_TILE + env % NET_TILE]
+    __host__ __device__ NetState(void* tile_base, const NetDev& P) {
+        char* p = (char*)tile_base;
         key = (uint64_t*)p;
-        p += 8 * npad;
+        p += 8 * NET_TILE;
         X = (double*)p;
-        Y = X + (size_t)P.J * npad;
-        U = Y + (size_t)P.E * npad;
-        ring = U + (size_t)P.M * npad;
-        p = (char*)(ring + (size_t)P.sumL * npad);
+        Y = X + (size_t)P.J * NET_TILE;
+        U = Y + (size_t)P.E * NET_TILE;
+        ring = U + (size_t)P.M * NET_TILE;
+        p = (char*)(ring + (size_t)P.sumL * NET_TILE);
         period = (int32_t*)p;
-        p += 4 * npad;
+        p += 4 * NET_TILE;
         episode = (uint32_t*)p;
     }
 };
-// ... followed by a per-instance scratch area [R_t E][consumed J] float64 used by the streaming STEP kernel
-static int64_t net_state_bytes(const NetDev& P, int64_t npad) {
-    return npad * (8 + 8 * (int64_t)(P.J + P.E + P.M + P.sumL) + 8 + 8 * (int64_t)(P.E + P.J));
+// ... followed by the per-instance scratch area [R_t E][consumed J] float64 used by the streaming STEP kernel
+__host__ __device__ static inline int64_t net_tile_bytes(const NetDev& P) {
+    return (int64_t)NET_TILE * (8 + 8 * (int64_t)(P.J + P.E + P.M + P.sumL) + 8 + 8 * (int64_t)(P.E + P.J));
+}
+static inline int64_t net_state_bytes(const NetDev& P, int64_t num_envs) {
+    return ((num_envs + NET_TILE - 1) / NET_TILE) * net_tile_bytes(P);
 }
 
 

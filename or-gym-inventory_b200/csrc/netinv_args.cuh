@@ -11,7 +11,7 @@
 #endif
 
 struct NetSimArgs {
-    int64_t N, npad, env_offset;
+    int64_t N, env_offset;
     int rollout;  // 0 = one period from / to state (STEP), 1 = fused episode (ROLLOUT)
     void* state;  // STEP: live state; ROLLOUT: scratch for the rings
     uint64_t seed;

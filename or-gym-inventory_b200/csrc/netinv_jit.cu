@@ -51,9 +51,11 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     o("#define NJ %d\n#define NE %d\n#define NM %d\n#define NOBS %d\n#define NSUML %d\n#define NT %d", J, E, M, P.obs_dim,
       P.sumL, P.T);
     o("#define OSTRIDE %d", P.obs_dim | 1);
+    // state tiles (netinv.cuh): NP instances per tile, slot stride NP, so every state access is base + constant
+    o("#define NP %d\n#define TILE_BYTES %lldLL", NET_TILE, (long long)net_tile_bytes(P));
     // ---- observation writer (:334-413)
     o("__device__ __forceinline__ void write_obs(const double (&X)[NJ > 0 ? NJ : 1], const double (&U)[NM > 0 ? NM : 1],");
-    o("    const double* __restrict__ ring, long long np, long long e, int t, float* o) {");
+    o("    const double* __restrict__ ring, int el, int t, float* o) {");
     for (int r = 0; r < M; r++) o("  o[%d] = (float)U[%d];", r, r);
     for (int j = 0; j < J; j++) o("  o[%d] = (float)X[%d];", M + j, j);
     {
@@ -61,9 +63,9 @@ std::string net_jit_source(const NetDev& P, int nthr) {
         for (int i = 0; i < E; i++) {
             const int L = P.L[i];
             if (L == 0) continue;
-            o("  { const int s0 = t %% %d; const double* b = ring + (long long)%d * np + e;", L, P.roff[i]);
+            o("  { const int s0 = t %% %d; const double* b = ring + %d * NP + el;", L, P.roff[i]);
             o("    double v[%d];", L);
-            o("    _Pragma(\"unroll\") for (int q = 0; q < %d; q++) { int sl = s0 + q; sl = sl >= %d ? sl - %d : sl; v[q] = b[(long long)sl * np]; }",
+            o("    _Pragma(\"unroll\") for (int q = 0; q < %d; q++) { int sl = s0 + q; sl = sl >= %d ? sl - %d : sl; v[q] = b[sl * NP]; }",
               L, L, L);
             o("    _Pragma(\"unroll\") for (int q = 0; q < %d; q++) o[%d + q] = (float)v[q]; }", L, k);
             k += L;
@@ -81,12 +83,13 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     o("  const int tid = threadIdx.x;");
     o("  const long long e0 = (long long)blockIdx.x * NTHR, e = e0 + tid;");
     o("  const bool valid = e < A.N;");
-    o("  const long long ec = valid ? e : 0, np = A.npad;");
-    o("  char* sb = (char*)A.state;");
+    o("  const long long ec = valid ? e : 0;");
+    o("  const int el = (int)(ec %% NP);");
+    o("  char* sb = (char*)A.state + (ec / NP) * TILE_BYTES;");
     o("  unsigned long long* s_key = (unsigned long long*)sb;");
-    o("  double* s_X = (double*)(sb + 8 * np); double* s_Y = s_X + (long long)NJ * np; double* s_U = s_Y + (long long)NE * np;");
-    o("  double* ring = s_U + (long long)NM * np;");
-    o("  int* s_period = (int*)(ring + (long long)NSUML * np); unsigned int* s_episode = (unsigned int*)(s_period + np);");
+    o("  double* s_X = (double*)(sb + 8 * NP); double* s_Y = s_X + NJ * NP; double* s_U = s_Y + NE * NP;");
+    o("  double* ring = s_U + NM * NP;");
+    o("  int* s_period = (int*)(ring + NSUML * NP); unsigned int* s_episode = (unsigned int*)(s_period + NP);");
     o("  double X[NJ > 0 ? NJ : 1], Y[NE > 0 ? NE : 1], U[NM > 0 ? NM : 1], R[NE > 0 ? NE : 1], S[NM > 0 ? NM : 1], Cn[NJ > 0 ? NJ : 1];");
     o("  unsigned long long key; unsigned int episode; int t0, t1; bool do_step = valid;");
     o("  float* orow = A.use_tile ? otile + tid * OSTRIDE : (A.obs ? A.obs + ec * NOBS : (float*)0);");
@@ -97,25 +100,25 @@ std::string net_jit_source(const NetDev& P, int nthr) {
         for (int r = 0; r < M; r++) o("%sU[%d] = 0.0;", ind, r);
     };
     auto emit_reset_state = [&](const char* ind) {
-        for (int j = 0; j < J; j++) o("%ss_X[(long long)%d * np + e] = %s;", ind, j, lit(P.I0[j]).c_str());
-        o("%sfor (int i = 0; i < NE; i++) s_Y[(long long)i * np + e] = 0.0;", ind);
-        o("%sfor (int r = 0; r < NM; r++) s_U[(long long)r * np + e] = 0.0;", ind);
-        o("%sfor (int k = 0; k < NSUML; k++) ring[(long long)k * np + e] = 0.0;", ind);
-        o("%ss_period[e] = 0;", ind);
+        for (int j = 0; j < J; j++) o("%ss_X[%d * NP + el] = %s;", ind, j, lit(P.I0[j]).c_str());
+        o("%sfor (int i = 0; i < NE; i++) s_Y[i * NP + el] = 0.0;", ind);
+        o("%sfor (int r = 0; r < NM; r++) s_U[r * NP + el] = 0.0;", ind);
+        o("%sfor (int k = 0; k < NSUML; k++) ring[k * NP + el] = 0.0;", ind);
+        o("%ss_period[el] = 0;", ind);
     };
     o("  if (ROLL) {");
     o("    key = A.seed + (unsigned long long)(A.env_offset + e); episode = A.episode; t0 = 0; t1 = NT;");
     emit_reset_regs("    ");
-    o("    if (valid) for (int k = 0; k < NSUML; k++) ring[(long long)k * np + e] = 0.0;");
+    o("    if (valid) for (int k = 0; k < NSUML; k++) ring[k * NP + el] = 0.0;");
     o("  } else {");
-    o("    key = s_key[ec]; episode = s_episode[ec]; t0 = s_period[ec]; t1 = t0 + 1;");
+    o("    key = s_key[el]; episode = s_episode[el]; t0 = s_period[el]; t1 = t0 + 1;");
     o("    if (valid && t0 >= NT) {");
     o("      do_step = false;");
     o("      if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {");
     emit_reset_state("        ");
     emit_reset_regs("        ");
-    o("        s_episode[e] = episode + 1;");
-    o("        write_obs(X, U, ring, np, e, 0, orow);");
+    o("        s_episode[el] = episode + 1;");
+    o("        write_obs(X, U, ring, el, 0, orow);");
     o("        A.reward[e] = 0.0; A.terminated[e] = 0; A.truncated[e] = 0;");
     o("      } else {");
     o("        atomicOr(A.err, ORGYM_ERR_STEP_PAST_END);");
@@ -124,9 +127,9 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     o("      }");
     o("    }");
     o("    if (do_step) {");
-    for (int j = 0; j < J; j++) o("      X[%d] = s_X[(long long)%d * np + e];", j, j);
-    for (int i = 0; i < E; i++) o("      Y[%d] = s_Y[(long long)%d * np + e];", i, i);
-    for (int r = 0; r < M; r++) o("      U[%d] = s_U[(long long)%d * np + e];", r, r);
+    for (int j = 0; j < J; j++) o("      X[%d] = s_X[%d * NP + el];", j, j);
+    for (int i = 0; i < E; i++) o("      Y[%d] = s_Y[%d * NP + el];", i, i);
+    for (int r = 0; r < M; r++) o("      U[%d] = s_U[%d * NP + el];", r, r);
     o("    }");
     o("  }");
     o("  double ret = 0.0, s_sales = 0.0, s_dem = 0.0, s_unf = 0.0, s_inv = 0.0, last_reward = 0.0;");
@@ -135,7 +138,7 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     // arrivals: all ring loads up front (independent -> overlapped)
     for (int i = 0; i < E; i++)
         if (P.L[i] > 0) {
-            o("    const long long sl%d = (long long)(%d + t %% %d) * np + ec;", i, P.roff[i], P.L[i]);
+            o("    const long long sl%d = (%d + t %% %d) * NP + el;", i, P.roff[i], P.L[i]);
             o("    const double Ar%d = ring[sl%d];", i, i);
         }
     o("    const float* arow = A.policy == ORGYM_NET_POLICY_CONSTANT ? A.actions : A.actions + ec * A.a_se + (long long)(ROLL ? t : 0) * A.a_st;");
@@ -269,17 +272,17 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     o("    const int tn = t0 + 1; const bool trunc = tn >= NT;");
     o("    const bool reset_now = trunc && A.autoreset == ORGYM_AUTORESET_SAME_STEP;");
     o("    if (!reset_now) {");
-    for (int j = 0; j < J; j++) o("      s_X[(long long)%d * np + e] = X[%d];", j, j);
-    for (int i = 0; i < E; i++) o("      s_Y[(long long)%d * np + e] = Y[%d];", i, i);
-    for (int r = 0; r < M; r++) o("      s_U[(long long)%d * np + e] = U[%d];", r, r);
-    o("      s_period[e] = tn;");
-    o("      write_obs(X, U, ring, np, e, tn, orow);");
+    for (int j = 0; j < J; j++) o("      s_X[%d * NP + el] = X[%d];", j, j);
+    for (int i = 0; i < E; i++) o("      s_Y[%d * NP + el] = Y[%d];", i, i);
+    for (int r = 0; r < M; r++) o("      s_U[%d * NP + el] = U[%d];", r, r);
+    o("      s_period[el] = tn;");
+    o("      write_obs(X, U, ring, el, tn, orow);");
     o("    } else {");
-    o("      if (A.final_obs) write_obs(X, U, ring, np, e, tn, A.final_obs + e * NOBS);");
+    o("      if (A.final_obs) write_obs(X, U, ring, el, tn, A.final_obs + e * NOBS);");
     emit_reset_state("      ");
     emit_reset_regs("      ");
-    o("      s_episode[e] = episode + 1;");
-    o("      write_obs(X, U, ring, np, e, 0, orow);");
+    o("      s_episode[el] = episode + 1;");
+    o("      write_obs(X, U, ring, el, 0, orow);");
     o("    }");
     o("    A.reward[e] = last_reward; A.terminated[e] = 0; A.truncated[e] = trunc ? 1 : 0;");
     o("  }");
@@ -333,28 +336,30 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
     o("    const AliasDev* __restrict__ dem) {");
     o("  __shared__ float tile[NTHR * 33];   // 32-column staging tile (+1 padding column: conflict-free)");
     o("  const int tid = threadIdx.x;");
-    o("  const long long e0 = (long long)blockIdx.x * NTHR, e = e0 + tid, np = A.npad;");
+    o("  const long long e0 = (long long)blockIdx.x * NTHR, e = e0 + tid;");
     o("  const int nvalid = (int)((A.N - e0) < NTHR ? (A.N - e0) : NTHR);");
     o("  const bool valid = tid < nvalid;");
-    o("  char* sb = (char*)A.state;");
+    o("  const long long ec = valid ? e : 0;");
+    o("  const int el = (int)(ec %% NP);");
+    o("  char* sb = (char*)A.state + (ec / NP) * TILE_BYTES;");
     o("  unsigned long long* s_key = (unsigned long long*)sb;");
-    o("  double* s_X = (double*)(sb + 8 * np); double* s_Y = s_X + (long long)NJ * np; double* s_U = s_Y + (long long)NE * np;");
-    o("  double* ring = s_U + (long long)NM * np;");
-    o("  int* s_period = (int*)(ring + (long long)NSUML * np); unsigned int* s_episode = (unsigned int*)(s_period + np);");
-    o("  double* sc_R = (double*)(s_episode + np); double* sc_C = sc_R + (long long)NE * np;");
+    o("  double* s_X = (double*)(sb + 8 * NP); double* s_Y = s_X + NJ * NP; double* s_U = s_Y + NE * NP;");
+    o("  double* ring = s_U + NM * NP;");
+    o("  int* s_period = (int*)(ring + NSUML * NP); unsigned int* s_episode = (unsigned int*)(s_period + NP);");
+    o("  double* sc_R = (double*)(s_episode + NP); double* sc_C = sc_R + NE * NP;");
     o("  float* trow = tile + tid * 33;");
     o("  bool do_step = valid;");
     o("  int t = 0; unsigned int episode = 0; unsigned long long key = 0;");
     o("  if (valid) {");
-    o("    t = s_period[e]; episode = s_episode[e]; key = s_key[e];");
+    o("    t = s_period[el]; episode = s_episode[el]; key = s_key[el];");
     o("    if (t >= NT) {");
     o("      do_step = false;");
     o("      if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {");
-    for (int j = 0; j < J; j++) o("        s_X[(long long)%d * np + e] = %s;", j, lit(P.I0[j]).c_str());
-    o("        for (int i = 0; i < NE; i++) s_Y[(long long)i * np + e] = 0.0;");
-    o("        for (int r = 0; r < NM; r++) s_U[(long long)r * np + e] = 0.0;");
-    o("        for (int k = 0; k < NSUML; k++) ring[(long long)k * np + e] = 0.0;");
-    o("        s_period[e] = 0; s_episode[e] = episode + 1;");
+    for (int j = 0; j < J; j++) o("        s_X[%d * NP + el] = %s;", j, lit(P.I0[j]).c_str());
+    o("        for (int i = 0; i < NE; i++) s_Y[i * NP + el] = 0.0;");
+    o("        for (int r = 0; r < NM; r++) s_U[r * NP + el] = 0.0;");
+    o("        for (int k = 0; k < NSUML; k++) ring[k * NP + el] = 0.0;");
+    o("        s_period[el] = 0; s_episode[el] = episode + 1;");
     o("        A.reward[e] = 0.0; A.terminated[e] = 0; A.truncated[e] = 0;");
     o("      } else {");
     o("        atomicOr(A.err, ORGYM_ERR_STEP_PAST_END);");
@@ -376,7 +381,7 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
         // independent loads first: the on-hand inventory of every supplier whose segment starts in this chunk
         for (int i = c0; i < c1; i++) {
             const int s = P.sup[i];
-            if (s >= 0 && (i == 0 || P.sup[i - 1] != s)) o("    xs%d = s_X[(long long)%d * np + e];", s, s);
+            if (s >= 0 && (i == 0 || P.sup[i - 1] != s)) o("    xs%d = s_X[%d * NP + el];", s, s);
         }
         for (int i = c0; i < c1; i++) {
             const int s = P.sup[i];
@@ -396,9 +401,9 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
                     o("      cons += f;");
                 else
                     o("      cons += f / %s;", lit(P.v[s]).c_str());
-                if (i == E - 1 || P.sup[i + 1] != s) o("      sc_C[(long long)%d * np + e] = cons;", s);
+                if (i == E - 1 || P.sup[i + 1] != s) o("      sc_C[%d * NP + el] = cons;", s);
             }
-            o("      sc_R[(long long)%d * np + e] = f;", i);
+            o("      sc_R[%d * NP + el] = f;", i);
             o("      if (A.info_sales) A.info_sales[e * (NE + NM) + %d] = f; }", i);
         }
         o("  }");
@@ -416,21 +421,21 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
         const int j1 = std::min(J, j0 + GROUP);
         o("    {");
         for (int j = j0; j < j1; j++) {  // load phase
-            o("      double x%d = s_X[(long long)%d * np + e];", j, j);
-            if (has_seg[j]) o("      const double c%d = sc_C[(long long)%d * np + e];", j, j);
+            o("      double x%d = s_X[%d * NP + el];", j, j);
+            if (has_seg[j]) o("      const double c%d = sc_C[%d * NP + el];", j, j);
             for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
                 const int i = P.pred_idx[z], L = P.L[i];
-                o("      const double rt%d = sc_R[(long long)%d * np + e]; const double y%d = s_Y[(long long)%d * np + e];", i, i, i, i);
+                o("      const double rt%d = sc_R[%d * NP + el]; const double y%d = s_Y[%d * NP + el];", i, i, i, i);
                 if (L > 0) {
-                    o("      double* const slot%d = ring + (long long)(%d + t %% %d) * np + e; const double ar%d = *slot%d;", i, P.roff[i], L,
+                    o("      double* const slot%d = ring + (%d + t %% %d) * NP + el; const double ar%d = *slot%d;", i, P.roff[i], L,
                       i, i);
                 }
             }
             for (int r = 0; r < M; r++)
-                if (P.rt_node[r] == j) o("      const double u%d = s_U[(long long)%d * np + e];", r, r);
+                if (P.rt_node[r] == j) o("      const double u%d = s_U[%d * NP + el];", r, r);
             for (int z = P.succ_ptr[j]; z < P.succ_ptr[j + 1]; z++) {
                 const int l = P.succ_idx[z];
-                if (l < E) o("      const double qs%d_%d = sc_R[(long long)%d * np + e];", j, l, l);
+                if (l < E) o("      const double qs%d_%d = sc_R[%d * NP + el];", j, l, l);
             }
         }
         for (int j = j0; j < j1; j++) {  // compute + store phase
@@ -442,7 +447,7 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
                     o("        { const double ar = rt%d;", i);
                 else
                     o("        { const double ar = ar%d; *slot%d = rt%d;", i, i, i);
-                o("          arr += ar; const double yn = (y%d - ar) + rt%d; s_Y[(long long)%d * np + e] = yn;", i, i, i);
+                o("          arr += ar; const double yn = (y%d - ar) + rt%d; s_Y[%d * NP + el] = yn;", i, i, i);
                 o("          PC += %s * rt%d; HCp += %s * (yn > 0.0 ? yn : 0.0); }", lit(P.p[i]).c_str(), i, lit(P.g[i]).c_str());
             }
             if (has_seg[j])
@@ -460,11 +465,11 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
                 o("          const double fill = d + u%d; const double invr = x > 0.0 ? x : 0.0;", r);
                 o("          S%d = invr < fill ? invr : fill; x = x - S%d; const double un = fill - S%d; U%d = %s;", r, r, r, r,
                   P.backlog ? "un" : "0.0");
-                o("          s_U[(long long)%d * np + e] = U%d;", r, r);
+                o("          s_U[%d * NP + el] = U%d;", r, r);
                 o("          if (A.info_demand) A.info_demand[e * NM + %d] = d;", r);
                 o("          if (A.info_sales) A.info_sales[e * (NE + NM) + %d] = S%d; }", E + r, r);
             }
-            o("        s_X[(long long)%d * np + e] = x;", j);
+            o("        s_X[%d * NP + el] = x;", j);
             for (int z = P.succ_ptr[j]; z < P.succ_ptr[j + 1]; z++) {
                 const int l = P.succ_idx[z];
                 if (l < E)
@@ -492,40 +497,40 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
     for (int i = 0; i < E; i++) {  // reorder links whose purchaser holds no inventory: pipeline bookkeeping only
         if (link_done[i]) continue;
         const int L = P.L[i];
-        o("    { const double rt = sc_R[(long long)%d * np + e];", i);
+        o("    { const double rt = sc_R[%d * NP + el];", i);
         if (L == 0)
             o("      const double ar = rt;");
         else
-            o("      double* slot = ring + (long long)(%d + t %% %d) * np + e; const double ar = *slot; *slot = rt;", P.roff[i], L);
-        o("      s_Y[(long long)%d * np + e] = (s_Y[(long long)%d * np + e] - ar) + rt; }", i, i);
+            o("      double* slot = ring + (%d + t %% %d) * NP + el; const double ar = *slot; *slot = rt;", P.roff[i], L);
+        o("      s_Y[%d * NP + el] = (s_Y[%d * NP + el] - ar) + rt; }", i, i);
     }
     o("    const int tn = t + 1; const bool trunc = tn >= NT;");
     o("    if (A.info_profit_total) A.info_profit_total[e] = total;");
     o("    A.reward[e] = disc[t] * total; A.terminated[e] = 0; A.truncated[e] = trunc ? 1 : 0;");
     o("    if (trunc && A.autoreset == ORGYM_AUTORESET_SAME_STEP) {");
     o("      if (A.final_obs) { double X[NJ], U[NM > 0 ? NM : 1];");
-    o("        for (int j = 0; j < NJ; j++) X[j] = s_X[(long long)j * np + e];");
-    o("        for (int r = 0; r < NM; r++) U[r] = s_U[(long long)r * np + e];");
-    o("        write_obs(X, U, ring, np, e, tn, A.final_obs + e * NOBS); }");
-    for (int j = 0; j < J; j++) o("      s_X[(long long)%d * np + e] = %s;", j, lit(P.I0[j]).c_str());
-    o("      for (int i = 0; i < NE; i++) s_Y[(long long)i * np + e] = 0.0;");
-    o("      for (int r = 0; r < NM; r++) s_U[(long long)r * np + e] = 0.0;");
-    o("      for (int k = 0; k < NSUML; k++) ring[(long long)k * np + e] = 0.0;");
-    o("      s_period[e] = 0; s_episode[e] = episode + 1;");
-    o("    } else s_period[e] = tn;");
+    o("        for (int j = 0; j < NJ; j++) X[j] = s_X[j * NP + el];");
+    o("        for (int r = 0; r < NM; r++) U[r] = s_U[r * NP + el];");
+    o("        write_obs(X, U, ring, el, tn, A.final_obs + e * NOBS); }");
+    for (int j = 0; j < J; j++) o("      s_X[%d * NP + el] = %s;", j, lit(P.I0[j]).c_str());
+    o("      for (int i = 0; i < NE; i++) s_Y[i * NP + el] = 0.0;");
+    o("      for (int r = 0; r < NM; r++) s_U[r * NP + el] = 0.0;");
+    o("      for (int k = 0; k < NSUML; k++) ring[k * NP + el] = 0.0;");
+    o("      s_period[el] = 0; s_episode[el] = episode + 1;");
+    o("    } else s_period[el] = tn;");
     o("  }");
     // ---- pass C: observation of the final state, 32 columns at a time
-    o("  const int tobs = valid ? s_period[e] : 0;");
+    o("  const int tobs = valid ? s_period[el] : 0;");
     {
         // column -> source expression
         std::vector<std::string> col((size_t)W);
         char buf[256];
         for (int r = 0; r < M; r++) {
-            snprintf(buf, sizeof(buf), "s_U[(long long)%d * np + e]", r);
+            snprintf(buf, sizeof(buf), "s_U[%d * NP + el]", r);
             col[(size_t)r] = buf;
         }
         for (int j = 0; j < J; j++) {
-            snprintf(buf, sizeof(buf), "s_X[(long long)%d * np + e]", j);
+            snprintf(buf, sizeof(buf), "s_X[%d * NP + el]", j);
             col[(size_t)(M + j)] = buf;
         }
         int k = M + J;
@@ -534,7 +539,7 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
             if (L == 0) continue;
             o("  const int w%d = tobs %% %d;", i, L);
             for (int q = 0; q < L; q++) {
-                snprintf(buf, sizeof(buf), "ring[(long long)(%d + (w%d + %d >= %d ? w%d + %d - %d : w%d + %d)) * np + e]", P.roff[i], i, q, L,
+                snprintf(buf, sizeof(buf), "ring[(%d + (w%d + %d >= %d ? w%d + %d - %d : w%d + %d)) * NP + el]", P.roff[i], i, q, L,
                          i, q, L, i, q);
                 col[(size_t)(k + q)] = buf;
             }
