@@ -14,6 +14,7 @@ statistics when N > 1).  Prints ONE JSON line (see the task contract); extra key
   cpu_baseline       the C oracle port of the reference's evaluation loop on all host cores (bounded sample)
   e2e                the same rollout through the public Python API with per-episode results copied to pinned host
                      memory every step
+  e2e_step_api       the host-driven policy loop: actions H2D, observation/reward/flags D2H every period (2^20 instances)
 `--impl reference` times the CPU port itself (the reference is pure Python and cannot travel to the GPU box; its
 in-container rates are recorded in DESIGN.md).
 """
@@ -418,6 +419,47 @@ def main():
                                                  "frac": N * ab / (sms0 * 1e-3) / 1e9 / hbm_peak}
         env0.close()
         del a, env0
+        # ---- the host-driven loop (a policy on the CPU: numpy actions in, observations out every period) ------------
+        # Same step kernel, but the Gymnasium tensors cross PCIe both ways each period and the host waits for them:
+        # this is what the reference's agent loop costs when only the env moves to the GPU.
+        Ns = min(N, 1 << 20)
+        envh = cls0(num_envs=Ns, device=dev, env_offset=offset, info_level=0)
+        obs_d, _ = envh.reset(seed=W["seed"])
+        if args.workload == "invmgmt":
+            a_h = torch.randint(0, 100, (Ns, 3), dtype=torch.int64).pin_memory()
+        elif args.workload == "newsvendor":
+            a_h = (torch.rand((Ns, 1)) * 100).pin_memory()
+        else:
+            a_h = (torch.rand((Ns, len(envh.reorder_links))) * 100).pin_memory()
+        a_d = torch.empty_like(a_h, device=dev)
+        obs_h = torch.empty(obs_d.shape, dtype=obs_d.dtype).pin_memory()
+        rew_h = torch.empty(Ns, dtype=torch.float64).pin_memory()
+        tr_h = torch.empty(Ns, dtype=torch.uint8).pin_memory()
+
+        def host_step():
+            a_d.copy_(a_h, non_blocking=True)
+            o, r, _, tr, _ = envh.step(a_d)
+            obs_h.copy_(o, non_blocking=True)
+            rew_h.copy_(r.view(-1), non_blocking=True)
+            tr_h.copy_(tr.view(-1).view(torch.uint8), non_blocking=True)
+            torch.cuda.synchronize()
+            return float(rew_h[0]) + float(obs_h.view(-1)[0])      # the host policy reads what came back
+
+        for _ in range(3):
+            host_step()
+        hs = 10
+        t0 = time.perf_counter()
+        for _ in range(hs):
+            host_step()
+        hdt = time.perf_counter() - t0
+        line["e2e_step_api"] = {"value": Ns * hs / hdt, "unit": "env-steps/s", "instances": Ns, "steps": hs,
+                                "h2d_bytes_per_step": a_h.numel() * a_h.element_size(),
+                                "d2h_bytes_per_step": obs_h.numel() * obs_h.element_size() + Ns * 9,
+                                "note": "host-driven policy loop on rank 0: actions from pinned host memory, observation + "
+                                        "reward + truncated flags back to pinned host memory, host waits every period "
+                                        "(PCIe-bound; the fused on-device policies exist to avoid exactly this)"}
+        envh.close()
+        del envh, a_d, a_h, obs_h
         torch.cuda.empty_cache()
         if world == 1:
             line["cpu_baseline"] = cpu_port_rate(args.workload, seconds=10.0)

@@ -348,6 +348,9 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
     o("  int* s_period = (int*)(ring + NSUML * NP); unsigned int* s_episode = (unsigned int*)(s_period + NP);");
     o("  double* sc_R = (double*)(s_episode + NP); double* sc_C = sc_R + NE * NP;");
     o("  float* trow = tile + tid * 33;");
+    // every warp transposes the 32 rows of its own lanes: the staging tile needs warp-level synchronisation only,
+    // so the warps of a CTA drift apart and cover each other's memory latency
+    o("  const int ln = tid & 31, wrow0 = tid & ~31, wrow1 = nvalid < wrow0 + 32 ? (nvalid > wrow0 ? nvalid : wrow0) : wrow0 + 32;");
     o("  bool do_step = valid;");
     o("  int t = 0; unsigned int episode = 0; unsigned long long key = 0;");
     o("  if (valid) {");
@@ -373,10 +376,10 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
         if (has_seg[j]) o("  double xs%d = 0.0;", j);
     for (int c0 = 0; c0 < E; c0 += 32) {
         const int c1 = std::min(E, c0 + 32);
-        o("  __syncthreads();");
-        o("  for (int i = tid; i < nvalid * 32; i += NTHR) { const int r = i >> 5, c = i & 31;");
-        o("    if (%d + c < NE) tile[r * 33 + c] = A.actions[(e0 + r) * NE + %d + c]; }", c0, c0);
-        o("  __syncthreads();");
+        o("  __syncwarp();");
+        o("  for (int r = wrow0; r < wrow1; r++)");
+        o("    if (%d + ln < NE) tile[r * 33 + ln] = A.actions[(e0 + r) * NE + %d + ln];", c0, c0);
+        o("  __syncwarp();");
         o("  if (do_step) {");
         // independent loads first: the on-hand inventory of every supplier whose segment starts in this chunk
         for (int i = c0; i < c1; i++) {
@@ -562,10 +565,10 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
             if (!dbuf) emit_loads("v", c0);
             if (dbuf && c0 + 32 < W) emit_loads("vn", c0 + 32);
             o("  _Pragma(\"unroll\") for (int c = 0; c < %d; c++) trow[c] = v[c];", c1 - c0);
-            o("  __syncthreads();");
-            o("  for (int i = tid; i < nvalid * 32; i += NTHR) { const int r = i >> 5, c = i & 31;");
-            o("    if (%d + c < NOBS) __stcs(A.obs + (e0 + r) * NOBS + %d + c, tile[r * 33 + c]); }", c0, c0);
-            o("  __syncthreads();");
+            o("  __syncwarp();");
+            o("  for (int r = wrow0; r < wrow1; r++)");
+            o("    if (%d + ln < NOBS) __stcs(A.obs + (e0 + r) * NOBS + %d + ln, tile[r * 33 + ln]);", c0, c0);
+            o("  __syncwarp();");
             if (dbuf && c0 + 32 < W) o("  _Pragma(\"unroll\") for (int c = 0; c < 32; c++) v[c] = vn[c];");
         }
     }
