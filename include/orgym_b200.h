@@ -115,6 +115,9 @@ typedef struct {
     int64_t* unfulfilled_dev; /* [N,m]  unfulfilled */
     double* profit_dev;       /* [N]    period_profit (undiscounted) */
     int64_t* final_obs_dev;   /* [N,obs_dim] last observation of an episode (SAME_STEP autoreset) */
+    /* layout of sales / unfulfilled: 0 = row-major [N][m]; ld > 0 = column-major [m][ld], ld >= N, element (env, k)
+     * at k*ld + env (coalesced stores).  final_obs_dev is always row-major. */
+    int64_t info_ld;
 } orgym_invmgmt_info_t;
 
 int orgym_invmgmt_create(const orgym_invmgmt_config_t* cfg, int64_t num_envs, int device, orgym_handle_t* out);
@@ -191,6 +194,7 @@ typedef struct {
     int64_t* demand_dev; /* [N] */
     double* parts_dev;   /* [N,4] revenue, purchase_cost, holding_cost, lost_sales_penalty (newsvendor.py:195-199) */
     float* final_obs_dev; /* [N,obs_dim] (SAME_STEP autoreset) */
+    int64_t info_ld;      /* layout of parts: 0 = row-major [N][4]; ld > 0 = column-major [4][ld], ld >= N */
 } orgym_newsvendor_info_t;
 
 int orgym_newsvendor_create(const orgym_newsvendor_config_t* cfg, int64_t num_envs, int device, orgym_handle_t* out);
@@ -288,6 +292,10 @@ typedef struct {
     double* profit_dev;    /* [N,J] P[t] per node */
     double* profit_total_dev; /* [N] undiscounted period profit (:630) */
     float* final_obs_dev;  /* [N,obs_dim] (SAME_STEP autoreset) */
+    /* layout of the two-dimensional tensors above (demand, sales, profit): 0 = row-major [N][dim];
+     * ld > 0 = column-major [dim][ld] with ld >= N, element (env, k) at k*ld + env -- every store of the kernels is then
+     * a coalesced one (the row-major form costs the 64-node step kernel ~30 %).  final_obs_dev is always row-major. */
+    int64_t info_ld;
 } orgym_netinv_info_t;
 
 int orgym_netinv_create(const orgym_netinv_config_t* cfg, int64_t num_envs, int device, orgym_handle_t* out);

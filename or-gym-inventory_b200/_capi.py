@@ -37,7 +37,7 @@ class InvConfig(C.Structure):
 
 class InvInfo(C.Structure):
     _fields_ = [("demand", C.c_void_p), ("sales", C.c_void_p), ("unfulfilled", C.c_void_p),
-                ("profit", C.c_void_p), ("final_obs", C.c_void_p)]
+                ("profit", C.c_void_p), ("final_obs", C.c_void_p), ("info_ld", C.c_int64)]
 
 
 class InvRolloutIn(C.Structure):
@@ -58,7 +58,7 @@ class NvConfig(C.Structure):
 
 
 class NvInfo(C.Structure):
-    _fields_ = [("demand", C.c_void_p), ("parts", C.c_void_p), ("final_obs", C.c_void_p)]
+    _fields_ = [("demand", C.c_void_p), ("parts", C.c_void_p), ("final_obs", C.c_void_p), ("info_ld", C.c_int64)]
 
 
 class NvRolloutIn(C.Structure):
@@ -85,7 +85,7 @@ class NetConfig(C.Structure):
 
 class NetInfo(C.Structure):
     _fields_ = [("demand", C.c_void_p), ("sales", C.c_void_p), ("profit", C.c_void_p),
-                ("profit_total", C.c_void_p), ("final_obs", C.c_void_p)]
+                ("profit_total", C.c_void_p), ("final_obs", C.c_void_p), ("info_ld", C.c_int64)]
 
 
 class NetRolloutIn(C.Structure):

@@ -91,6 +91,7 @@ struct InvStepArgs {
     int64_t* info_sales;
     int64_t* info_unf;
     double* info_profit;
+    int64_t info_ld;  // 0: sales / unfulfilled row-major [N][m]; > 0: column-major [m][info_ld]
     int64_t* final_obs;
     uint32_t* err;
     int use_bulk;
@@ -468,29 +469,38 @@ __global__ void __launch_bounds__(ORGYM_TILE, (NS <= 4 && sizeof(S) == 4) ? ORGY
             sv[0] = (long long)s0;
 #pragma unroll
             for (int i = 0; i < NS; i++) sv[i + 1] = (EXACT || i < n) ? (long long)Rf[i] : 0;
-            if (A.info_sales) {
-                int64_t* row = A.info_sales + e * m;
-                if (EXACT && (((NS + 1) & 1) == 0)) {
+            if (A.info_ld) {  // column-major: one coalesced 8-byte store per stage
 #pragma unroll
-                    for (int j = 0; j < NS + 1; j += 2)
-                        *reinterpret_cast<longlong2*>(row + j) = make_longlong2(sv[j], sv[j + 1 <= NS ? j + 1 : NS]);
-                } else {
+                for (int j = 0; j <= NS; j++)
+                    if (EXACT || j <= n) {
+                        if (A.info_sales) A.info_sales[(int64_t)j * A.info_ld + e] = sv[j];
+                        if (A.info_unf) A.info_unf[(int64_t)j * A.info_ld + e] = (long long)U[j];
+                    }
+            } else {
+                if (A.info_sales) {
+                    int64_t* row = A.info_sales + e * m;
+                    if (EXACT && (((NS + 1) & 1) == 0)) {
 #pragma unroll
-                    for (int j = 0; j <= NS; j++)
-                        if (EXACT || j <= n) row[j] = sv[j];
+                        for (int j = 0; j < NS + 1; j += 2)
+                            *reinterpret_cast<longlong2*>(row + j) = make_longlong2(sv[j], sv[j + 1 <= NS ? j + 1 : NS]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j <= NS; j++)
+                            if (EXACT || j <= n) row[j] = sv[j];
+                    }
                 }
-            }
-            if (A.info_unf) {
-                int64_t* row = A.info_unf + e * m;
-                if (EXACT && (((NS + 1) & 1) == 0)) {
+                if (A.info_unf) {
+                    int64_t* row = A.info_unf + e * m;
+                    if (EXACT && (((NS + 1) & 1) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < NS + 1; j += 2)
-                        *reinterpret_cast<longlong2*>(row + j) =
-                            make_longlong2((long long)U[j], (long long)U[j + 1 <= NS ? j + 1 : NS]);
-                } else {
+                        for (int j = 0; j < NS + 1; j += 2)
+                            *reinterpret_cast<longlong2*>(row + j) =
+                                make_longlong2((long long)U[j], (long long)U[j + 1 <= NS ? j + 1 : NS]);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j <= NS; j++)
-                        if (EXACT || j <= n) row[j] = (long long)U[j];
+                        for (int j = 0; j <= NS; j++)
+                            if (EXACT || j <= n) row[j] = (long long)U[j];
+                    }
                 }
             }
         }
@@ -948,6 +958,8 @@ extern "C" int orgym_invmgmt_step(orgym_handle_t h, void* state_dev, const void*
         A.info_sales = info->sales_dev;
         A.info_unf = info->unfulfilled_dev;
         A.info_profit = info->profit_dev;
+        ORGYM_REQUIRE(info->info_ld == 0 || info->info_ld >= H->base.num_envs, "info_ld must be 0 (row-major) or >= num_envs");
+        A.info_ld = info->info_ld;
         A.final_obs = info->final_obs_dev;
     }
     A.err = H->base.err_dev;

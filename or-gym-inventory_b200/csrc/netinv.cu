@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(NTHR) net_sim_kernel(const __grid_constant__ N
             s_sales += sl;
             s_dem += d;
             s_unf += P.backlog ? un : 0.0;
-            if (!A.rollout && A.info_demand && do_step) A.info_demand[e * M + r] = d;
+            if (!A.rollout && A.info_demand && do_step) A.info_demand[NET_IIDX(A, e, M, r)] = d;
         }
         // ---- 5) profit per node, Python sum order (:578-613)
         double total = 0.0;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(NTHR) net_sim_kernel(const __grid_constant__ N
             double pj = (((SR - PC) - OC) - HC) - UP;  // :611
             total += pj;
             s_inv += xp;
-            if (!A.rollout && A.info_profit && do_step) A.info_profit[e * J + j] = pj;
+            if (!A.rollout && A.info_profit && do_step) A.info_profit[NET_IIDX(A, e, J, j)] = pj;
         }
         last_reward = P.disc[t] * total;  // :619
         ret += last_reward;
@@ -280,8 +280,8 @@ __global__ void __launch_bounds__(NTHR) net_sim_kernel(const __grid_constant__ N
         if (!A.rollout && do_step) {
             if (A.info_profit_total) A.info_profit_total[e] = total;
             if (A.info_sales) {
-                for (int i = 0; i < E; i++) A.info_sales[e * (E + M) + i] = sR[i * NTHR + tid];
-                for (int r = 0; r < M; r++) A.info_sales[e * (E + M) + E + r] = sS[r * NTHR + tid];
+                for (int i = 0; i < E; i++) A.info_sales[NET_IIDX(A, e, E + M, i)] = sR[i * NTHR + tid];
+                for (int r = 0; r < M; r++) A.info_sales[NET_IIDX(A, e, E + M, E + r)] = sS[r * NTHR + tid];
             }
         }
     }
@@ -628,6 +628,8 @@ extern "C" int orgym_netinv_step(orgym_handle_t h, void* state_dev, const float*
         A.info_sales = info->sales_dev;
         A.info_profit = info->profit_dev;
         A.info_profit_total = info->profit_total_dev;
+        ORGYM_REQUIRE(info->info_ld == 0 || info->info_ld >= H->base.num_envs, "info_ld must be 0 (row-major) or >= num_envs");
+        A.info_ld = info->info_ld;
         A.final_obs = info->final_obs_dev;
     }
     A.err = H->base.err_dev;

@@ -10,6 +10,9 @@
 #define ORGYM_NET_POLICY_CONSTANT 1
 #endif
 
+// element (env e, column k) of a two-dimensional info tensor with `dim` columns
+#define NET_IIDX(A, e, dim, k) ((A).info_ld ? (long long)(k) * (A).info_ld + (e) : (e) * (long long)(dim) + (k))
+
 struct NetSimArgs {
     int64_t N, env_offset;
     int rollout;  // 0 = one period from / to state (STEP), 1 = fused episode (ROLLOUT)
@@ -31,6 +34,7 @@ struct NetSimArgs {
     double* info_sales;
     double* info_profit;
     double* info_profit_total;
+    int64_t info_ld;  // 0: info tensors row-major [N][dim]; > 0: column-major [dim][info_ld]
     float* final_obs;
     uint32_t* err;
     int use_tile;  // STEP: stage the observation block in shared memory and store it coalesced

@@ -42,6 +42,26 @@ int net_jit_uses_stream(const NetDev& P) {
     return stream;
 }
 
+// streaming STEP kernel, observation pass: geometry of the asynchronous staging (cp.async)
+static int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* v = getenv(name);
+    if (!v) return dflt;
+    const int x = atoi(v);
+    return x < lo || x > hi ? dflt : x;
+}
+static int stream_async() { return env_int("ORGYM_NET_JIT_ASYNC", 1, 0, 1); }
+static int stream_cw() {
+    const int c = env_int("ORGYM_NET_JIT_CW", 16, 8, 32);
+    return c >= 32 ? 32 : (c >= 16 ? 16 : 8);
+}
+static int stream_nst() { return env_int("ORGYM_NET_JIT_NST", 3, 2, 6); }
+size_t net_jit_stream_smem(int nthr) {
+    const size_t act = (size_t)nthr * 33 * 4;
+    if (!stream_async()) return act;
+    const size_t st = (size_t)stream_nst() * nthr * (stream_cw() + 1) * 8;
+    return st > act ? st : act;
+}
+
 std::string net_jit_source(const NetDev& P, int nthr) {
     const int J = P.J, E = P.E, M = P.M;
     Src o;
@@ -200,7 +220,7 @@ std::string net_jit_source(const NetDev& P, int nthr) {
         o("      double fill = d + U[%d]; double x = X[%d]; double invr = x > 0.0 ? x : 0.0;", r, j);
         o("      double sl = invr < fill ? invr : fill; S[%d] = sl; X[%d] = x - sl; double un = fill - sl;", r, j);
         o("      U[%d] = %s; s_sales += sl; s_dem += d; s_unf += %s;", r, P.backlog ? "un" : "0.0", P.backlog ? "un" : "0.0");
-        o("      if (!ROLL && A.info_demand && do_step) A.info_demand[e * NM + %d] = d; }", r);
+        o("      if (!ROLL && A.info_demand && do_step) A.info_demand[NET_IIDX(A, e, NM, %d)] = d; }", r);
     }
     // 5) profit (:578-613)
     o("    double total = 0.0;");
@@ -231,15 +251,15 @@ std::string net_jit_source(const NetDev& P, int nthr) {
                 o("      OC = %s * (sold / %s);", lit(P.o[j]).c_str(), lit(P.v[j]).c_str());
         }
         o("      (void)sold; double pj = (((SR - PC) - OC) - HC) - UP; total += pj; s_inv += xp;");
-        o("      if (!ROLL && A.info_profit && do_step) A.info_profit[e * NJ + %d] = pj; }", j);
+        o("      if (!ROLL && A.info_profit && do_step) A.info_profit[NET_IIDX(A, e, NJ, %d)] = pj; }", j);
     }
     o("    last_reward = disc[t] * total; ret += last_reward;");
     o("    if (ROLL && A.reward_traj && valid) A.reward_traj[e * NT + t] = last_reward;");
     o("    if (!ROLL && do_step) {");
     o("      if (A.info_profit_total) A.info_profit_total[e] = total;");
     o("      if (A.info_sales) {");
-    for (int i = 0; i < E; i++) o("        A.info_sales[e * (NE + NM) + %d] = R[%d];", i, i);
-    for (int r = 0; r < M; r++) o("        A.info_sales[e * (NE + NM) + %d] = S[%d];", E + r, r);
+    for (int i = 0; i < E; i++) o("        A.info_sales[NET_IIDX(A, e, NE + NM, %d)] = R[%d];", i, i);
+    for (int r = 0; r < M; r++) o("        A.info_sales[NET_IIDX(A, e, NE + NM, %d)] = S[%d];", E + r, r);
     o("      }");
     o("    }");
     o("  }");  // t loop
@@ -334,7 +354,8 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
         if (P.sup[i] >= 0) has_seg[P.sup[i]] = 1;
     o("extern \"C\" __global__ void __launch_bounds__(NTHR, %d) net_jit_step(const NetSimArgs A, const double* __restrict__ disc,", min_blocks);
     o("    const AliasDev* __restrict__ dem) {");
-    o("  __shared__ float tile[NTHR * 33];   // 32-column staging tile (+1 padding column: conflict-free)");
+    o("  extern __shared__ __align__(16) unsigned char smem_raw[];");
+    o("  float* tile = (float*)smem_raw;   // [NTHR][33] 32-column staging tile (+1 padding column: conflict-free)");
     o("  const int tid = threadIdx.x;");
     o("  const long long e0 = (long long)blockIdx.x * NTHR, e = e0 + tid;");
     o("  const int nvalid = (int)((A.N - e0) < NTHR ? (A.N - e0) : NTHR);");
@@ -407,7 +428,7 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
                 if (i == E - 1 || P.sup[i + 1] != s) o("      sc_C[%d * NP + el] = cons;", s);
             }
             o("      sc_R[%d * NP + el] = f;", i);
-            o("      if (A.info_sales) A.info_sales[e * (NE + NM) + %d] = f; }", i);
+            o("      if (A.info_sales) A.info_sales[NET_IIDX(A, e, NE + NM, %d)] = f; }", i);
         }
         o("  }");
     }
@@ -469,8 +490,8 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
                 o("          S%d = invr < fill ? invr : fill; x = x - S%d; const double un = fill - S%d; U%d = %s;", r, r, r, r,
                   P.backlog ? "un" : "0.0");
                 o("          s_U[%d * NP + el] = U%d;", r, r);
-                o("          if (A.info_demand) A.info_demand[e * NM + %d] = d;", r);
-                o("          if (A.info_sales) A.info_sales[e * (NE + NM) + %d] = S%d; }", E + r, r);
+                o("          if (A.info_demand) A.info_demand[NET_IIDX(A, e, NM, %d)] = d;", r);
+                o("          if (A.info_sales) A.info_sales[NET_IIDX(A, e, NE + NM, %d)] = S%d; }", E + r, r);
             }
             o("        s_X[%d * NP + el] = x;", j);
             for (int z = P.succ_ptr[j]; z < P.succ_ptr[j + 1]; z++) {
@@ -493,7 +514,7 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
                     o("        OC = %s * (sold / %s);", lit(P.o[j]).c_str(), lit(P.v[j]).c_str());
             }
             o("        (void)sold; const double pj = (((SR - PC) - OC) - HC) - UP; total += pj;");
-            o("        if (A.info_profit) A.info_profit[e * NJ + %d] = pj; }", j);
+            o("        if (A.info_profit) A.info_profit[NET_IIDX(A, e, NJ, %d)] = pj; }", j);
         }
         o("    }");
     }
@@ -548,28 +569,63 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
             }
             k += L;
         }
-        // double-buffered: the loads of chunk c+1 are issued before chunk c is flushed, so their latency overlaps the flush
-        int dbuf = 1;
-        if (const char* dv = getenv("ORGYM_NET_JIT_DBUF")) dbuf = atoi(dv) ? 1 : 0;
-        o("  float v[32];");
-        if (dbuf) o("  float vn[32];");
-        auto emit_loads = [&](const char* dst, int c0) {
-            const int c1 = std::min(W, c0 + 32);
-            o("  if (valid) {");
-            for (int c = c0; c < c1; c++) o("    %s[%d] = (float)%s;", dst, c - c0, col[(size_t)c].c_str());
-            o("  }");
-        };
-        if (dbuf) emit_loads("v", 0);
-        for (int c0 = 0; c0 < W; c0 += 32) {
-            const int c1 = std::min(W, c0 + 32);
-            if (!dbuf) emit_loads("v", c0);
-            if (dbuf && c0 + 32 < W) emit_loads("vn", c0 + 32);
-            o("  _Pragma(\"unroll\") for (int c = 0; c < %d; c++) trow[c] = v[c];", c1 - c0);
-            o("  __syncwarp();");
-            o("  for (int r = wrow0; r < wrow1; r++)");
-            o("    if (%d + ln < NOBS) __stcs(A.obs + (e0 + r) * NOBS + %d + ln, tile[r * 33 + ln]);", c0, c0);
-            o("  __syncwarp();");
-            if (dbuf && c0 + 32 < W) o("  _Pragma(\"unroll\") for (int c = 0; c < 32; c++) v[c] = vn[c];");
+        if (stream_async()) {
+            // Asynchronous staging: every thread copies the float64 sources of CW observation columns of its own
+            // instance straight into shared memory with cp.async (SASS LDGSTS: no destination registers, no
+            // scoreboard wait), NST chunks deep; the warp then converts and writes the rows of its 32 lanes with
+            // coalesced stores.  Every warp owns the rows of its lanes in every stage, so __syncwarp suffices.
+            const int CW = stream_cw(), NST = stream_nst(), RPI = 32 / CW;
+            const int nchunk = (W + CW - 1) / CW;
+            o("  __syncthreads();   // the action tile of pass A and the staging buffers share the dynamic shared memory");
+            o("  double* dt = (double*)smem_raw;   // [%d stages][NTHR][%d + 1]", NST, CW);
+            o("  const unsigned dt_me = (unsigned)__cvta_generic_to_shared(dt + tid * %d);", CW + 1);
+            o("  const int lc = ln %% %d, lr = ln / %d;", CW, CW);
+            auto emit_issue = [&](int ch) {
+                if (ch < nchunk) {
+                    const int c0 = ch * CW, c1 = std::min(W, c0 + CW), st = ch % NST;
+                    o("  if (valid) {");
+                    for (int c = c0; c < c1; c++)
+                        o("    asm volatile(\"cp.async.ca.shared.global [%%0], [%%1], 8;\" :: \"r\"(dt_me + %du * NTHR + %du), \"l\"(&%s) : \"memory\");",
+                          (unsigned)(st * (CW + 1) * 8), (unsigned)(8 * (c - c0)), col[(size_t)c].c_str());
+                    o("  }");
+                }
+                o("  asm volatile(\"cp.async.commit_group;\" ::: \"memory\");");
+            };
+            for (int ch = 0; ch < NST - 1; ch++) emit_issue(ch);
+            for (int ch = 0; ch < nchunk; ch++) {
+                const int c0 = ch * CW, st = ch % NST;
+                emit_issue(ch + NST - 1);
+                o("  asm volatile(\"cp.async.wait_group %d;\" ::: \"memory\");", NST - 1);
+                o("  __syncwarp();");
+                o("  { const double* sb_ = dt + %d * NTHR;", st * (CW + 1));
+                o("    for (int r = wrow0 + lr; r < wrow1; r += %d)", RPI);
+                o("      if (%d + lc < NOBS) __stcs(A.obs + (e0 + r) * NOBS + %d + lc, (float)sb_[r * %d + lc]); }", c0, c0, CW + 1);
+                o("  __syncwarp();");
+            }
+        } else {
+            // double-buffered: the loads of chunk c+1 are issued before chunk c is flushed, so their latency overlaps the flush
+            int dbuf = 1;
+            if (const char* dv = getenv("ORGYM_NET_JIT_DBUF")) dbuf = atoi(dv) ? 1 : 0;
+            o("  float v[32];");
+            if (dbuf) o("  float vn[32];");
+            auto emit_loads = [&](const char* dst, int c0) {
+                const int c1 = std::min(W, c0 + 32);
+                o("  if (valid) {");
+                for (int c = c0; c < c1; c++) o("    %s[%d] = (float)%s;", dst, c - c0, col[(size_t)c].c_str());
+                o("  }");
+            };
+            if (dbuf) emit_loads("v", 0);
+            for (int c0 = 0; c0 < W; c0 += 32) {
+                const int c1 = std::min(W, c0 + 32);
+                if (!dbuf) emit_loads("v", c0);
+                if (dbuf && c0 + 32 < W) emit_loads("vn", c0 + 32);
+                o("  _Pragma(\"unroll\") for (int c = 0; c < %d; c++) trow[c] = v[c];", c1 - c0);
+                o("  __syncwarp();");
+                o("  for (int r = wrow0; r < wrow1; r++)");
+                o("    if (%d + ln < NOBS) __stcs(A.obs + (e0 + r) * NOBS + %d + ln, tile[r * 33 + ln]);", c0, c0);
+                o("  __syncwarp();");
+                if (dbuf && c0 + 32 < W) o("  _Pragma(\"unroll\") for (int c = 0; c < 32; c++) v[c] = vn[c];");
+            }
         }
     }
     o("}");
@@ -615,7 +671,8 @@ int net_jit_launch(const NetHandle* H, const NetSimArgs& A_in, cudaStream_t s) {
     size_t tile = (size_t)nthr * (P.obs_dim | 1) * 4;
     size_t smem = 16;
     if (!A.rollout && H->jit_stream) {
-        A.use_tile = 0;  // the streaming kernel stages through its own static 32-column tile
+        A.use_tile = 0;  // the streaming kernel stages through its own tiles
+        smem = net_jit_stream_smem(nthr);
     } else if (!A.rollout) {
         A.use_tile = tile <= 160 * 1024 ? 1 : 0;
         if (A.use_tile) smem = tile;

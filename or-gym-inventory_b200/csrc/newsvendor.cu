@@ -218,6 +218,7 @@ struct NvStepArgs {
     uint8_t* truncated;
     int64_t* info_demand;
     double* info_parts;
+    int64_t info_ld;  // 0: parts row-major [N][4]; > 0: column-major [4][info_ld]
     float* final_obs;
     uint32_t* err;
     int use_bulk;
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(ORGYM_TILE, NV_STEP_MINB) nv_step_kernel(const
             A.truncated[e] = trunc ? 1 : 0;
             if (A.info_demand) A.info_demand[e] = d;
             if (A.info_parts)
-                for (int z = 0; z < 4; z++) A.info_parts[e * 4 + z] = parts[z];
+                for (int z = 0; z < 4; z++) A.info_parts[A.info_ld ? z * A.info_ld + e : e * 4 + z] = parts[z];
         }
     }
     float* g = A.obs + (size_t)e0 * W;
@@ -641,6 +642,8 @@ extern "C" int orgym_newsvendor_step(orgym_handle_t h, void* state_dev, const fl
     if (info) {
         A.info_demand = info->demand_dev;
         A.info_parts = info->parts_dev;
+        ORGYM_REQUIRE(info->info_ld == 0 || info->info_ld >= H->base.num_envs, "info_ld must be 0 (row-major) or >= num_envs");
+        A.info_ld = info->info_ld;
         A.final_obs = info->final_obs_dev;
     }
     A.err = H->base.err_dev;

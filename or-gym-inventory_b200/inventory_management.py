@@ -181,9 +181,11 @@ class InvManagementMasterEnv(BatchedEnv):
         self._info_t = {}
         if self.info_level >= 1:
             self._info_t = dict(demand_realized=torch.zeros(N, dtype=torch.int64, device=dev),
-                                sales=torch.zeros((N, m), dtype=torch.int64, device=dev),
-                                unfulfilled=torch.zeros((N, m), dtype=torch.int64, device=dev),
+                                # [N, m] tensors over column-major storage: coalesced stores in the step kernel
+                                sales=torch.zeros((m, N), dtype=torch.int64, device=dev).t(),
+                                unfulfilled=torch.zeros((m, N), dtype=torch.int64, device=dev).t(),
                                 period_profit=torch.zeros(N, dtype=torch.float64, device=dev))
+            self._info.info_ld = N
             self._info.demand = self._info_t["demand_realized"].data_ptr()
             self._info.sales = self._info_t["sales"].data_ptr()
             self._info.unfulfilled = self._info_t["unfulfilled"].data_ptr()

@@ -370,10 +370,13 @@ class NetInvMgmtMasterEnv(BatchedEnv):
         self._info = _capi.NetInfo()
         self._info_t = {}
         if self.info_level >= 1:
-            self._info_t = dict(demand=torch.zeros((N, M), dtype=torch.float64, device=dev),
-                                sales=torch.zeros((N, E + M), dtype=torch.float64, device=dev),
-                                profit_node=torch.zeros((N, J), dtype=torch.float64, device=dev),
+            # [N, dim] tensors backed by column-major storage (a transposed view): the kernels then write every info
+            # value with coalesced stores; indexing / .cpu() / .numpy() behave as for any [N, dim] tensor
+            self._info_t = dict(demand=torch.zeros((M, N), dtype=torch.float64, device=dev).t(),
+                                sales=torch.zeros((E + M, N), dtype=torch.float64, device=dev).t(),
+                                profit_node=torch.zeros((J, N), dtype=torch.float64, device=dev).t(),
                                 profit_period_undiscounted=torch.zeros(N, dtype=torch.float64, device=dev))
+            self._info.info_ld = N
             self._info.demand = self._info_t["demand"].data_ptr()
             self._info.sales = self._info_t["sales"].data_ptr()
             self._info.profit = self._info_t["profit_node"].data_ptr()

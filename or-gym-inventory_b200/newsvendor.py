@@ -86,7 +86,8 @@ class NewsvendorEnv(BatchedEnv):
         self._info_t = {}
         if self.info_level >= 1:
             self._info_t = dict(demand=torch.zeros(N, dtype=torch.int64, device=dev),
-                                parts=torch.zeros((N, 4), dtype=torch.float64, device=dev))
+                                parts=torch.zeros((4, N), dtype=torch.float64, device=dev).t())  # column-major storage
+            self._info.info_ld = N
             self._info.demand = self._info_t["demand"].data_ptr()
             self._info.parts = self._info_t["parts"].data_ptr()
         if autoreset_mode == "same_step":

@@ -74,3 +74,42 @@ def test_newsvendor_and_network_accept_numpy():
     r2 = net.step(np.full((N, 11), 40.0, np.float32), demand=np.full((N, 1), 20.0))[1].cpu().numpy().copy()
     assert np.array_equal(r1, r2)
     nv.close(); net.close()
+
+
+@pytest.mark.parametrize("family", ["serial", "newsvendor", "network", "network_generic"])
+def test_info_tensor_layouts_agree(family):
+    """The C ABI writes the two-dimensional info tensors row-major (info_ld = 0) or column-major (info_ld >= N, what the
+    Python host uses for coalesced stores); both must hold the same values."""
+    torch = _torch()
+    N = 333                                   # ragged: not a multiple of the tile size
+    rng = np.random.default_rng(5)
+
+    def make():
+        if family == "serial":
+            return pkg.InvManagementLostSalesEnv(num_envs=N, device="cuda:0"), rng.integers(0, 120, size=(N, 3)), ("sales", "unfulfilled")
+        if family == "newsvendor":
+            return pkg.NewsvendorEnv(num_envs=N, device="cuda:0"), (rng.random((N, 1)) * 100).astype(np.float32), ("parts",)
+        env = pkg.NetInvMgmtLostSalesEnv(num_envs=N, device="cuda:0", specialise=(family == "network"))
+        return env, (rng.random((N, len(env.reorder_links))) * 60).astype(np.float32), ("demand", "sales", "profit_node")
+
+    rng = np.random.default_rng(5)
+    env_c, acts, names = make()
+    rng = np.random.default_rng(5)
+    env_r, _, _ = make()
+    field = {"sales": "sales", "unfulfilled": "unfulfilled", "parts": "parts", "demand": "demand", "profit_node": "profit"}
+    for nm in names:                          # give env_r plain row-major buffers
+        t = torch.full(tuple(env_r._info_t[nm].shape), -7, dtype=env_r._info_t[nm].dtype, device="cuda")
+        assert t.is_contiguous() and env_c._info_t[nm].stride(0) == 1      # column-major storage behind [N, dim]
+        env_r._info_t[nm] = t
+        setattr(env_r._info, field[nm], t.data_ptr())
+    env_r._info.info_ld = 0
+    env_c.reset(seed=21)
+    env_r.reset(seed=21)
+    for _ in range(3):
+        env_c.step(acts)
+        env_r.step(acts)
+        for nm in names:
+            a, b = env_c._info_t[nm].cpu().numpy(), env_r._info_t[nm].cpu().numpy()
+            assert a.shape == b.shape and np.array_equal(a, b), nm
+    env_c.close()
+    env_r.close()

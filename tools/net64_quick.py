@@ -5,7 +5,7 @@ import or_gym_inventory_b200 as pkg
 G = pkg.synthetic_graph(64)
 N = int(os.environ.get('N64', 1 << 17))
 t0 = time.time()
-env = pkg.NetInvMgmtMasterEnv(graph=G, backlog=False, num_envs=N, device="cuda:0")
+env = pkg.NetInvMgmtMasterEnv(graph=G, backlog=False, num_envs=N, device="cuda:0", info_level=int(os.environ.get("INFO", 1)))
 print("create s", round(time.time() - t0, 1), "E", len(env.reorder_links), "J", len(env.main_nodes), "M", len(env.retail_links), "obs", env.obs_dim)
 E = len(env.reorder_links)
 a = torch.rand((N, E), device="cuda") * 100
