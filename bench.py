@@ -390,15 +390,15 @@ def main():
         torch.cuda.synchronize()
         sms = s0.elapsed_time(s1) / 20
         ab = ALG_BYTES_STEP_API[args.workload]
-        ach = N * ab / (sms * 1e-3) / 1e9
-        line["roofline_step_api"] = {"kernel": sk, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                                     "frac": ach / hbm_peak,
-                                     "traffic": (counts.get(args.workload + "_step", {}).get("dram_bytes_per_env_step") or 0) * N or None,
-                                     "kernel_ms": sms, "env_steps_per_s": N / (sms * 1e-3),
-                                     "algorithmic_bytes_per_env_step": ab, "instances": N, "peak_source": peak_src,
-                                     "note": "info tensors (demand/sales/unfulfilled/profit) are written too; they are "
-                                             "not part of the algorithmic byte count"}
-        # the same kernel without the optional info tensors (they are not part of the algorithmic byte count)
+        # optional info tensors written on top of the algorithmic bytes (Python host default, info_level=1)
+        if args.workload == "invmgmt":
+            ib = 8 + 8 * 4 + 8 * 4 + 8                      # demand, sales[m], unfulfilled[m], period profit
+        elif args.workload == "newsvendor":
+            ib = 8 + 8 * 4                                  # demand, four reward parts
+        else:
+            nE, nM, nJ = len(env.reorder_links), len(env.retail_links), len(env.main_nodes)
+            ib = 8 * (nM + (nE + nM) + nJ + 1)              # demand, sales, node profit, period profit
+        # the same kernel without the optional info tensors = exactly the algorithmic bytes of SURVEY.md §8d
         env.close()
         del env
         torch.cuda.empty_cache()
@@ -415,8 +415,20 @@ def main():
         s1.record()
         torch.cuda.synchronize()
         sms0 = s0.elapsed_time(s1) / 20
-        line["roofline_step_api"]["info_off"] = {"kernel_ms": sms0, "achieved": N * ab / (sms0 * 1e-3) / 1e9,
-                                                 "frac": N * ab / (sms0 * 1e-3) / 1e9 / hbm_peak}
+        ach = N * ab / (sms0 * 1e-3) / 1e9
+        ach_i = N * (ab + ib) / (sms * 1e-3) / 1e9
+        line["roofline_step_api"] = {"kernel": sk, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": ach / hbm_peak,
+                                     "traffic": (counts.get(args.workload + "_step", {}).get("dram_bytes_per_env_step") or 0) * N or None,
+                                     "kernel_ms": sms0, "env_steps_per_s": N / (sms0 * 1e-3),
+                                     "algorithmic_bytes_per_env_step": ab, "instances": N, "peak_source": peak_src,
+                                     "note": "env built with info_level=0: the kernel moves exactly the algorithmic bytes "
+                                             "(actions, observation, reward, flags, state read+write); `traffic` is the "
+                                             "ncu DRAM byte count of the capture WITH info tensors",
+                                     "with_info_tensors": {"kernel_ms": sms, "bytes_per_env_step": ab + ib,
+                                                           "achieved": ach_i, "frac": ach_i / hbm_peak,
+                                                           "env_steps_per_s": N / (sms * 1e-3),
+                                                           "frac_counting_algorithmic_bytes_only": N * ab / (sms * 1e-3) / 1e9 / hbm_peak}}
         env0.close()
         del a, env0
         # ---- the host-driven loop (a policy on the CPU: numpy actions in, observations out every period) ------------
