@@ -217,6 +217,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
+    host_cores = 0
+    if world > 1:      # each rank streams results to pinned host memory: keep them on the GPU's own NUMA node
+        from or_gym_inventory_b200.sharding import bind_host_to_gpu
+        host_cores = bind_host_to_gpu(local)
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -280,6 +284,7 @@ def main():
             "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": W["name"], "instances_per_gpu": N, "periods": T, "seed": W["seed"],
                        "env_steps_per_bench_step": N * T * world,
+                       "host_cores_per_rank": host_cores or None,
                        "l2": "no input tensors (on-device policy + Philox demand); the per-episode outputs written "
                              f"every step ({N * 40 / 1e6:.0f} MB) exceed the 126 MB L2"},
             "gpu_launches": 2 * args.steps,

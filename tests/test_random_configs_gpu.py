@@ -164,3 +164,73 @@ def test_netinv_random_graph(case, mode, monkeypatch):
         assert np.array_equal(o["obs"][-1], last[e])
         assert np.array_equal(o["X"][-1], X[e].cpu().numpy()) and np.array_equal(o["Y"][-1], Y[e].cpu().numpy())
     env.close()
+
+
+def test_invmgmt_maximum_sizes():
+    """The build limits of include/orgym_b200.h: 16 stages, lead times up to 64 (and 0), a horizon longer than the
+    longest lead time; observation rows of 16*65 int64 do not fit a shared-memory tile."""
+    from oracle import oracle
+    torch = _torch()
+    rng = np.random.default_rng(77)
+    n, T, N = 16, 70, 130
+    L = rng.integers(0, 65, n)
+    L[0], L[1], L[2] = 64, 0, 63
+    cfg = dict(periods=T, I0=rng.integers(0, 200, n).tolist(), p=31.5,
+               r=np.sort(rng.uniform(0.5, 30, n + 1))[::-1].round(3).tolist(), k=rng.uniform(0, 1, n + 1).round(3).tolist(),
+               h=rng.uniform(0, 0.5, n).round(3).tolist(), c=rng.integers(1, 300, n).tolist(), L=L.tolist(),
+               dist_param={"mu": 33.0}, alpha=0.97)
+    for backlog, wide in ((True, False), (False, True)):
+        cls = pkg.InvManagementBacklogEnv if backlog else pkg.InvManagementLostSalesEnv
+        env = cls(num_envs=N, device="cuda:0", wide_state=wide, autoreset_mode="disabled", **cfg)
+        assert env.observation_space.shape[-1] == n * 65
+        acts = rng.integers(0, 320, size=(N, T, n))
+        dem = rng.poisson(33.0, size=(N, T)).astype(np.int64)
+        obs, _ = env.reset(seed=1)
+        rew = np.zeros((N, T))
+        mid = None
+        for t in range(T):
+            obs, r, _, trunc, _ = env.step(torch.from_numpy(acts[:, t]).cuda(), demand=torch.from_numpy(dem[:, t]).cuda())
+            rew[:, t] = r.cpu().numpy()
+            if t == 40:
+                mid = obs.cpu().numpy().copy()
+        last = obs.cpu().numpy()
+        out = env.rollout("actions", actions=acts, demand=dem, want=("reward_traj",))
+        assert np.array_equal(out["reward_traj"].cpu().numpy(), rew)
+        for e in (0, 1, 64, 127, 128, 129):
+            o = oracle.invmgmt_episode(env.params, actions=acts[e], demand=dem[e])
+            assert np.array_equal(o["reward"], rew[e])
+            assert np.array_equal(o["obs"][41], mid[e]) and np.array_equal(o["obs"][-1], last[e])
+        assert env.errors() == 0
+        env.close()
+    with pytest.raises(Exception):
+        pkg.InvManagementBacklogEnv(num_envs=4, device="cuda:0", I0=[10] * 17, r=[1.0] * 18, k=[0.1] * 18, h=[0.1] * 17,
+                                    c=[10] * 17, L=[1] * 17)
+    with pytest.raises(Exception):
+        pkg.InvManagementBacklogEnv(num_envs=4, device="cuda:0", L=[65, 5, 10])
+
+
+def test_newsvendor_maximum_lead_time():
+    from oracle import oracle
+    torch = _torch()
+    rng = np.random.default_rng(78)
+    N, Lmax = 200, 64
+    env = pkg.NewsvendorEnv(num_envs=N, device="cuda:0", lead_time=Lmax, step_limit=80, autoreset_mode="disabled")
+    env.reset(seed=4)
+    par = env.export_params().cpu().numpy()
+    T = env.step_limit
+    acts = (rng.random((N, T)) * 60).astype(np.float32)
+    dem = rng.poisson(30.0, size=(N, T)).astype(np.int64)
+    rew = np.zeros((N, T))
+    for t in range(T):
+        obs, r, _, _, _ = env.step(torch.from_numpy(acts[:, t]).cuda(), demand=torch.from_numpy(dem[:, t]).cuda())
+        rew[:, t] = r.cpu().numpy()
+    last = obs.cpu().numpy()
+    out = env.rollout("actions", actions=acts, demand=dem, fixed_params=par, want=("reward_traj", "final_obs"))
+    assert np.array_equal(out["reward_traj"].cpu().numpy(), rew)
+    assert np.array_equal(out["final_obs"].cpu().numpy(), last)
+    for e in (0, 99, 199):
+        o = oracle.newsvendor_episode(env.params, actions=acts[e], demand=dem[e], fixed=par[e])
+        assert np.array_equal(o["reward"], rew[e]) and np.array_equal(o["obs"][-1], last[e])
+    env.close()
+    with pytest.raises(Exception):
+        pkg.NewsvendorEnv(num_envs=4, device="cuda:0", lead_time=65)

@@ -58,3 +58,13 @@ def test_summary_allreduce_gloo_world2():
     assert d["episodes"] == 1001 and np.isclose(d["TotalReward_mean"], ret.mean(), atol=1e-9)
     assert np.isclose(d["TotalReward_std"], ret.std(), rtol=1e-9) and d["AvgServiceLevel"] == 0.75
     assert d["AvgEndingInv_mean"] == 2.0
+
+
+def test_bind_host_to_gpu_is_a_no_op_without_nvml():
+    import os
+    from or_gym_inventory_b200.sharding import bind_host_to_gpu
+    before = os.sched_getaffinity(0)
+    n = bind_host_to_gpu(0)
+    assert n == 0 or n == len(os.sched_getaffinity(0))
+    if n == 0:
+        assert os.sched_getaffinity(0) == before
