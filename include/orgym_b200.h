@@ -50,7 +50,10 @@ extern "C" {
 #define ORGYM_E_CUDA (-2)        /* CUDA runtime error, or no device */
 #define ORGYM_E_UNSUPPORTED (-3) /* valid for the reference but outside this build's limits */
 
-/* compile-time limits of this build */
+/* compile-time limits of this build.  Every configuration inside them runs; the fast paths additionally need the
+ * per-CTA working set to fit in shared memory -- serial env step: 128 x obs_dim x (4|8) B observation tile (else the
+ * rows are written directly); serial env rollout: 128 x sum(max(L_i,1)) x (4|8) B x (1|2) rings (else a device
+ * scratch buffer is allocated on first use); network env: specialised kernels up to 128 reorder links. */
 #define ORGYM_INV_MAX_STAGES 16 /* inventory-holding stages n = m-1 */
 #define ORGYM_INV_MAX_LEAD 64
 #define ORGYM_NV_MAX_LEAD 64

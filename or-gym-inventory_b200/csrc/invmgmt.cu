@@ -15,6 +15,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include <type_traits>
 
 #define MAXN ORGYM_INV_MAX_STAGES
 
@@ -41,6 +42,8 @@ struct InvHandle {
     const void* hint_state;
     int hint_t;
     long long user_dmax;  // largest value of a user_D trace (0 for sampled demand)
+    void* ring_scratch = nullptr;  // rollout rings that do not fit in shared memory (allocated on first use)
+    size_t ring_scratch_bytes = 0;
 };
 
 // ---- state layout: field[slot][env], env stride npad -------------------------------------------------------
@@ -91,6 +94,7 @@ struct InvStepArgs {
     int64_t* info_sales;
     int64_t* info_unf;
     double* info_profit;
+    int direct_obs;  // observation rows too long for a shared-memory tile: write them straight to global memory
     int64_t info_ld;  // 0: sales / unfulfilled row-major [N][m]; > 0: column-major [m][info_ld]
     int64_t* final_obs;
     uint32_t* err;
@@ -246,13 +250,28 @@ __device__ __forceinline__ void obs_tile_store(int64_t* __restrict__ g, const S*
     }
 }
 
+// One env's observation row: normally a row of the shared-memory staging tile (stored coalesced afterwards); for rows
+// that do not fit in shared memory (e.g. 16 stages x lead time 64 = 1040 entries) the row in global memory itself.
+template <typename S>
+struct ObsRow {
+    S* s;
+    int64_t* g;  // non-null: direct mode
+    __device__ __forceinline__ void put(int k, S v) const {
+        if (g)
+            g[k] = (int64_t)v;
+        else
+            s[k] = v;
+    }
+    __device__ __forceinline__ int64_t get(int k) const { return g ? g[k] : (int64_t)s[k]; }
+};
+
 // Lead-time ring slots and the action window of one env for period t (the second group of loads of a step).
 // arr[i] = R[t - L_i] (ring slot t % L_i); window positions 0..k-2 of the observation at t+1 go straight into the
 // env's row of the staging tile (position k-1 is the current period's request, filled in by the caller).
 // All loads of up to CH periods are issued before the first store so that their latencies overlap.
 template <int NS, bool EXACT, typename S, int CH>
 __device__ __forceinline__ void inv_load_rings(const InvDev& P, const InvState<S>& st, int64_t e, int t, int n,
-                                               S (&arr)[NS], S* orow) {
+                                               S (&arr)[NS], const ObsRow<S>& orow) {
     const int Lm = P.lt_max;
     const int tn = t + 1;
     const int k = tn < Lm ? tn : Lm;  // window length at t+1 (:378)
@@ -284,7 +303,7 @@ __device__ __forceinline__ void inv_load_rings(const InvDev& P, const InvState<S
                 if (q < Lm && q != k - 1) {
 #pragma unroll
                     for (int i = 0; i < NS; i++)
-                        if (EXACT || i < n) orow[n + q * n + i] = v[u][i];
+                        if (EXACT || i < n) orow.put(n + q * n + i, v[u][i]);
                 }
             }
         }
@@ -308,7 +327,7 @@ __global__ void __launch_bounds__(ORGYM_TILE, (NS <= 4 && sizeof(S) == 4) ? ORGY
     const bool bulk_in = A.use_bulk && full;
     // shared: obs tile (S) | action tile (8 B / element) | mbarrier | alias table
     S* obs_tile = (S*)smem;
-    size_t off = ((size_t)ORGYM_TILE * ostride * sizeof(S) + 15) & ~(size_t)15;
+    size_t off = (!EXACT && A.direct_obs) ? 0 : (((size_t)ORGYM_TILE * ostride * sizeof(S) + 15) & ~(size_t)15);
     unsigned char* act_tile = smem + off;
     off += (size_t)ORGYM_TILE * n * 8;
     uint64_t* bar = (uint64_t*)(smem + off);
@@ -337,7 +356,9 @@ __global__ void __launch_bounds__(ORGYM_TILE, (NS <= 4 && sizeof(S) == 4) ? ORGY
     uint32_t episode = 0;
     uint64_t key = 0;
     bool do_step = valid;
-    S* orow = obs_tile + tid * ostride;
+    // only the generic instantiation carries the direct mode (the specialised ones keep a compile-time null pointer)
+    const bool direct = !EXACT && A.direct_obs;
+    const ObsRow<S> orow{obs_tile + tid * ostride, direct ? A.obs + e * P.obs_dim : nullptr};
     S arr[NS];
     const int Lm = P.lt_max;
     // The ring / window addresses depend on the env's period, which itself has to be loaded: two dependent round trips
@@ -363,14 +384,15 @@ __global__ void __launch_bounds__(ORGYM_TILE, (NS <= 4 && sizeof(S) == 4) ? ORGY
             if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {
                 inv_reset_env(P, st, e);
                 st.episode[e] = episode + 1;
-                for (int k = 0; k < P.obs_dim; k++) orow[k] = k < n ? (S)P.I0[k] : (S)0;
+                for (int k = 0; k < P.obs_dim; k++) orow.put(k, k < n ? (S)P.I0[k] : (S)0);
                 A.reward[e] = 0.0;
                 A.terminated[e] = 0;
                 A.truncated[e] = 0;
             } else {  // reference: IndexError on R[t] (inventory_management.py:267)
                 atomicOr(A.err, ORGYM_ERR_STEP_PAST_END);
                 const int64_t* old = A.obs + e * P.obs_dim;
-                for (int k = 0; k < P.obs_dim; k++) orow[k] = (S)old[k];
+                if (!direct)
+                    for (int k = 0; k < P.obs_dim; k++) orow.put(k, (S)old[k]);
                 A.reward[e] = 0.0;
                 A.terminated[e] = 0;
                 A.truncated[e] = 1;
@@ -432,8 +454,8 @@ __global__ void __launch_bounds__(ORGYM_TILE, (NS <= 4 && sizeof(S) == 4) ? ORGY
 #pragma unroll
         for (int i = 0; i < NS; i++)
             if (EXACT || i < n) {
-                orow[i] = I[i];
-                if (Lm > 0) orow[n + (k - 1) * n + i] = req[i];
+                orow.put(i, I[i]);
+                if (Lm > 0) orow.put(n + (k - 1) * n + i, req[i]);
             }
         if (!reset_now) {
             const int aslot = Lm > 0 ? mod_small(t, Lm, P.Lm_magic) : 0;
@@ -452,11 +474,11 @@ __global__ void __launch_bounds__(ORGYM_TILE, (NS <= 4 && sizeof(S) == 4) ? ORGY
             // SAME_STEP autoreset: the terminal observation goes to final_obs, the env restarts immediately
             if (A.final_obs) {
                 int64_t* fo = A.final_obs + e * P.obs_dim;
-                for (int q = 0; q < P.obs_dim; q++) fo[q] = (int64_t)orow[q];
+                for (int q = 0; q < P.obs_dim; q++) fo[q] = orow.get(q);
             }
             inv_reset_env(P, st, e);
             st.episode[e] = episode + 1;
-            for (int q = 0; q < P.obs_dim; q++) orow[q] = q < n ? (S)P.I0[q] : (S)0;
+            for (int q = 0; q < P.obs_dim; q++) orow.put(q, q < n ? (S)P.I0[q] : (S)0);
         }
         A.reward[e] = reward;
         A.terminated[e] = 0;  // :349
@@ -505,7 +527,7 @@ __global__ void __launch_bounds__(ORGYM_TILE, (NS <= 4 && sizeof(S) == 4) ? ORGY
             }
         }
     }
-    obs_tile_store<S>(A.obs + (size_t)e0 * P.obs_dim, obs_tile, P.obs_dim, ostride, nvalid, bulk_out);
+    if (!direct) obs_tile_store<S>(A.obs + (size_t)e0 * P.obs_dim, obs_tile, P.obs_dim, ostride, nvalid, bulk_out);
 }
 
 // ---- export -----------------------------------------------------------------------------------------------------
@@ -543,6 +565,8 @@ struct InvRolloutArgs {
     int64_t* final_B;
     int32_t* stats32;
     double* partials;  // [gridDim.x][8]
+    void* ring_scratch;    // non-null: the rings do not fit in shared memory and live here as [slot][ring_stride]
+    int64_t ring_stride;   // >= round_up(N, ROLL_THREADS)
 };
 
 #define ROLL_THREADS 128
@@ -561,25 +585,31 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
     // reads and writes a dummy slot whose value is never used).
     uint2* tab = (uint2*)smem;
     const int K = (P.dem.kind == ORGYM_DIST_USER) ? 0 : (1 << P.dem.log2k);
-    S* rring = (S*)(smem + (size_t)K * 8);
-    S* aring = rring + (size_t)A.rslots * ROLL_THREADS;
+    // Rings too long for shared memory (sum of lead times in the hundreds) fall back to a global scratch buffer with
+    // the same [slot][lane] indexing; only the generic instantiation carries that mode.
+    const bool gring = !EXACT && A.ring_scratch != nullptr;
+    typedef typename std::conditional<EXACT, int, long long>::type RI;  // ring offsets (elements)
+    const RI rstride = gring ? (RI)A.ring_stride : (RI)ROLL_THREADS;
+    const RI lane = gring ? (RI)e : (RI)tid;
+    S* rring = gring ? (S*)A.ring_scratch : (S*)(smem + (size_t)K * 8);
+    S* aring = rring + (size_t)A.rslots * (size_t)rstride;
     for (int i = tid; i < K; i += ROLL_THREADS) tab[i] = P.dem.table[i];
     for (int k = 0; k < A.rslots; k++) {
-        rring[k * ROLL_THREADS + tid] = 0;
-        if (need_aring) aring[k * ROLL_THREADS + tid] = 0;
+        rring[k * rstride + lane] = 0;
+        if (need_aring) aring[k * rstride + lane] = 0;
     }
     __syncthreads();
 
     const uint64_t key = A.seed + (uint64_t)(A.env_offset + e);
     S I[NS], B[NS + 1], psum[NS], lmask[NS];
-    int rbase[NS], rpos[NS], rlen[NS];  // ring base / position / length in elements of the [slot][thread] layout
+    RI rbase[NS], rpos[NS], rlen[NS];  // ring base / position / length in elements of the [slot][lane] layout
 #pragma unroll
     for (int i = 0; i < NS; i++) {
         I[i] = (EXACT || i < n) ? (S)P.I0[i] : (S)0;
         psum[i] = 0;
-        rbase[i] = A.rroff[i] * ROLL_THREADS + tid;
+        rbase[i] = A.rroff[i] * rstride + lane;
         rpos[i] = 0;
-        rlen[i] = (P.L[i] > 0 ? P.L[i] : 1) * ROLL_THREADS;
+        rlen[i] = (P.L[i] > 0 ? P.L[i] : 1) * rstride;
         lmask[i] = P.L[i] > 0 ? (S)-1 : (S)0;
     }
 #pragma unroll
@@ -665,14 +695,14 @@ __global__ void __launch_bounds__(ROLL_THREADS) inv_rollout_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < NS; i++)
             if (EXACT || i < n) {
-                const int slot = rbase[i] + rpos[i];
+                const RI slot = rbase[i] + rpos[i];
                 rring[slot] = Rf[i];
                 if (need_aring) {
                     S old = aring[slot];
                     aring[slot] = req[i];
                     psum[i] = (psum[i] + req[i] - old) & lmask[i];  // stays 0 for a stage without lead time
                 }
-                const int np1 = rpos[i] + ROLL_THREADS;
+                const RI np1 = rpos[i] + rstride;
                 rpos[i] = np1 == rlen[i] ? 0 : np1;
             }
     }
@@ -732,7 +762,7 @@ static void launch_step(const InvHandle* H, const InvStepArgs& A, size_t smem, c
         cudaFuncSetAttribute(inv_step_kernel<NSV, true, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         inv_step_kernel<NSV, true, S><<<grid, ORGYM_TILE, smem, s>>>(P, A);                                          \
         break;
-    switch (P.n) {
+    switch (A.direct_obs ? 0 : P.n) {
         STEP_CASE(1) STEP_CASE(2) STEP_CASE(3) STEP_CASE(4) STEP_CASE(5) STEP_CASE(6) STEP_CASE(7) STEP_CASE(8)
         default:
             cudaFuncSetAttribute(inv_step_kernel<MAXN, false, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -750,7 +780,7 @@ static void launch_rollout(const InvHandle* H, const InvRolloutArgs& A, size_t s
         cudaFuncSetAttribute(inv_rollout_kernel<NSV, true, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         inv_rollout_kernel<NSV, true, S><<<grid, ROLL_THREADS, smem, s>>>(P, A);                                        \
         break;
-    switch (P.n) {
+    switch (A.ring_scratch ? 0 : P.n) {
         ROLL_CASE(1) ROLL_CASE(2) ROLL_CASE(3) ROLL_CASE(4) ROLL_CASE(5) ROLL_CASE(6) ROLL_CASE(7) ROLL_CASE(8)
         default:
             cudaFuncSetAttribute(inv_rollout_kernel<MAXN, false, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -880,6 +910,7 @@ extern "C" int orgym_invmgmt_destroy(orgym_handle_t h) {
     {
         DeviceGuard g(H->base.device);
         for (void* p : H->allocs) cudaFree(p);
+        if (H->ring_scratch) cudaFree(H->ring_scratch);
     }
     orgym_handle_base_free(&H->base);
     delete H;
@@ -975,9 +1006,9 @@ extern "C" int orgym_invmgmt_step(orgym_handle_t h, void* state_dev, const void*
     int ostride = (P.obs_dim & 1) ? P.obs_dim : P.obs_dim + 1;
     size_t smem = (((size_t)ORGYM_TILE * ostride * (H->wide ? 8 : 4) + 15) & ~(size_t)15) + (size_t)ORGYM_TILE * P.n * 8 + 16 +
                   (P.dem.kind == ORGYM_DIST_USER ? 0 : (size_t(8) << P.dem.log2k));
-    if (smem > 220 * 1024) {
-        orgym_set_error("observation tile of %zu bytes does not fit in shared memory (obs_dim=%d)", smem, P.obs_dim);
-        return ORGYM_E_UNSUPPORTED;
+    if (smem > 200 * 1024) {  // rows too long to stage: the generic kernel writes them directly (correct, not fast)
+        A.direct_obs = 1;
+        smem = (size_t)ORGYM_TILE * P.n * 8 + 16 + (P.dem.kind == ORGYM_DIST_USER ? 0 : (size_t(8) << P.dem.log2k));
     }
     if (H->wide)
         launch_step<long long>(H, A, smem, (cudaStream_t)stream);
@@ -1065,9 +1096,24 @@ extern "C" int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t en
     size_t ring = (size_t)A.rslots * ROLL_THREADS * (wide ? 8 : 4);
     size_t smem = (P.dem.kind == ORGYM_DIST_USER ? 0 : (size_t(8) << P.dem.log2k)) +
                   ring * (in->policy == ORGYM_POLICY_BASE_STOCK ? 2 : 1);
-    if (smem > 220 * 1024) {
-        orgym_set_error("lead-time rings of %zu bytes do not fit in shared memory (sum of lead times = %d)", smem, P.sumL);
-        return ORGYM_E_UNSUPPORTED;
+    if (smem > 200 * 1024) {  // rings too long for shared memory: global scratch, generic kernel (correct, not fast)
+        const int64_t stride = round_up(A.N, ROLL_THREADS);
+        const size_t need = (size_t)A.rslots * (size_t)stride * 8 * 2;
+        if (H->ring_scratch_bytes < need) {
+            if (H->ring_scratch) cudaFree(H->ring_scratch);
+            H->ring_scratch = nullptr;
+            H->ring_scratch_bytes = 0;
+            if (cudaMalloc(&H->ring_scratch, need) != cudaSuccess) {
+                cudaGetLastError();
+                orgym_set_error("lead-time rings (sum of lead times = %d) need a %zu-byte device scratch buffer: allocation failed",
+                                P.sumL, need);
+                return ORGYM_E_CUDA;
+            }
+            H->ring_scratch_bytes = need;
+        }
+        A.ring_scratch = H->ring_scratch;
+        A.ring_stride = stride;
+        smem = P.dem.kind == ORGYM_DIST_USER ? 0 : (size_t(8) << P.dem.log2k);
     }
     if (wide)
         launch_rollout<long long>(H, A, smem, (cudaStream_t)stream);

@@ -200,6 +200,14 @@ def test_invmgmt_maximum_sizes():
             o = oracle.invmgmt_episode(env.params, actions=acts[e], demand=dem[e])
             assert np.array_equal(o["reward"], rew[e])
             assert np.array_equal(o["obs"][41], mid[e]) and np.array_equal(o["obs"][-1], last[e])
+        # on-device base-stock: both ring sets (fulfilled orders, requested orders) exceed shared memory here
+        ob = env.rollout("base_stock", demand=dem, safety_factor=1.25, want=("ep_return", "final_I"))
+        for e in (0, 64, 129):
+            o = oracle.invmgmt_episode(env.params, policy="base_stock", demand=dem[e], safety_factor=1.25)
+            assert ob["ep_return"][e].item() == seq_sum(o["reward"])
+            assert np.array_equal(o["I"][-1], ob["final_I"][e].cpu().numpy())
+        sampled = env.rollout("base_stock", seed=3, want=("ep_return", "summary"))
+        assert np.isfinite(sampled["ep_return"].cpu().numpy()).all() and sampled["summary"][0].item() == N
         assert env.errors() == 0
         env.close()
     with pytest.raises(Exception):
