@@ -242,3 +242,38 @@ def test_newsvendor_maximum_lead_time():
     env.close()
     with pytest.raises(Exception):
         pkg.NewsvendorEnv(num_envs=4, device="cuda:0", lead_time=65)
+
+
+def test_netinv_maximum_sizes(monkeypatch):
+    """Network env at the build limits: 64 main nodes, 128 reorder links, 30 retail links, lead times 0..64, 70 periods
+    (observation rows of ~1000 float32) -- through the generic kernel (the specialised kernels are covered by the
+    64-node test of test_netinv_gpu.py)."""
+    from oracle import oracle
+    torch = _torch()
+    monkeypatch.setenv("ORGYM_NET_JIT", "0")
+    g = pkg.synthetic_graph(1, layers=(16, 20, 22, 22, 20))
+    links = [e for e in g.edges() if "L" in g.edges[e]]
+    for k, e in enumerate(links[:6]):
+        g.edges[e]["L"] = [64, 63, 0, 1, 64, 33][k]
+    T, N = 70, 70
+    rng = np.random.default_rng(9)
+    for backlog in (True, False):
+        env = pkg.NetInvMgmtMasterEnv(graph=g, num_periods=T, backlog=backlog, num_envs=N, device="cuda:0",
+                                      autoreset_mode="disabled")
+        P = env.params
+        J, E, M = len(P.main_nodes), len(P.reorder_links), len(P.retail_links)
+        assert (J, E) == (64, 128) and 16 <= M <= 32 and not env.specialised
+        acts = (rng.random((N, T, E)) * 90).astype(np.float32)
+        dem = rng.poisson(20, size=(N, T, M)).astype(np.float64)
+        obs, _ = env.reset(seed=2)
+        rew = np.zeros((N, T))
+        for t in range(T):
+            obs, r, _, _, _ = env.step(torch.from_numpy(acts[:, t]).cuda(), demand=torch.from_numpy(dem[:, t]).cuda())
+            rew[:, t] = r.cpu().numpy()
+        last = obs.cpu().numpy()
+        out = env.rollout("actions", actions=acts, demand=dem, want=("reward_traj",))
+        assert np.array_equal(out["reward_traj"].cpu().numpy(), rew)
+        for e in (0, 33, 69):
+            o = oracle.netinv_episode(P, actions=acts[e], demand=dem[e])
+            assert np.array_equal(o["reward"], rew[e]) and np.array_equal(o["obs"][-1], last[e])
+        env.close()
