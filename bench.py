@@ -305,29 +305,40 @@ def main():
     # ---- e2e (every rank): the public evaluate() API -- per-episode results land in pinned host memory every step;
     # the copy of step k overlaps the kernel of step k+1 (two buffer sets, second stream); host waits for every result
     if not args.no_extras:
-        e2e_want = ("ep_return", "stats32", "summary") if args.workload == "invmgmt" else want
         pol = {"invmgmt": ("base_stock", dict(safety_factor=1.0)), "newsvendor": ("classic", {}),
                "netinv": ("constant", dict(order_fraction=0.1))}[args.workload]
         reps = max(4, min(args.steps, 20))
-        d2h = 0
-        for res in env.evaluate(pol[0], episodes=3, seed=W["seed"], first_episode=300, want=e2e_want, **pol[1]):
-            d2h = sum(v.numel() * v.element_size() for v in res.values())
-        barrier()
-        t0 = time.perf_counter()
-        chk = 0.0
-        for res in env.evaluate(pol[0], episodes=reps, seed=W["seed"], first_episode=400, want=e2e_want, **pol[1]):
-            chk += float(res["summary"][0])          # touch the host copy
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        assert chk == float(N) * reps
-        line["e2e"] = {"value": float(N) * T * reps * world / float(dt.item()), "unit": "env-steps/s",
-                       "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h * world, "steps": reps,
+
+        def run_e2e(e2e_want, first):
+            d2h = 0
+            for res in env.evaluate(pol[0], episodes=3, seed=W["seed"], first_episode=first, want=e2e_want, **pol[1]):
+                d2h = sum(v.numel() * v.element_size() for v in res.values())
+            barrier()
+            t0 = time.perf_counter()
+            chk = 0.0
+            for res in env.evaluate(pol[0], episodes=reps, seed=W["seed"], first_episode=first + 100, want=e2e_want, **pol[1]):
+                chk += float(res["summary"][0]) + float(res["ep_return"][-1]) * 0.0      # touch the host copies
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            assert chk == float(N) * reps
+            return float(N) * T * reps * world / float(dt.item()), d2h * world
+
+        # headline: what the reference's evaluation report needs -- every episode's return (histograms, quantiles) and
+        # the 8 aggregate statistics (mean / std of return, service level, stock-outs, inventory: process_results)
+        v1, b1 = run_e2e(("ep_return", "summary"), 300)
+        # everything the reference keeps per episode (return + sales / demand / stock-out / inventory sums): PCIe-bound
+        full_want = ("ep_return", "stats32", "summary") if args.workload == "invmgmt" else want
+        v2, b2 = run_e2e(full_want, 600)
+        line["e2e"] = {"value": v1, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": b1, "steps": reps,
                        "note": "public API env.evaluate(): this workload's inputs are the policy/seed scalars passed as "
-                               "kernel parameters (no input tensors); every per-episode result (float64 return + 4 "
-                               "statistics) is copied to pinned host memory each step and consumed by the host inside "
-                               "the timed region; copy of step k overlaps the kernel of step k+1"}
+                               "kernel parameters (no input tensors); every episode's float64 return and the 8 aggregate "
+                               "statistics are copied to pinned host memory each step and consumed by the host inside the "
+                               "timed region; copy of step k overlaps the kernel of step k+1",
+                       "with_per_episode_statistics": {"value": v2, "d2h_bytes_per_step": b2,
+                                                       "note": "additionally the four per-episode statistics of the "
+                                                               "reference's evaluate_agent rows (PCIe-bound)"}}
     else:
         line["e2e"] = None
 

@@ -182,6 +182,17 @@ int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t env_offset, u
                           const orgym_invmgmt_rollout_in_t* in, const orgym_invmgmt_rollout_out_t* out,
                           void* stream);
 
+/* The fused rollout is additionally specialised per configuration at run time: for 1..6 stages, up to 64 periods and
+ * a sum of lead times up to 40, the on-device base-stock (integer levels) and random policies run kernels generated
+ * as straight-line CUDA for this config (lead-time rings in registers, every index a literal) and compiled for sm_100a
+ * with NVRTC on the first such rollout (cubins cached like the network env's; ORGYM_INV_JIT=0 keeps the ahead-of-time
+ * kernel).  Results are bit-identical to the ahead-of-time kernel.  orgym_invmgmt_codegen returns the generated source
+ * and, with compile_check != 0, runs it through NVRTC (no GPU needed). */
+int orgym_invmgmt_codegen(const orgym_invmgmt_config_t* cfg, int compile_check, char* buf, int64_t buflen,
+                          int64_t* needed);
+/* 1 once this handle's rollouts run the specialised kernels */
+int orgym_invmgmt_is_specialised(orgym_handle_t h);
+
 /* ------------------------------------------------------------------------- *
  * Newsvendor: NewsvendorEnv (newsvendor.py:13)
  * ------------------------------------------------------------------------- */

@@ -17,6 +17,9 @@
 #include "common.cuh"
 #include <type_traits>
 
+#include "invmgmt_jit.cuh"
+#include "jit.cuh"
+
 #define MAXN ORGYM_INV_MAX_STAGES
 
 struct InvDev {
@@ -44,6 +47,11 @@ struct InvHandle {
     long long user_dmax;  // largest value of a user_D trace (0 for sampled demand)
     void* ring_scratch = nullptr;  // rollout rings that do not fit in shared memory (allocated on first use)
     size_t ring_scratch_bytes = 0;
+    // run-time specialised rollout kernels (invmgmt_jit.cu), built on the first eligible rollout
+    std::vector<double> disc_host;
+    int jit_state = 0;  // 0 = not tried, 1 = ready, -1 = unavailable (the ahead-of-time kernel is used)
+    JitKernel jit;              // module + base-stock kernel
+    cudaKernel_t jit_rnd = nullptr;  // random-policy kernel of the same module
 };
 
 // ---- state layout: field[slot][env], env stride npad -------------------------------------------------------
@@ -874,6 +882,7 @@ extern "C" int orgym_invmgmt_create(const orgym_invmgmt_config_t* cfg, int64_t n
         ce = cudaMemcpy(disc_dev, disc.data(), sizeof(double) * (size_t)P.T, cudaMemcpyHostToDevice);
     }
     P.disc = disc_dev;
+    H->disc_host = disc;
     H->max_blocks = (int)((num_envs + ROLL_THREADS - 1) / ROLL_THREADS);
     H->hint_state = nullptr;
     H->hint_t = -1;
@@ -911,6 +920,7 @@ extern "C" int orgym_invmgmt_destroy(orgym_handle_t h) {
         DeviceGuard g(H->base.device);
         for (void* p : H->allocs) cudaFree(p);
         if (H->ring_scratch) cudaFree(H->ring_scratch);
+        if (H->jit.lib) orgym_jit_release(&H->jit);
     }
     orgym_handle_base_free(&H->base);
     delete H;
@@ -1036,6 +1046,114 @@ extern "C" int orgym_invmgmt_export_state(orgym_handle_t h, const void* state_de
     return ORGYM_OK;
 }
 
+// ---- run-time specialised rollout (invmgmt_jit.cu) ------------------------------------------------------------------
+static void inv_jit_spec(const InvDev& P, const std::vector<double>& disc, InvJitSpec* S) {
+    S->n = P.n;
+    S->T = P.T;
+    S->backlog = P.backlog;
+    for (int i = 0; i < P.n; i++) {
+        S->L[i] = P.L[i];
+        S->c[i] = P.c[i];
+        S->I0[i] = P.I0[i];
+    }
+    for (int j = 0; j <= P.n; j++) {
+        S->up[j] = P.up[j];
+        S->uc[j] = P.uc[j];
+        S->kc[j] = P.kc[j];
+        S->hc[j] = P.hc[j];
+    }
+    S->disc = disc;
+    S->log2k = P.dem.log2k;
+    S->base = P.dem.base;
+}
+
+static int inv_jit_enabled() {
+    const char* v = getenv("ORGYM_INV_JIT");
+    return !(v && v[0] == '0');
+}
+
+// debugging / test aid (no GPU needed): the CUDA source generated for a config; compile_check != 0 also runs it through
+// NVRTC.  Returns ORGYM_E_UNSUPPORTED (with the reason) for configurations the generator does not cover.
+extern "C" int orgym_invmgmt_codegen(const orgym_invmgmt_config_t* cfg, int compile_check, char* buf, int64_t buflen,
+                                     int64_t* needed) {
+    ORGYM_REQUIRE(cfg && cfg->init_inv && cfg->capacity && cfg->lead_time && cfg->unit_price && cfg->unit_cost &&
+                      cfg->demand_cost && cfg->holding_cost,
+                  "null argument");
+    const int n = cfg->num_stages - 1;
+    ORGYM_REQUIRE(n >= 1 && n <= MAXN && cfg->periods > 0, "bad stage count / horizon");
+    InvJitSpec S;
+    S.n = n;
+    S.T = cfg->periods;
+    S.backlog = cfg->backlog ? 1 : 0;
+    for (int i = 0; i < n; i++) {
+        S.L[i] = (int)cfg->lead_time[i];
+        S.c[i] = cfg->capacity[i];
+        S.I0[i] = cfg->init_inv[i];
+    }
+    for (int j = 0; j <= n; j++) {
+        S.up[j] = cfg->unit_price[j];
+        S.uc[j] = cfg->unit_cost[j];
+        S.kc[j] = cfg->demand_cost[j];
+        S.hc[j] = cfg->holding_cost[j];
+    }
+    S.disc.resize((size_t)S.T);
+    for (int t = 0; t < S.T; t++) S.disc[(size_t)t] = std::pow(cfg->alpha, (double)t);
+    if (cfg->dist.kind == ORGYM_DIST_USER) {
+        orgym_set_error("user-trace demand runs the ahead-of-time kernel");
+        return ORGYM_E_UNSUPPORTED;
+    }
+    std::vector<double> pmf;
+    int64_t base = 0;
+    if (int rc = orgym_dist_pmf(&cfg->dist, &pmf, &base)) return rc;
+    S.log2k = 0;
+    while ((size_t(1) << S.log2k) < pmf.size()) S.log2k++;
+    S.base = (int)base;
+    if (!inv_jit_eligible(S)) {
+        orgym_set_error("configuration outside the specialiser's range (1..6 stages, <= 64 periods, sum of lead times <= 40)");
+        return ORGYM_E_UNSUPPORTED;
+    }
+    std::string src = inv_jit_source(S);
+    if (needed) *needed = (int64_t)src.size();
+    if (buf && buflen > 0) {
+        size_t k = src.size() < (size_t)buflen - 1 ? src.size() : (size_t)buflen - 1;
+        memcpy(buf, src.data(), k);
+        buf[k] = 0;
+    }
+    if (compile_check) {
+        std::string err;
+        if (orgym_jit_compile_only(src, &err) != 0) {
+            orgym_set_error("%s", err.substr(0, 900).c_str());
+            return ORGYM_E_UNSUPPORTED;
+        }
+    }
+    return ORGYM_OK;
+}
+
+// 1 once the handle's rollouts run the specialised kernels (they are built on the first eligible rollout)
+extern "C" int orgym_invmgmt_is_specialised(orgym_handle_t h) {
+    if (orgym_check_handle(h, FAM_INVMGMT)) return ORGYM_E_INVALID;
+    return ((InvHandle*)h)->jit_state > 0 ? 1 : 0;
+}
+
+// builds the specialised kernels on first use; returns true when they are ready
+static bool inv_jit_ready(InvHandle* H) {
+    if (H->jit_state != 0) return H->jit_state > 0;
+    H->jit_state = -1;
+    if (!inv_jit_enabled() || H->dev.dem.kind == ORGYM_DIST_USER) return false;
+    InvJitSpec S;
+    inv_jit_spec(H->dev, H->disc_host, &S);
+    if (!inv_jit_eligible(S)) return false;
+    std::string err;
+    if (orgym_jit_compile(inv_jit_source(S), "inv_jit_rollout_bs", &H->jit, &err) != 0) return false;
+    if (cudaLibraryGetKernel(&H->jit_rnd, H->jit.lib, "inv_jit_rollout_rnd") != cudaSuccess) {
+        cudaGetLastError();
+        orgym_jit_release(&H->jit);
+        return false;
+    }
+    H->jit_state = 1;
+    return true;
+}
+
 extern "C" int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t env_offset, uint32_t episode,
                                      const orgym_invmgmt_rollout_in_t* in, const orgym_invmgmt_rollout_out_t* out,
                                      void* stream) {
@@ -1093,6 +1211,36 @@ extern "C" int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t en
     }
     const bool bounded = (double)(P.T + 1) * P.n * (double)(vmax + dmax) * 4.0 < 2147483648.0;
     const bool wide = H->wide || in->policy == ORGYM_POLICY_ACTIONS || in->demand_dev != nullptr || !bounded;
+    // fast path: kernels specialised for this configuration (register-resident rings, straight-line periods)
+    const bool jit_policy = (in->policy == ORGYM_POLICY_BASE_STOCK && A.target_is_int) || in->policy == ORGYM_POLICY_RANDOM;
+    if (!wide && jit_policy && !A.reward_traj && !A.final_I && !A.final_B && inv_jit_ready(H)) {
+        InvJitArgs J;
+        memset(&J, 0, sizeof(J));
+        J.N = A.N;
+        J.env_offset = A.env_offset;
+        J.seed = A.seed;
+        J.episode = A.episode;
+        for (int i = 0; i < P.n; i++) J.target[i] = (int32_t)A.target_int[i];
+        J.table = P.dem.table;
+        J.ep_return = A.ep_return;
+        J.stats = A.stats;
+        J.stats32 = A.stats32;
+        J.partials = A.partials;
+        void* args[] = {(void*)&J};
+        const unsigned grid = (unsigned)((A.N + INV_JIT_THREADS - 1) / INV_JIT_THREADS);
+        cudaKernel_t fn = in->policy == ORGYM_POLICY_BASE_STOCK ? H->jit.fn : H->jit_rnd;
+        cudaError_t le = cudaLaunchKernel((const void*)fn, dim3(grid), dim3(INV_JIT_THREADS), args, 0, (cudaStream_t)stream);
+        if (le != cudaSuccess) {
+            orgym_set_error("specialised rollout kernel launch failed: %s", cudaGetErrorString(le));
+            return ORGYM_E_CUDA;
+        }
+        if (out->summary_dev) {
+            int nblocks = (int)grid;
+            int rrc = orgym_launch_reduce(H->partials, nblocks, out->summary_dev, (cudaStream_t)stream);
+            if (rrc != ORGYM_OK) return rrc;
+        }
+        return ORGYM_OK;
+    }
     size_t ring = (size_t)A.rslots * ROLL_THREADS * (wide ? 8 : 4);
     size_t smem = (P.dem.kind == ORGYM_DIST_USER ? 0 : (size_t(8) << P.dem.log2k)) +
                   ring * (in->policy == ORGYM_POLICY_BASE_STOCK ? 2 : 1);

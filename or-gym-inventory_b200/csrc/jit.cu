@@ -15,6 +15,7 @@
 #include "jit_embed.inc"
 const char* orgym_jit_device_rng_src() { return k_device_rng_src; }
 const char* orgym_jit_net_args_src() { return k_net_args_src; }
+const char* orgym_jit_inv_args_src() { return k_inv_args_src; }
 
 namespace {
 typedef struct _nvrtcProgram* nvrtcProgram;

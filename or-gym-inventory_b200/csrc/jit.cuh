@@ -21,3 +21,5 @@ int orgym_jit_compile_only(const std::string& src, std::string* err);
 const char* orgym_jit_device_rng_src();
 // text of netinv_args.cuh
 const char* orgym_jit_net_args_src();
+// text of invmgmt_jit_args.cuh
+const char* orgym_jit_inv_args_src();

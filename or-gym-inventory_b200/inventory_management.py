@@ -272,6 +272,12 @@ class InvManagementMasterEnv(BatchedEnv):
             self._record(torch.clamp(a, min=0).to(torch.int64), self._reward, info)  # requested order (:250)
         return self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), info
 
+    @property
+    def rollout_specialised(self):
+        """True once `rollout` runs the kernels generated for this configuration (built on the first eligible rollout:
+        on-device base-stock with integer levels or random policy, sampled demand, no trajectory outputs)."""
+        return bool(_capi.lib().orgym_invmgmt_is_specialised(self._h))
+
     # -- batched views of the attributes the reference agents read ---------------------------------------------------
     def export_state(self):
         """(I int64[N,m-1], B int64[N,m], period int32[N]) -- current on-hand inventory, backlog, period."""

@@ -287,3 +287,42 @@ def test_history_buffers_match_reference_arrays(path):
         assert np.array_equal(getattr(env, name).cpu().numpy(), g[name]), name
     assert np.array_equal(env.P.cpu().numpy(), g["reward"])
     env.close()
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_specialised_rollout_matches_ahead_of_time_kernel(case, monkeypatch):
+    """The rollout kernels generated per configuration at run time (invmgmt_jit.cu: rings in registers, straight-line
+    periods) must reproduce the ahead-of-time kernel bit for bit: returns, statistics, summary, both policies."""
+    torch = _torch()
+    rng = np.random.default_rng(500 + case)
+    if case == 0:
+        cfg = {}
+    elif case == 1:
+        cfg = dict(dist=2, dist_param={"n": 40, "p": 0.45})
+    else:
+        n = int(rng.integers(1, 7))
+        L = rng.integers(0, 7, n)
+        cfg = dict(periods=int(rng.integers(2, 65)), I0=rng.integers(0, 200, n).tolist(), p=float(rng.uniform(5, 40)),
+                   r=np.sort(rng.uniform(0.5, 30, n + 1))[::-1].round(3).tolist(), k=rng.uniform(0, 1, n + 1).round(3).tolist(),
+                   h=rng.uniform(0, 0.5, n).round(3).tolist(), c=rng.integers(1, 300, n).tolist(), L=L.tolist(),
+                   dist_param={"mu": float(rng.integers(1, 50))}, alpha=float(rng.uniform(0.8, 1.0)))
+    cls = pkg.InvManagementBacklogEnv if case % 2 else pkg.InvManagementLostSalesEnv
+    N = 1000 + case
+    want = ("ep_return", "stats", "stats32", "summary")
+    outs = {}
+    for mode in ("jit", "aot"):
+        monkeypatch.setenv("ORGYM_INV_JIT", "1" if mode == "jit" else "0")
+        env = cls(num_envs=N, device="cuda:0", env_offset=17, **cfg)
+        res = []
+        for pol, kw in (("base_stock", dict(safety_factor=1.0)), ("base_stock", dict(safety_factor=2.0)), ("random", {})):
+            o = env.rollout(pol, seed=99, episode=3, want=want, **kw)
+            res.append({k: v.cpu().numpy().copy() for k, v in o.items()})
+        assert env.rollout_specialised == (mode == "jit")
+        # outputs the specialised kernels do not produce fall back to the ahead-of-time kernel transparently
+        o = env.rollout("base_stock", seed=99, episode=3, safety_factor=1.0, want=("ep_return", "reward_traj"))
+        assert np.array_equal(o["ep_return"].cpu().numpy(), res[0]["ep_return"])
+        outs[mode] = res
+        env.close()
+    for a, b in zip(outs["jit"], outs["aot"]):
+        for k in want:
+            assert np.array_equal(a[k], b[k]), (case, k)
