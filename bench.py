@@ -8,7 +8,8 @@ InvManagementLostSalesEnv defaults (4-stage serial chain, periods=30, Poisson mu
 fused 30-period rollout with the on-device base-stock policy (SF=1.0), Philox seed 5000.  One bench "step" is one
 fused rollout of the whole batch = 2^24 * 30 env-steps per GPU (+ the 64-byte NCCL allreduce of the episode
 statistics when N > 1).  Prints ONE JSON line (see the task contract); extra keys:
-  roofline           dominant kernel (inv_rollout_kernel): issue-slot roofline (the kernel keeps its state on chip,
+  roofline           dominant kernel (inv_jit_rollout_bs, the rollout kernel specialised for the config at run time;
+                     inv_rollout_kernel when NVRTC is unavailable): issue-slot roofline (the kernel keeps its state on chip,
                      so HBM traffic is ~1 B/env-step by construction) + its HBM figures
   roofline_step_api  the HBM-bound one-period kernel (inv_step_kernel) at the same batch size, 466 B/env-step
   cpu_baseline       the C oracle port of the reference's evaluation loop on all host cores (bounded sample)
@@ -56,7 +57,7 @@ WORKLOADS = {
 }
 
 
-KERNEL_SOURCES = {"invmgmt": ("invmgmt.cu", "common.cuh", "device_rng.cuh"),
+KERNEL_SOURCES = {"invmgmt": ("invmgmt.cu", "invmgmt_jit.cu", "invmgmt_jit_args.cuh", "common.cuh", "device_rng.cuh"),
                   "newsvendor": ("newsvendor.cu", "common.cuh", "device_rng.cuh"),
                   "netinv": ("netinv.cu", "netinv.cuh", "netinv_jit.cu", "netinv_args.cuh", "common.cuh", "device_rng.cuh")}
 
@@ -233,7 +234,7 @@ def main():
     if args.workload == "invmgmt":
         env = pkg.InvManagementLostSalesEnv(num_envs=N, device=dev, env_offset=offset)
         roll = lambda ep, want: env.rollout("base_stock", seed=W["seed"], episode=ep, safety_factor=1.0, want=want)  # noqa: E731
-        kernel, dtype = "inv_rollout_kernel<3,true,int>", "int32 state + f64 reward"
+        kernel, dtype = "inv_jit_rollout_bs | inv_rollout_kernel<3,true,int>", "int32 state + f64 reward"
     elif args.workload == "newsvendor":
         env = pkg.NewsvendorEnv(num_envs=N, device=dev, env_offset=offset)
         roll = lambda ep, want: env.rollout("classic", seed=W["seed"], episode=ep, want=want)  # noqa: E731
@@ -258,6 +259,9 @@ def main():
     for w in range(max(args.warmup, 3)):
         step(w)
     barrier()
+    if args.workload == "invmgmt":
+        kernel = ("inv_jit_rollout_bs (specialised at run time, NVRTC)" if env.rollout_specialised
+                  else "inv_rollout_kernel<3,true,int>")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

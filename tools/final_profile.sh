@@ -13,7 +13,7 @@ python bench.py --steps 5 --warmup 3 > /dev/null 2>&1 && \
 for fam in inv nv net; do
   python tools/prof_quick.py $fam > /dev/null 2>&1 || continue
   case $fam in
-    inv) rx='inv_step_kernel|inv_rollout_kernel'; skip=13; cnt=2;;   # last step launch + first rollout
+    inv) rx='inv_step_kernel|inv_jit_rollout|inv_rollout_kernel'; skip=13; cnt=2;;   # last step launch + first rollout
     nv)  rx='nv_step_kernel|nv_rollout_kernel';  skip=7;  cnt=2;;
     net) rx='net_jit_step|net_jit_rollout';       skip=11; cnt=2;;
   esac
