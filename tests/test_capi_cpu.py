@@ -88,3 +88,32 @@ def test_network_kernel_specialiser_compiles_without_gpu(lib, kind):
     assert rc == 0, lib.orgym_last_error()
     src = buf.value.decode()
     assert len(src) == need.value and "net_jit_step" in src and "net_jit_rollout" in src and f"#define NE {len(P.reorder_links)}" in src
+
+
+@pytest.mark.parametrize("kind", ["default_lost", "default_backlog", "zero_lead", "binomial"])
+def test_serial_rollout_specialiser_compiles_without_gpu(lib, kind):
+    """invmgmt_jit.cu: configuration -> straight-line CUDA for the fused rollout -> NVRTC compile check for sm_100a."""
+    cfgs = {"default_lost": dict(backlog=False), "default_backlog": dict(backlog=True),
+            "zero_lead": dict(backlog=True, I0=[50, 60], r=[1.5, 1.0, 0.5], k=[0.1, 0.05, 0.02], h=[0.1, 0.05], c=[80, 70],
+                              L=[0, 3], periods=12, alpha=0.9),
+            "binomial": dict(backlog=False, dist=2, dist_param={"n": 30, "p": 0.4})}
+    P = pkg.InvManagementParams(**cfgs[kind])
+    keep = []
+    cfg = P.to_c(keep)
+    need = C.c_int64(0)
+    buf = C.create_string_buffer(1 << 20)
+    rc = lib.orgym_invmgmt_codegen(C.byref(cfg), 1, buf, len(buf), C.byref(need))
+    assert rc == 0, lib.orgym_last_error()
+    src = buf.value.decode()
+    assert len(src) == need.value and "inv_jit_rollout_bs" in src and "inv_jit_rollout_rnd" in src
+    assert src.count("// ---- period") == 2 * P.num_periods
+
+
+def test_serial_rollout_specialiser_reports_unsupported_configs(lib):
+    P = pkg.InvManagementParams(backlog=True, I0=[10] * 7, r=[9, 8, 7, 6, 5, 4, 3, 2], k=[0.1] * 8, h=[0.1] * 7, c=[10] * 7,
+                                L=[1] * 7)
+    keep = []
+    cfg = P.to_c(keep)
+    need = C.c_int64(0)
+    rc = lib.orgym_invmgmt_codegen(C.byref(cfg), 0, None, 0, C.byref(need))
+    assert rc == -3 and b"specialiser" in lib.orgym_last_error()
