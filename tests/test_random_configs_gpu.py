@@ -2,6 +2,8 @@
 C oracle (which is pinned to the reference by the golden vectors).  Covers what the goldens cannot enumerate: stage
 counts 1..12, lead times including 0, lost sales / backlog, float / negative / over-capacity actions, random graphs
 with yields < 1, multi-market retailers, L = 0 links, both network kernels."""
+import os
+
 import numpy as np
 import pytest
 
@@ -9,6 +11,8 @@ import or_gym_inventory_b200 as pkg
 from helpers import seq_sum
 
 pytestmark = pytest.mark.gpu
+# ORGYM_STRESS=k multiplies the number of random cases (one-off soak runs; the default suite stays short)
+STRESS = max(1, int(os.environ.get("ORGYM_STRESS", "1")))
 
 
 def _torch():
@@ -16,7 +20,7 @@ def _torch():
     return torch
 
 
-@pytest.mark.parametrize("case", range(12))
+@pytest.mark.parametrize("case", range(12 * STRESS))
 def test_invmgmt_random_config(case):
     from oracle import oracle
     torch = _torch()
@@ -63,7 +67,7 @@ def test_invmgmt_random_config(case):
     env.close()
 
 
-@pytest.mark.parametrize("case", range(8))
+@pytest.mark.parametrize("case", range(8 * STRESS))
 def test_newsvendor_random_config(case):
     from oracle import oracle
     torch = _torch()
@@ -130,7 +134,7 @@ def _random_graph(rng):
 
 
 @pytest.mark.parametrize("mode", ["specialised", "stream", "generic"])
-@pytest.mark.parametrize("case", range(6))
+@pytest.mark.parametrize("case", range(6 * STRESS))
 def test_netinv_random_graph(case, mode, monkeypatch):
     from oracle import oracle
     torch = _torch()
