@@ -385,7 +385,10 @@ def main():
         alg_bytes = N * 40.0           # per launch: 8 B return + 32 B statistics per episode
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         issue_peak = SM_COUNT * SCHED_PER_SM * sm_mhz * 1e6           # warp-instructions / s at the observed clock
-        c = counts.get(args.workload, {})
+        ckey = args.workload
+        if args.workload == "invmgmt" and "inv_jit" not in kernel:
+            ckey = "invmgmt_aot"       # NVRTC unavailable: the ahead-of-time kernel ran (its own instruction count)
+        c = counts.get(ckey, {})
         src_now = kernel_source_hash(args.workload)
         stale = bool(c) and c.get("src_sha1") not in (None, src_now)
         roof = {"kernel": kernel, "bound": "issue", "unit": "warp-inst/s", "peak": issue_peak,
