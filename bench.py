@@ -58,7 +58,7 @@ WORKLOADS = {
 
 
 KERNEL_SOURCES = {"invmgmt": ("invmgmt.cu", "invmgmt_jit.cu", "invmgmt_jit_args.cuh", "common.cuh", "device_rng.cuh"),
-                  "newsvendor": ("newsvendor.cu", "common.cuh", "device_rng.cuh"),
+                  "newsvendor": ("newsvendor.cu", "poisson_mu.cuh", "common.cuh", "device_rng.cuh"),
                   "netinv": ("netinv.cu", "netinv.cuh", "netinv_jit.cu", "netinv_args.cuh", "common.cuh", "device_rng.cuh")}
 
 

@@ -1,6 +1,7 @@
 // api.cu -- family-independent part of the C ABI: error string, version, handle header, error bits,
 // alias-table construction for the fixed demand distributions, stand-alone samplers (K6).
 #include "common.cuh"
+#include "poisson_mu.cuh"
 #include <mutex>
 
 static thread_local std::string g_last_error;

@@ -9,6 +9,7 @@
 // branch produced each operand (NumPy >= 2 promotion rules); `Sc` carries the operand kind so the chain is
 // reproduced bit for bit.  Pipeline state is float32 like the reference's `state` vector.
 #include "common.cuh"
+#include "poisson_mu.cuh"
 
 #define NV_MAXL ORGYM_NV_MAX_LEAD
 #ifndef NV_STEP_MINB
@@ -68,15 +69,20 @@ __device__ __forceinline__ Sc mk(double v, int k) {
     s.k = k;
     return s;
 }
+// Result kind = max(kind a, kind b) (PY < F32 < F64): float64 wins, two Python scalars stay Python (float64 arithmetic),
+// anything else is float32.  Branch-free: both precisions are computed and one is selected -- the kinds differ from
+// lane to lane (they depend on which operand a min/max picked), so branches would diverge anyway.
 __device__ __forceinline__ Sc sc_mul(Sc a, Sc b) {
-    if (a.k == K_F64 || b.k == K_F64) return mk(a.v * b.v, K_F64);
-    if (a.k == K_PY && b.k == K_PY) return mk(a.v * b.v, K_PY);
-    return mk((double)((float)a.v * (float)b.v), K_F32);
+    const double r64 = a.v * b.v;
+    const double r32 = (double)((float)a.v * (float)b.v);
+    const int k = a.k > b.k ? a.k : b.k;
+    return mk(k == K_F32 ? r32 : r64, k);
 }
 __device__ __forceinline__ Sc sc_sub(Sc a, Sc b) {
-    if (a.k == K_F64 || b.k == K_F64) return mk(a.v - b.v, K_F64);
-    if (a.k == K_PY && b.k == K_PY) return mk(a.v - b.v, K_PY);
-    return mk((double)((float)a.v - (float)b.v), K_F32);
+    const double r64 = a.v - b.v;
+    const double r32 = (double)((float)a.v - (float)b.v);
+    const int k = a.k > b.k ? a.k : b.k;
+    return mk(k == K_F32 ? r32 : r64, k);
 }
 
 struct NvParams {
@@ -441,6 +447,8 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kern
     }
     const PoisSplit ps = poisson_split(P.pt, q.mu);  // per-episode constants of the demand sampler
     uint4 dw = make_uint4(0, 0, 0, 0);
+    __shared__ double pcdf[ORGYM_PT_CDF * NV_ROLL_THREADS];  // cdf of the Poisson(r) remainder, [k][thread]
+    if (ps.i0 >= 0 && !A.demand) poisson_small_table(ps.r, ps.p0, P.rcp, pcdf + tid, NV_ROLL_THREADS);
     int head = 0;
     double ret = 0.0, s_sales = 0.0, s_dem = 0.0, s_lost = 0.0, s_ex = 0.0;
     for (int t = 0; t < P.T; t++) {
@@ -481,7 +489,9 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kern
             d = poisson_ptrs(q.mu, key, A.episode, t);
         else {  // one Philox block per two periods (same words as poisson_mu)
             if ((t & 1) == 0) dw = philox_block(key, (uint32_t)t >> 1, A.episode, STREAM_POISSON_TAB, 0);
-            d = poisson_tab_draw(P.pt, P.rcp, ps, (t & 1) ? dw.z : dw.x, (t & 1) ? dw.w : dw.y);
+            const uint32_t wa = (t & 1) ? dw.z : dw.x, wi = (t & 1) ? dw.w : dw.y;
+            d = poisson_tab_alias(P.pt, ps, wa) +
+                poisson_small_lookup(((double)wi + 0.5) * (1.0 / 4294967296.0), pcdf + tid, NV_ROLL_THREADS, ps.r, ps.p0, P.rcp);
         }
         float oq;
         double su, ex, sh;
@@ -699,6 +709,7 @@ extern "C" int orgym_newsvendor_rollout(orgym_handle_t h, uint64_t seed, int64_t
     A.partials = out->summary_dev ? H->partials : nullptr;
     size_t smem = (size_t)H->dev.L * NV_ROLL_THREADS * 4 + 16;
     int nblocks = (int)((A.N + NV_ROLL_THREADS - 1) / NV_ROLL_THREADS);
+    cudaFuncSetAttribute(nv_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // + 17 KB static
     nv_rollout_kernel<<<nblocks, NV_ROLL_THREADS, smem, (cudaStream_t)stream>>>(H->dev, A);
     ORGYM_CUDA(cudaGetLastError());
     if (out->summary_dev) {
