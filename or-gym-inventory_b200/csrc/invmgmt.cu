@@ -15,6 +15,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "launch_util.cuh"
 #include <type_traits>
 
 #include "invmgmt_jit.cuh"
@@ -767,13 +768,13 @@ static void launch_step(const InvHandle* H, const InvStepArgs& A, size_t smem, c
     unsigned grid = (unsigned)((A.N + ORGYM_TILE - 1) / ORGYM_TILE);
 #define STEP_CASE(NSV)                                                                                              \
     case NSV:                                                                                                       \
-        cudaFuncSetAttribute(inv_step_kernel<NSV, true, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        orgym_ensure_dyn_smem<inv_step_kernel<NSV, true, S>>(smem);                                                  \
         inv_step_kernel<NSV, true, S><<<grid, ORGYM_TILE, smem, s>>>(P, A);                                          \
         break;
     switch (A.direct_obs ? 0 : P.n) {
         STEP_CASE(1) STEP_CASE(2) STEP_CASE(3) STEP_CASE(4) STEP_CASE(5) STEP_CASE(6) STEP_CASE(7) STEP_CASE(8)
         default:
-            cudaFuncSetAttribute(inv_step_kernel<MAXN, false, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            orgym_ensure_dyn_smem<inv_step_kernel<MAXN, false, S>>(smem);
             inv_step_kernel<MAXN, false, S><<<grid, ORGYM_TILE, smem, s>>>(P, A);
     }
 #undef STEP_CASE
@@ -785,14 +786,13 @@ static void launch_rollout(const InvHandle* H, const InvRolloutArgs& A, size_t s
     unsigned grid = (unsigned)((A.N + ROLL_THREADS - 1) / ROLL_THREADS);
 #define ROLL_CASE(NSV)                                                                                                 \
     case NSV:                                                                                                          \
-        cudaFuncSetAttribute(inv_rollout_kernel<NSV, true, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        orgym_ensure_dyn_smem<inv_rollout_kernel<NSV, true, S>>(smem);                                               \
         inv_rollout_kernel<NSV, true, S><<<grid, ROLL_THREADS, smem, s>>>(P, A);                                        \
         break;
     switch (A.ring_scratch ? 0 : P.n) {
         ROLL_CASE(1) ROLL_CASE(2) ROLL_CASE(3) ROLL_CASE(4) ROLL_CASE(5) ROLL_CASE(6) ROLL_CASE(7) ROLL_CASE(8)
         default:
-            cudaFuncSetAttribute(inv_rollout_kernel<MAXN, false, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem);
+            orgym_ensure_dyn_smem<inv_rollout_kernel<MAXN, false, S>>(smem);
             inv_rollout_kernel<MAXN, false, S><<<grid, ROLL_THREADS, smem, s>>>(P, A);
     }
 #undef ROLL_CASE

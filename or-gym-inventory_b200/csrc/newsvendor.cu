@@ -9,6 +9,7 @@
 // branch produced each operand (NumPy >= 2 promotion rules); `Sc` carries the operand kind so the chain is
 // reproduced bit for bit.  Pipeline state is float32 like the reference's `state` vector.
 #include "common.cuh"
+#include "launch_util.cuh"
 #include "poisson_mu.cuh"
 
 #define NV_MAXL ORGYM_NV_MAX_LEAD
@@ -659,7 +660,7 @@ extern "C" int orgym_newsvendor_step(orgym_handle_t h, void* state_dev, const fl
     A.err = H->base.err_dev;
     A.use_bulk = nv_use_bulk() && ((uintptr_t)obs_dev % 16 == 0);
     size_t smem = (size_t)ORGYM_TILE * (H->dev.obs_dim + 1) * 4;
-    cudaFuncSetAttribute(nv_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    orgym_ensure_dyn_smem<nv_step_kernel>(smem);
     nv_step_kernel<<<(unsigned)((A.N + ORGYM_TILE - 1) / ORGYM_TILE), ORGYM_TILE, smem, (cudaStream_t)stream>>>(H->dev, A);
     ORGYM_CUDA(cudaGetLastError());
     return ORGYM_OK;
@@ -709,7 +710,7 @@ extern "C" int orgym_newsvendor_rollout(orgym_handle_t h, uint64_t seed, int64_t
     A.partials = out->summary_dev ? H->partials : nullptr;
     size_t smem = (size_t)H->dev.L * NV_ROLL_THREADS * 4 + 16;
     int nblocks = (int)((A.N + NV_ROLL_THREADS - 1) / NV_ROLL_THREADS);
-    cudaFuncSetAttribute(nv_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // + 17 KB static
+    orgym_ensure_dyn_smem<nv_rollout_kernel>(smem);  // + 17 KB static
     nv_rollout_kernel<<<nblocks, NV_ROLL_THREADS, smem, (cudaStream_t)stream>>>(H->dev, A);
     ORGYM_CUDA(cudaGetLastError());
     if (out->summary_dev) {

@@ -177,6 +177,7 @@ class InvManagementMasterEnv(BatchedEnv):
         self._reward = torch.zeros(N, dtype=torch.float64, device=dev)
         self._terminated = torch.zeros(N, dtype=torch.uint8, device=dev)
         self._truncated = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._term_b, self._trunc_b = self._terminated.view(torch.bool), self._truncated.view(torch.bool)  # cached views
         self._info = _capi.InvInfo()
         self._info_t = {}
         if self.info_level >= 1:
@@ -270,7 +271,7 @@ class InvManagementMasterEnv(BatchedEnv):
             info["final_obs"] = self._final_obs
         if self.record_history:
             self._record(torch.clamp(a, min=0).to(torch.int64), self._reward, info)  # requested order (:250)
-        return self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), info
+        return self._obs, self._reward, self._term_b, self._trunc_b, info
 
     @property
     def rollout_specialised(self):

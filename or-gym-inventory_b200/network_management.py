@@ -367,6 +367,7 @@ class NetInvMgmtMasterEnv(BatchedEnv):
         self._reward = torch.zeros(N, dtype=torch.float64, device=dev)
         self._terminated = torch.zeros(N, dtype=torch.uint8, device=dev)
         self._truncated = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._term_b, self._trunc_b = self._terminated.view(torch.bool), self._truncated.view(torch.bool)  # cached views
         self._info = _capi.NetInfo()
         self._info_t = {}
         if self.info_level >= 1:
@@ -445,7 +446,7 @@ class NetInvMgmtMasterEnv(BatchedEnv):
             info["final_obs"] = self._final_obs
         if self.record_history:
             self._record(info)
-        return self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), info
+        return self._obs, self._reward, self._term_b, self._trunc_b, info
 
     def export_state(self):
         """(X f64[N,J], Y f64[N,E], U f64[N,M], period i32[N]) in main_nodes / reorder_links / retail_links order."""

@@ -83,6 +83,7 @@ class NewsvendorEnv(BatchedEnv):
         self._terminated = torch.zeros(N, dtype=torch.uint8, device=dev)
         self._truncated = torch.zeros(N, dtype=torch.uint8, device=dev)
         self._info = _capi.NvInfo()
+        self._info_views = None
         self._info_t = {}
         if self.info_level >= 1:
             self._info_t = dict(demand=torch.zeros(N, dtype=torch.int64, device=dev),
@@ -128,14 +129,17 @@ class NewsvendorEnv(BatchedEnv):
             self._h, self._ptr(self._state), self._ptr(a), self._ptr(d), _AUTORESET[self.autoreset_mode],
             self._ptr(self._obs), self._ptr(self._reward), self._ptr(self._terminated), self._ptr(self._truncated),
             C.byref(self._info), self._stream()))
-        info = {}
-        if self._info_t:
-            p = self._info_t["parts"]
-            info = dict(demand=self._info_t["demand"], revenue=p[:, 0], purchase_cost=p[:, 1], holding_cost=p[:, 2],
-                        lost_sales_penalty=p[:, 3])
-        if self.autoreset_mode == "same_step":
-            info["final_obs"] = self._final_obs
-        return self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), info
+        if self._info_views is None:      # views of the (fixed) output buffers, built once: slicing costs microseconds
+            v = {}
+            if self._info_t:
+                p = self._info_t["parts"]
+                v = dict(demand=self._info_t["demand"], revenue=p[:, 0], purchase_cost=p[:, 1], holding_cost=p[:, 2],
+                         lost_sales_penalty=p[:, 3])
+            if self.autoreset_mode == "same_step":
+                v["final_obs"] = self._final_obs
+            self._info_views = (v, self._terminated.view(torch.bool), self._truncated.view(torch.bool))
+        v, term, trunc = self._info_views
+        return self._obs, self._reward, term, trunc, dict(v)
 
     def export_params(self):
         """float64[N,5]: price, cost, h, k, mu as the reference's Python floats (newsvendor.py:105-111)."""
