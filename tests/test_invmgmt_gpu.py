@@ -326,3 +326,29 @@ def test_specialised_rollout_matches_ahead_of_time_kernel(case, monkeypatch):
     for a, b in zip(outs["jit"], outs["aot"]):
         for k in want:
             assert np.array_equal(a[k], b[k]), (case, k)
+
+
+def test_evaluation_report_reproduces_the_reference_summary_row():
+    """The reference's per-agent summary (mean / median / std / min / max of TotalReward, mean service level, stock-out
+    quantity and ending inventory -- benchmark_InvManagementBacklogEnv.py:493-504) from one fused rollout, on device."""
+    import pandas as pd
+    N = 20001
+    env = pkg.InvManagementBacklogEnv(num_envs=N, device="cuda:0")
+    out = env.rollout("base_stock", seed=4000, safety_factor=1.0, want=("ep_return", "stats", "summary"))
+    rep = pkg.evaluation_report(out, env.num_periods)
+    ret, st = out["ep_return"].cpu().numpy(), out["stats"].cpu().numpy().astype(np.float64)
+    sl = np.where(st[:, 1] > 1e-6, st[:, 0] / np.maximum(1e-6, st[:, 1]), 1.0)
+    df = pd.DataFrame(dict(TotalReward=ret, AvgServiceLevel=sl, TotalStockoutQty=st[:, 2], AvgEndingInv=st[:, 3] / env.num_periods))
+    assert rep["SuccessfulEpisodes"] == N
+    assert rep["MedianReward"] == df.TotalReward.median() and rep["MinReward"] == ret.min() and rep["MaxReward"] == ret.max()
+    assert np.isclose(rep["AvgReward"], ret.mean(), rtol=1e-12) and np.isclose(rep["StdReward"], df.TotalReward.std(), rtol=1e-10)
+    assert np.isclose(rep["AvgServiceLevel"], sl.mean(), rtol=1e-12)
+    assert np.isclose(rep["AvgStockoutQty"], st[:, 2].mean(), rtol=1e-12)
+    assert np.isclose(rep["AvgEndInv"], df.AvgEndingInv.mean(), rtol=1e-12)
+    # the in-kernel summary agrees on what it carries (means, population std)
+    d = pkg.describe_summary(out["summary"].cpu().numpy(), env.num_periods)
+    assert d["episodes"] == N and np.isclose(d["TotalReward_mean"], rep["AvgReward"], rtol=1e-12)
+    assert np.isclose(d["TotalStockoutQty_mean"], rep["AvgStockoutQty"], rtol=1e-12)
+    # order statistic by bisection == sort
+    assert pkg.kth_smallest(out["ep_return"], 1234) == np.sort(ret)[1234]
+    env.close()
