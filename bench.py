@@ -544,6 +544,28 @@ def main():
                 eo.close()
                 del eo
                 torch.cuda.empty_cache()
+            if args.workload == "invmgmt":
+                # the north-star target is quoted on InvManagementBacklogEnv; the random policy is cfg 3's second driver
+                for label, cls_o, pol_o, kw_o in (
+                        ("invmgmt_backlog_base_stock", pkg.InvManagementBacklogEnv, "base_stock", dict(safety_factor=1.0)),
+                        ("invmgmt_lost_sales_random", pkg.InvManagementLostSalesEnv, "random", {})):
+                    eo = cls_o(num_envs=N, device=dev)
+                    for k in range(3):
+                        eo.rollout(pol_o, seed=W["seed"], episode=k, **kw_o)
+                    torch.cuda.synchronize()
+                    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    o0.record()
+                    for k in range(20):
+                        eo.rollout(pol_o, seed=W["seed"], episode=10 + k, **kw_o)
+                    o1.record()
+                    torch.cuda.synchronize()
+                    oms = o0.elapsed_time(o1) / 20
+                    others[label] = {"workload": f"{cls_o.__name__} defaults, fused rollout, {pol_o} policy", "instances": N,
+                                     "periods": T, "ms_per_rollout": oms, "env_steps_per_s": N * T / (oms * 1e-3),
+                                     "specialised_kernel": eo.rollout_specialised}
+                    eo.close()
+                    del eo
+                    torch.cuda.empty_cache()
             line["other_configs"] = others
     if rank == 0:
         emit(line)
