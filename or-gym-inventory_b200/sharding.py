@@ -41,11 +41,41 @@ def describe_summary(summary, periods):
             "TotalStockoutQty_mean": s[5] / n, "AvgEndingInv_mean": s[6] / n / max(periods, 1)}
 
 
+def _gpu_numa_node(device_index):
+    """NUMA node of a CUDA device from sysfs (-1 when unknown)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(int(device_index))
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            return int(f.read().strip())
+    except Exception:  # noqa: BLE001
+        return -1
+
+
+def _prefer_memory_node(node):
+    """set_mempolicy(MPOL_PREFERRED, {node}) for the calling thread: pages allocated from now on (including the pinned
+    result buffers cudaHostAlloc creates) come from `node` even when the CPU cores of that node are not available to
+    this process.  Returns True on success."""
+    import ctypes
+    import platform
+    if node < 0 or node >= 64 or platform.machine() != "x86_64":
+        return False
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238
+        return libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(65)) == 0
+    except Exception:  # noqa: BLE001
+        return False
+
+
 def bind_host_to_gpu(device_index):
-    """Pin the calling process to the CPU cores NVML reports as local to GPU `device_index` (same NUMA node / PCIe root).
-    Pinned host buffers allocated afterwards are first touched there, so the per-episode device->host result copies of
-    `evaluate()` do not cross the socket interconnect when 8 ranks stream results at once.  Returns the number of cores
-    in the new affinity mask, or 0 when NVML is unavailable (nothing is changed then)."""
+    """Keep a rank's host side next to its GPU: pin the process to the CPU cores NVML reports as local to GPU
+    `device_index` and prefer that GPU's NUMA node for memory, so that the pinned result buffers of `evaluate()` are
+    allocated there and the per-episode device->host copies of 8 ranks do not funnel through one socket.  Best effort:
+    returns the number of cores in the affinity mask afterwards (0 when NVML is unavailable; nothing changes then)."""
+    _prefer_memory_node(_gpu_numa_node(device_index))
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -61,4 +91,3 @@ def bind_host_to_gpu(device_index):
         return len(os.sched_getaffinity(0))
     except Exception:  # noqa: BLE001 -- an optimisation only
         return 0
-
