@@ -410,14 +410,19 @@ struct NvRolloutArgs {
 
 __device__ __forceinline__ float clipf(float q, float hi) { return q < 0.0f ? 0.0f : (q > hi ? hi : q); }
 
+// LT > 0: the lead time is the compile-time constant LT (1..7): the pipeline lives in LT registers and the period loop
+// is unrolled by LT, so that the position of every pipeline element is static (logical element j of the period with
+// offset u sits in pv[(u + j) % LT]) -- no ring indexing, no shifting.  LT == 0: any lead time, ring in shared memory.
+template <int LT>
 __global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kernel(const __grid_constant__ NvDev P,
                                                                      const __grid_constant__ NvRolloutArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* ring = (float*)smem;  // [L][threads], logical index j lives at slot (head + j) % L
-    const int tid = threadIdx.x, L = P.L;
+    const int tid = threadIdx.x, L = LT > 0 ? LT : P.L;
     const int64_t e = (int64_t)blockIdx.x * NV_ROLL_THREADS + tid;
     const bool valid = e < A.N;
-    for (int j = 0; j < L; j++) ring[j * NV_ROLL_THREADS + tid] = 0.0f;
+    if (LT == 0)
+        for (int j = 0; j < L; j++) ring[j * NV_ROLL_THREADS + tid] = 0.0f;
     const uint64_t key = A.seed + (uint64_t)(A.env_offset + e);
     NvParams q;
     if (A.fixed && valid) {
@@ -452,14 +457,8 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kern
     if (ps.i0 >= 0 && !A.demand) poisson_small_table(ps.r, ps.p0, P.rcp, pcdf + tid, NV_ROLL_THREADS);
     int head = 0;
     double ret = 0.0, s_sales = 0.0, s_dem = 0.0, s_lost = 0.0, s_ex = 0.0;
-    for (int t = 0; t < P.T; t++) {
-        auto get = [&](int j) {
-            int s = head + j;
-            s = s >= L ? s - L : s;
-            return ring[s * NV_ROLL_THREADS + tid];
-        };
-        float psum = nv_pipe_sum(L, get);
-        float pipe0 = L > 0 ? ring[head * NV_ROLL_THREADS + tid] : 0.0f;
+    // one period given the pipeline sum and the arriving order; returns the order placed (the new last element)
+    auto period = [&](const int t, const float psum, const float pipe0) -> float {
         float act;
         if (A.policy == ORGYM_NV_POLICY_ACTIONS)
             act = valid ? A.actions[e * A.a_se + (int64_t)t * A.a_st] : 0.0f;
@@ -501,9 +500,38 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kern
         s_sales += su; s_dem += (double)d; s_lost += sh; s_ex += ex;
         if (valid && A.reward_traj) A.reward_traj[e * P.T + t] = r;
         if (valid && A.action_traj) A.action_traj[e * P.T + t] = act;
-        if (L > 0) {  // shift left, append: overwrite the slot that just arrived and advance the head
-            ring[head * NV_ROLL_THREADS + tid] = oq;
-            head = head + 1 == L ? 0 : head + 1;
+        return oq;
+    };
+    float pv[LT > 0 ? LT : 1];
+#pragma unroll
+    for (int j = 0; j < (LT > 0 ? LT : 1); j++) pv[j] = 0.0f;
+    if (LT > 0) {
+        for (int t0 = 0; t0 < P.T; t0 += LT) {
+#pragma unroll
+            for (int u = 0; u < LT; u++) {
+                const int t = t0 + u;
+                if (t < P.T) {
+                    float r = 0.0f;  // np.sum over fewer than 8 float32 values: sequential, oldest first
+#pragma unroll
+                    for (int j = 0; j < LT; j++) r = r + pv[(u + j) % LT];
+                    pv[u] = period(t, r, pv[u]);  // the slot that just arrived receives the new order (:177-179)
+                }
+            }
+        }
+    } else {
+        for (int t = 0; t < P.T; t++) {
+            auto get = [&](int j) {
+                int s = head + j;
+                s = s >= L ? s - L : s;
+                return ring[s * NV_ROLL_THREADS + tid];
+            };
+            const float psum = nv_pipe_sum(L, get);
+            const float pipe0 = L > 0 ? ring[head * NV_ROLL_THREADS + tid] : 0.0f;
+            const float oq = period(t, psum, pipe0);
+            if (L > 0) {  // shift left, append: overwrite the slot that just arrived and advance the head
+                ring[head * NV_ROLL_THREADS + tid] = oq;
+                head = head + 1 == L ? 0 : head + 1;
+            }
         }
     }
     if (valid) {
@@ -514,10 +542,22 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kern
         if (A.final_obs) {
             float* o = A.final_obs + e * P.obs_dim;
             o[0] = (float)q.price; o[1] = (float)q.cost; o[2] = fh; o[3] = fk; o[4] = fmu;
-            for (int j = 0; j < L; j++) {
-                int s = head + j;
-                s = s >= L ? s - L : s;
-                o[5 + j] = ring[s * NV_ROLL_THREADS + tid];
+            if (LT > 0) {
+                const int u_end = P.T % LT;  // offset of the period after the last one
+#pragma unroll
+                for (int j = 0; j < LT; j++) {
+                    float v = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < LT; k++)
+                        if ((u_end + j) % LT == k) v = pv[k];
+                    o[5 + j] = v;
+                }
+            } else {
+                for (int j = 0; j < L; j++) {
+                    int s = head + j;
+                    s = s >= L ? s - L : s;
+                    o[5 + j] = ring[s * NV_ROLL_THREADS + tid];
+                }
             }
         }
     }
@@ -710,8 +750,18 @@ extern "C" int orgym_newsvendor_rollout(orgym_handle_t h, uint64_t seed, int64_t
     A.partials = out->summary_dev ? H->partials : nullptr;
     size_t smem = (size_t)H->dev.L * NV_ROLL_THREADS * 4 + 16;
     int nblocks = (int)((A.N + NV_ROLL_THREADS - 1) / NV_ROLL_THREADS);
-    orgym_ensure_dyn_smem<nv_rollout_kernel>(smem);  // + 17 KB static
-    nv_rollout_kernel<<<nblocks, NV_ROLL_THREADS, smem, (cudaStream_t)stream>>>(H->dev, A);
+#define NV_ROLL_CASE(LTV)                                                                          \
+    case LTV:                                                                                      \
+        orgym_ensure_dyn_smem<nv_rollout_kernel<LTV>>(16);                                         \
+        nv_rollout_kernel<LTV><<<nblocks, NV_ROLL_THREADS, 16, (cudaStream_t)stream>>>(H->dev, A); \
+        break;
+    switch (H->dev.L) {  // lead times 1..7: register-resident pipeline (see the kernel)
+        NV_ROLL_CASE(1) NV_ROLL_CASE(2) NV_ROLL_CASE(3) NV_ROLL_CASE(4) NV_ROLL_CASE(5) NV_ROLL_CASE(6) NV_ROLL_CASE(7)
+        default:
+            orgym_ensure_dyn_smem<nv_rollout_kernel<0>>(smem);  // + 17 KB static
+            nv_rollout_kernel<0><<<nblocks, NV_ROLL_THREADS, smem, (cudaStream_t)stream>>>(H->dev, A);
+    }
+#undef NV_ROLL_CASE
     ORGYM_CUDA(cudaGetLastError());
     if (out->summary_dev) {
         int rr = orgym_launch_reduce(H->partials, nblocks, out->summary_dev, (cudaStream_t)stream);
