@@ -117,3 +117,32 @@ def test_serial_rollout_specialiser_reports_unsupported_configs(lib):
     need = C.c_int64(0)
     rc = lib.orgym_invmgmt_codegen(C.byref(cfg), 0, None, 0, C.byref(need))
     assert rc == -3 and b"specialiser" in lib.orgym_last_error()
+
+
+def test_header_is_plain_c_and_matches_the_ctypes_mirror(tmp_path):
+    """include/orgym_b200.h must compile as C99 (it is the drop-in boundary for any host language), and every struct of
+    the Python host's ctypes mirror must have the size and field offsets the C compiler gives the header's struct."""
+    import subprocess
+    from or_gym_inventory_b200 import _capi
+    pairs = [("orgym_dist_t", _capi.Dist), ("orgym_invmgmt_config_t", _capi.InvConfig), ("orgym_invmgmt_info_t", _capi.InvInfo),
+             ("orgym_invmgmt_rollout_in_t", _capi.InvRolloutIn), ("orgym_invmgmt_rollout_out_t", _capi.InvRolloutOut),
+             ("orgym_newsvendor_config_t", _capi.NvConfig), ("orgym_newsvendor_info_t", _capi.NvInfo),
+             ("orgym_newsvendor_rollout_in_t", _capi.NvRolloutIn), ("orgym_newsvendor_rollout_out_t", _capi.NvRolloutOut),
+             ("orgym_netinv_config_t", _capi.NetConfig), ("orgym_netinv_info_t", _capi.NetInfo),
+             ("orgym_netinv_rollout_in_t", _capi.NetRolloutIn), ("orgym_netinv_rollout_out_t", _capi.NetRolloutOut)]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "orgym_b200.h"', 'int main(void) {']
+    for cname, _ in pairs:
+        src.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+    src.append('  return 0; }')
+    c = tmp_path / "abi.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    sizes = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in pairs:
+        assert int(sizes[cname]) == C.sizeof(cls), (cname, sizes[cname], C.sizeof(cls))
+    # field order / count: the last field of every mirror sits where the C struct ends (modulo tail padding <= 8)
+    for cname, cls in pairs:
+        last = cls._fields_[-1][0]
+        end = getattr(cls, last).offset + getattr(cls, last).size
+        assert 0 <= int(sizes[cname]) - end < 8, cname
