@@ -146,3 +146,49 @@ def test_header_is_plain_c_and_matches_the_ctypes_mirror(tmp_path):
         last = cls._fields_[-1][0]
         end = getattr(cls, last).offset + getattr(cls, last).size
         assert 0 <= int(sizes[cname]) - end < 8, cname
+
+
+def _build_c_host(tmp_path):
+    import subprocess
+    exe = tmp_path / "c_host"
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", f"{cuda}/include",
+                           os.path.join(ROOT, "examples", "c_host.c"), "-L", os.path.join(ROOT, "or-gym-inventory_b200", "csrc"),
+                           "-lorgym_b200", "-L", f"{cuda}/lib64", "-lcudart", "-lm", "-o", str(exe)])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.pathsep.join(
+        [os.path.join(ROOT, "or-gym-inventory_b200", "csrc"), f"{cuda}/lib64", os.environ.get("LD_LIBRARY_PATH", "")]))
+    return exe, env
+
+
+def test_c_host_example_builds_and_fails_loudly_without_a_gpu(lib, tmp_path):
+    """examples/c_host.c drives the library from plain C (no Python, no torch); without a device it must say so."""
+    import subprocess
+    import torch
+    exe, env = _build_c_host(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu-marked run of the example")
+    p = subprocess.run([str(exe)], env=env, capture_output=True, text=True)
+    assert p.returncode == 2 and "no CUDA device" in p.stderr
+
+
+@pytest.mark.gpu
+def test_c_host_example_matches_the_python_host(lib, tmp_path):
+    import re
+    import subprocess
+    exe, env = _build_c_host(tmp_path)
+    p = subprocess.run([str(exe)], env=env, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    m = re.search(r"rollout,\s+base-stock SF=1.0:\s+mean episode return ([-0-9.]+) over 4096", p.stdout)
+    s = re.search(r"step API,\s+constant order 20: mean episode return ([-0-9.]+) over 4096", p.stdout)
+    assert m and s, p.stdout
+    e = pkg.InvManagementBacklogEnv(num_envs=4096, device="cuda:0")
+    out = e.rollout("base_stock", seed=4000, safety_factor=1.0, want=("ep_return", "summary"))
+    assert abs(out["ep_return"].mean().item() - float(m.group(1))) < 1e-3
+    import torch
+    e.reset(seed=4000)
+    a = torch.full((4096, 3), 20, dtype=torch.int64, device="cuda")
+    tot = 0.0
+    for _ in range(e.num_periods):
+        tot += e.step(a)[1].sum().item()
+    assert abs(tot / 4096 - float(s.group(1))) < 1e-3
+    e.close()
