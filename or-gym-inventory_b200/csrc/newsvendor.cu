@@ -410,9 +410,10 @@ struct NvRolloutArgs {
 
 __device__ __forceinline__ float clipf(float q, float hi) { return q < 0.0f ? 0.0f : (q > hi ? hi : q); }
 
-// LT > 0: the lead time is the compile-time constant LT (1..7): the pipeline lives in LT registers and the period loop
-// is unrolled by LT, so that the position of every pipeline element is static (logical element j of the period with
-// offset u sits in pv[(u + j) % LT]) -- no ring indexing, no shifting.  LT == 0: any lead time, ring in shared memory.
+// LT > 0: the lead time is the compile-time constant LT (1..7): the pipeline lives in LT registers, summed and shifted
+// with static indices (LT adds, LT - 1 moves per period) instead of a shared-memory ring with modular indexing.
+// (Unrolling the period loop by LT to avoid even the moves was measured slower: 5x the code, instruction-fetch stalls.)
+// LT == 0: any lead time, ring in shared memory.
 template <int LT>
 __global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kernel(const __grid_constant__ NvDev P,
                                                                      const __grid_constant__ NvRolloutArgs A) {
@@ -506,17 +507,14 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kern
 #pragma unroll
     for (int j = 0; j < (LT > 0 ? LT : 1); j++) pv[j] = 0.0f;
     if (LT > 0) {
-        for (int t0 = 0; t0 < P.T; t0 += LT) {
+        for (int t = 0; t < P.T; t++) {
+            float r = 0.0f;  // np.sum over fewer than 8 float32 values: sequential, oldest first
 #pragma unroll
-            for (int u = 0; u < LT; u++) {
-                const int t = t0 + u;
-                if (t < P.T) {
-                    float r = 0.0f;  // np.sum over fewer than 8 float32 values: sequential, oldest first
+            for (int j = 0; j < LT; j++) r = r + pv[j];
+            const float oq = period(t, r, pv[0]);
 #pragma unroll
-                    for (int j = 0; j < LT; j++) r = r + pv[(u + j) % LT];
-                    pv[u] = period(t, r, pv[u]);  // the slot that just arrived receives the new order (:177-179)
-                }
-            }
+            for (int j = 0; j + 1 < LT; j++) pv[j] = pv[j + 1];  // shift left, append (:177-179): LT - 1 register moves
+            pv[LT - 1] = oq;
         }
     } else {
         for (int t = 0; t < P.T; t++) {
@@ -543,15 +541,8 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kern
             float* o = A.final_obs + e * P.obs_dim;
             o[0] = (float)q.price; o[1] = (float)q.cost; o[2] = fh; o[3] = fk; o[4] = fmu;
             if (LT > 0) {
-                const int u_end = P.T % LT;  // offset of the period after the last one
 #pragma unroll
-                for (int j = 0; j < LT; j++) {
-                    float v = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < LT; k++)
-                        if ((u_end + j) % LT == k) v = pv[k];
-                    o[5 + j] = v;
-                }
+                for (int j = 0; j < LT; j++) o[5 + j] = pv[j];
             } else {
                 for (int j = 0; j < L; j++) {
                     int s = head + j;
