@@ -145,3 +145,14 @@ def test_evaluation_report_is_exact_across_ranks_gloo_world2():
                 assert rep[k] == v, k
             else:
                 assert np.isclose(rep[k], v, rtol=1e-12, atol=1e-9), k
+
+
+def test_kth_smallest_handles_ties_signed_zero_and_extremes():
+    from or_gym_inventory_b200.metrics import kth_smallest
+    rng = np.random.default_rng(3)
+    cases = [np.array([5.0]), np.array([2.0, 2.0, 2.0, 2.0]), np.array([-0.0, 0.0, -1e-300, 1e-300, -1e308, 1e308]),
+             np.round(rng.normal(0, 3, 500)), rng.normal(0, 1e-200, 300), -np.abs(rng.normal(0, 1e6, 257))]
+    for x in cases:
+        srt = np.sort(x)
+        for k in sorted({0, len(x) // 2, len(x) - 1}):
+            assert kth_smallest(torch.from_numpy(x.copy()), k) == srt[k]
