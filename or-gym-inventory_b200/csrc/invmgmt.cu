@@ -1046,8 +1046,46 @@ extern "C" int orgym_invmgmt_export_state(orgym_handle_t h, const void* state_de
     return ORGYM_OK;
 }
 
+// ---- rigorous value bounds of an episode driven by an on-device policy (requests within [0, c_i]) -------------------
+// The reference's dynamics let on-hand inventory of the upstream stages go negative (a stage subtracts its own inbound
+// order, :300), and a negative supplier inventory makes fulfilled orders negative (:265).  Telescoping the pipeline gives
+//   I_i(t) = I0_i - sum of the <= min(L_i, T) orders of stage i still in transit          (i >= 1)
+// so with  Rhi_i = c_i,  Rlo_i = min(0, Ilo_{i+1})  (Rlo_{n-1} = 0: no supplier constraint):
+//   Ilo_i = I0_i - min(L_i,T) * Rhi_i,   Ihi_i = I0_i - min(L_i,T) * Rlo_i,   and for the retailer 0 <= I_0 <= I0_0 + T * c_0.
+// Backlogs grow by at most (request - fulfilled) <= c_i - Rlo_i per period.  *xvar bounds every state value, order, sale
+// and unfulfilled quantity of any period; *xsum bounds the per-episode statistics (sums over periods and stages).
+static void inv_value_bounds(const InvDev& P, double dmax, double* xvar, double* xsum) {
+    const int n = P.n, T = P.T;
+    double Ilo[MAXN + 1], Ihi[MAXN + 1], Rlo[MAXN + 1];
+    double x = dmax;
+    for (int i = n - 1; i >= 0; i--) {
+        Rlo[i] = (i == n - 1) ? 0.0 : std::min(0.0, Ilo[i + 1]);
+        const double Lp = (double)std::min(P.L[i], T);
+        if (i >= 1) {
+            Ilo[i] = (double)P.I0[i] - Lp * (double)P.c[i];
+            Ihi[i] = (double)P.I0[i] - Lp * Rlo[i];
+        } else {
+            Ilo[i] = 0.0;
+            Ihi[i] = (double)P.I0[i] + (double)T * (double)P.c[i];
+        }
+        const double grow = (double)P.c[i] - Rlo[i];                   // request - fulfilled, per period
+        const double Bmax = P.backlog ? (double)T * grow : 0.0;        // B[i+1]
+        const double Umax = (double)P.c[i] + Bmax - Rlo[i];            // cur_i - r_i
+        x = std::max({x, std::fabs(Ilo[i]), std::fabs(Ihi[i]), std::fabs(Rlo[i]), (double)P.c[i], Bmax, Umax});
+    }
+    const double B0 = P.backlog ? (double)T * (dmax - Rlo[0]) : 0.0;   // retail backlog
+    x = std::max({x, B0, dmax + B0 - Rlo[0]});                         // fill, U_0, s0
+    *xvar = x;
+    *xsum = x * (double)T * (double)std::max(n, 1);
+}
+
 // ---- run-time specialised rollout (invmgmt_jit.cu) ------------------------------------------------------------------
 static void inv_jit_spec(const InvDev& P, const std::vector<double>& disc, InvJitSpec* S) {
+    {
+        double xv = 0.0, xs = 0.0;
+        inv_value_bounds(P, (double)P.dem.base + (double)(1LL << P.dem.log2k), &xv, &xs);
+        S->xbound = xv < 9.0e15 ? (long long)xv + 1 : 0;
+    }
     S->n = P.n;
     S->T = P.T;
     S->backlog = P.backlog;
@@ -1108,6 +1146,21 @@ extern "C" int orgym_invmgmt_codegen(const orgym_invmgmt_config_t* cfg, int comp
     S.log2k = 0;
     while ((size_t(1) << S.log2k) < pmf.size()) S.log2k++;
     S.base = (int)base;
+    {
+        InvDev Pb;
+        memset(&Pb, 0, sizeof(Pb));
+        Pb.n = n;
+        Pb.T = S.T;
+        Pb.backlog = S.backlog;
+        for (int i = 0; i < n; i++) {
+            Pb.L[i] = S.L[i];
+            Pb.c[i] = S.c[i];
+            Pb.I0[i] = S.I0[i];
+        }
+        double xv = 0.0, xs = 0.0;
+        inv_value_bounds(Pb, (double)S.base + (double)(1LL << S.log2k), &xv, &xs);
+        S.xbound = xv < 9.0e15 ? (long long)xv + 1 : 0;
+    }
     if (!inv_jit_eligible(S)) {
         orgym_set_error("configuration outside the specialiser's range (1..6 stages, <= 64 periods, sum of lead times <= 40)");
         return ORGYM_E_UNSUPPORTED;
@@ -1209,7 +1262,10 @@ extern "C" int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t en
         dmax = 0;  // trace values were copied to the device at create; bound them through the config-time maximum
         dmax = H->user_dmax;
     }
-    const bool bounded = (double)(P.T + 1) * P.n * (double)(vmax + dmax) * 4.0 < 2147483648.0;
+    double xvar = 0.0, xsum = 0.0;
+    inv_value_bounds(P, (double)dmax, &xvar, &xsum);
+    (void)vmax;
+    const bool bounded = xvar < 1073741824.0 && xsum < 2147483648.0;
     const bool wide = H->wide || in->policy == ORGYM_POLICY_ACTIONS || in->demand_dev != nullptr || !bounded;
     // fast path: kernels specialised for this configuration (register-resident rings, straight-line periods)
     const bool jit_policy = (in->policy == ORGYM_POLICY_BASE_STOCK && A.target_is_int) || in->policy == ORGYM_POLICY_RANDOM;

@@ -13,6 +13,7 @@
 // Reference: inventory_management.py:224-352 (step), benchmark_InvManagementBacklogEnv.py:142-198 (BaseStockAgent).
 #include "invmgmt_jit.cuh"
 
+#include <cmath>
 #include <cstdarg>
 
 #include "jit.cuh"
@@ -47,6 +48,7 @@ int env_int(const char* name, int dflt, int lo, int hi) {
 void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int min_blocks) {
     const int n = S.n, T = S.T;
     const bool bs = policy == 0, bl = S.backlog != 0;
+    const bool exact = inv_jit_profit_is_exact(S) && env_int("ORGYM_INV_JIT_FMA", 1, 0, 1) != 0;
     const char* W4[4] = {"w.x", "w.y", "w.z", "w.w"};
     const char* A4[4] = {"a4.x", "a4.y", "a4.z", "a4.w"};
     o("extern \"C\" __global__ void __launch_bounds__(NTHR, %d) %s(const InvJitArgs A) {", min_blocks, name);
@@ -114,21 +116,34 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
         o("    const int U_0 = fill - s0;");
         for (int i = 0; i < n; i++) o("    const int U_%d = cur_%d - r_%d;", i + 1, i, i);
         // profit (:315-321): elementwise float64, np.sum over m < 8 stages = sequential sum starting from 0.0
-        for (int j = 0; j <= n; j++) {
-            if (j == 0)
-                o("    double tm_%d; { const double s = (double)s0;", j);
-            else
-                o("    double tm_%d; { const double s = (double)r_%d;", j, j - 1);
-            o("      const double rev = %s * s, pc = %s * s, pen = %s * (double)U_%d;", lit(S.up[j]).c_str(),
-              lit(S.uc[j]).c_str(), lit(S.kc[j]).c_str(), j);
-            if (j == n)
-                o("      tm_%d = (rev - pc) - pen; }", j);
-            else
-                o("      const int inv = Ic_%d > 0 ? Ic_%d : 0; const double hold = %s * (double)inv; tm_%d = ((rev - pc) - hold) - pen; }",
-                  j, j, lit(S.hc[j]).c_str(), j);
+        if (exact) {
+            // every operation is exact (inv_jit_profit_is_exact): one fused chain, (up - uc) folded into one coefficient
+            o("    double pr = 0.0;");
+            for (int j = n; j >= 0; j--) {
+                o("    pr = fma(%s, (double)U_%d, pr);", lit(-S.kc[j]).c_str(), j);
+                if (j < n) o("    { const int inv = Ic_%d > 0 ? Ic_%d : 0; pr = fma(%s, (double)inv, pr); }", j, j, lit(-S.hc[j]).c_str());
+                if (j == 0)
+                    o("    pr = fma(%s, (double)s0, pr);", lit(S.up[j] - S.uc[j]).c_str());
+                else
+                    o("    pr = fma(%s, (double)r_%d, pr);", lit(S.up[j] - S.uc[j]).c_str(), j - 1);
+            }
+        } else {
+            for (int j = 0; j <= n; j++) {
+                if (j == 0)
+                    o("    double tm_%d; { const double s = (double)s0;", j);
+                else
+                    o("    double tm_%d; { const double s = (double)r_%d;", j, j - 1);
+                o("      const double rev = %s * s, pc = %s * s, pen = %s * (double)U_%d;", lit(S.up[j]).c_str(),
+                  lit(S.uc[j]).c_str(), lit(S.kc[j]).c_str(), j);
+                if (j == n)
+                    o("      tm_%d = (rev - pc) - pen; }", j);
+                else
+                    o("      const int inv = Ic_%d > 0 ? Ic_%d : 0; const double hold = %s * (double)inv; tm_%d = ((rev - pc) - hold) - pen; }",
+                      j, j, lit(S.hc[j]).c_str(), j);
+            }
+            o("    double pr = 0.0;");
+            for (int j = 0; j <= n; j++) o("    pr = pr + tm_%d;", j);
         }
-        o("    double pr = 0.0;");
-        for (int j = 0; j <= n; j++) o("    pr = pr + tm_%d;", j);
         o("    ret += %s * pr;", lit(S.disc[(size_t)t]).c_str());
         // statistics and state
         o("    s_sales += s0; s_dem += d; s_stock += U_0;");
@@ -165,6 +180,36 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
     o("}");
 }
 }  // namespace
+
+// The profit of a period is a sum of products coefficient x integer.  Every coefficient is a float32 value, i.e. an
+// integer multiple of some power of two; let Q be the smallest such quantum over all coefficients.  Then every product,
+// partial sum and difference that can occur is an integer multiple of Q, and float64 represents all multiples of Q below
+// 2^53 * Q exactly.  If the largest possible magnitude  xbound * sum_j (|up_j| + |uc_j| + |hc_j| + |kc_j|)  stays below
+// that, no operation ever rounds: the reference's evaluation order, any re-association and fused multiply-adds all give
+// the same float64 value, and the generator may use the cheapest form (3 DFMA per stage instead of 4 DMUL + 3 DADD).
+bool inv_jit_profit_is_exact(const InvJitSpec& S) {
+    if (S.xbound <= 0) return false;
+    int qexp = 1 << 20;  // exponent of the finest quantum
+    double mag = 0.0;
+    for (int j = 0; j <= S.n; j++) {
+        const double cs[4] = {S.up[j], S.uc[j], S.hc[j], S.kc[j]};
+        for (double c : cs) {
+            if (!(c >= 0.0) || !std::isfinite(c)) return false;
+            mag += c;
+            if (c == 0.0) continue;
+            if ((double)(float)c != c) return false;  // not a float32 value: no 24-bit significand guarantee
+            int e;
+            double m = std::frexp(c, &e);             // c = m * 2^e, 0.5 <= m < 1
+            long long mi = (long long)std::ldexp(m, 53);  // 53-bit integer significand
+            int tz = 0;
+            while ((mi & 1) == 0) { mi >>= 1; tz++; }
+            qexp = std::min(qexp, e - 53 + tz);       // c = odd * 2^(e - 53 + tz)
+        }
+    }
+    if (qexp == (1 << 20)) return true;               // all coefficients zero
+    const double limit = std::ldexp(1.0, 52 + qexp);  // half of 2^53 * Q: one bit of head-room
+    return mag * (double)S.xbound < limit;
+}
 
 bool inv_jit_eligible(const InvJitSpec& S) {
     if (S.n < 1 || S.n > 6) return false;  // m = n + 1 < 8: the reward sum is numpy's sequential branch

@@ -14,7 +14,10 @@ struct InvJitSpec {  // host-side copy of everything the generator bakes into th
         hc[ORGYM_INV_MAX_STAGES + 1];
     std::vector<double> disc;  // alpha**t
     int log2k, base;           // alias table geometry of the demand distribution
+    long long xbound;          // bound on |on-hand|, |backlog|, |sales| of any stage in any period (0 = unknown)
 };
+// true when every float64 operation of a period's profit is exact for |integers| <= xbound (see invmgmt_jit.cu)
+bool inv_jit_profit_is_exact(const InvJitSpec& S);
 #define INV_JIT_THREADS 128
 // configurations the generator covers (everything else runs the ahead-of-time kernel)
 bool inv_jit_eligible(const InvJitSpec& S);
