@@ -192,3 +192,21 @@ def test_c_host_example_matches_the_python_host(lib, tmp_path):
         tot += e.step(a)[1].sum().item()
     assert abs(tot / 4096 - float(s.group(1))) < 1e-3
     e.close()
+
+
+def test_serial_rollout_specialiser_uses_fused_profit_only_when_provably_exact(lib):
+    """Defaults: float32 coefficients on a 2^-29 grid and values below ~7e4 -> no float64 operation can round -> the
+    generator emits the fused multiply-add chain.  Capacities of a million push the bound past 2^52 * quantum -> it must
+    keep the reference's operation order (4 products + 3 subtractions per stage, sequential sum)."""
+    def source(**kw):
+        P = pkg.InvManagementParams(backlog=True, **kw)
+        keep = []
+        cfg = P.to_c(keep)
+        need = C.c_int64(0)
+        buf = C.create_string_buffer(4 << 20)
+        assert lib.orgym_invmgmt_codegen(C.byref(cfg), 0, buf, len(buf), C.byref(need)) == 0, lib.orgym_last_error()
+        return buf.value.decode()
+    exact = source()
+    assert "fma(" in exact and "tm_0" not in exact
+    big = source(c=[1_000_000, 2_000_000, 2_300_000])
+    assert "fma(" not in big and "tm_0" in big and "pr = pr + tm_3;" in big
