@@ -190,6 +190,10 @@ int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t env_offset, u
  * and, with compile_check != 0, runs it through NVRTC (no GPU needed). */
 int orgym_invmgmt_codegen(const orgym_invmgmt_config_t* cfg, int compile_check, char* buf, int64_t buflen,
                           int64_t* needed);
+/* diagnostic (no GPU needed): rigorous bounds on the integers of an episode driven by an on-device policy (requests within
+ * [0, c_i]): *xvar bounds |on-hand|, |backlog|, |order|, |sales| of any stage and period, *xsum the per-episode statistics.
+ * They decide between int32 and int64 rollout arithmetic and feed the specialiser's proof that the profit never rounds. */
+int orgym_invmgmt_value_bounds(const orgym_invmgmt_config_t* cfg, double* xvar, double* xsum);
 /* 1 once this handle's rollouts run the specialised kernels */
 int orgym_invmgmt_is_specialised(orgym_handle_t h);
 

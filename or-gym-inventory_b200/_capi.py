@@ -142,6 +142,7 @@ SYMBOLS = {
                                        C.POINTER(NetRolloutOut), C.c_void_p]),
     "orgym_invmgmt_codegen": (C.c_int, [C.POINTER(InvConfig), C.c_int, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]),
     "orgym_invmgmt_is_specialised": (C.c_int, [_H]),
+    "orgym_invmgmt_value_bounds": (C.c_int, [C.POINTER(InvConfig), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "orgym_netinv_codegen": (C.c_int, [C.POINTER(NetConfig), C.c_int, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]),
     "orgym_netinv_is_specialised": (C.c_int, [_H]),
     "orgym_errors": (C.c_int, [_H, C.POINTER(C.c_uint32), C.c_int, C.c_void_p]),

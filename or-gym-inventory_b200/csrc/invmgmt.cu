@@ -1182,6 +1182,39 @@ extern "C" int orgym_invmgmt_codegen(const orgym_invmgmt_config_t* cfg, int comp
     return ORGYM_OK;
 }
 
+// diagnostic (no GPU needed): the rigorous bounds inv_value_bounds derives for a configuration driven by an on-device
+// policy -- *xvar bounds every state value / order / sale of any period, *xsum the per-episode statistics.  They decide
+// between int32 and int64 rollouts and feed the specialiser's exactness proof; the CPU suite checks them against
+// brute-force simulation with the oracle.
+extern "C" int orgym_invmgmt_value_bounds(const orgym_invmgmt_config_t* cfg, double* xvar, double* xsum) {
+    ORGYM_REQUIRE(cfg && xvar && xsum && cfg->init_inv && cfg->capacity && cfg->lead_time, "null argument");
+    const int n = cfg->num_stages - 1;
+    ORGYM_REQUIRE(n >= 1 && n <= MAXN && cfg->periods > 0, "bad stage count / horizon");
+    InvDev Pb;
+    memset(&Pb, 0, sizeof(Pb));
+    Pb.n = n;
+    Pb.T = cfg->periods;
+    Pb.backlog = cfg->backlog ? 1 : 0;
+    for (int i = 0; i < n; i++) {
+        Pb.L[i] = (int)cfg->lead_time[i];
+        Pb.c[i] = cfg->capacity[i];
+        Pb.I0[i] = cfg->init_inv[i];
+    }
+    double dmax = 0.0;
+    if (cfg->dist.kind == ORGYM_DIST_USER) {
+        for (int t = 0; t < cfg->dist.user_D_len; t++) dmax = std::max(dmax, std::fabs((double)cfg->dist.user_D[t]));
+    } else {
+        std::vector<double> pmf;
+        int64_t base = 0;
+        if (int rc = orgym_dist_pmf(&cfg->dist, &pmf, &base)) return rc;
+        int log2k = 0;
+        while ((size_t(1) << log2k) < pmf.size()) log2k++;
+        dmax = (double)base + (double)(1LL << log2k);
+    }
+    inv_value_bounds(Pb, dmax, xvar, xsum);
+    return ORGYM_OK;
+}
+
 // 1 once the handle's rollouts run the specialised kernels (they are built on the first eligible rollout)
 extern "C" int orgym_invmgmt_is_specialised(orgym_handle_t h) {
     if (orgym_check_handle(h, FAM_INVMGMT)) return ORGYM_E_INVALID;

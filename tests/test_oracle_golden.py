@@ -154,3 +154,41 @@ def test_netinv_lostsales_class_quirk():
     P = pkg.NetInvMgmtParams(env_config={"backlog": False})
     assert P.backlog is True
     assert pkg.NetInvMgmtParams(backlog=False).backlog is False
+
+
+@pytest.mark.parametrize("case", range(40))
+def test_value_bounds_hold_under_brute_force(case):
+    """orgym_invmgmt_value_bounds (the telescoping bound behind the int32 / int64 rollout decision and the specialiser's
+    exactness proof) against simulation: random and adversarial order sequences within [0, c], long lead times, both
+    backlog modes -- no on-hand inventory, backlog, fulfilled order, sale or unfulfilled quantity may exceed it."""
+    import ctypes as C
+    import or_gym_inventory_b200 as pkg
+    from or_gym_inventory_b200 import _capi
+    from oracle import oracle
+    rng = np.random.default_rng(7000 + case)
+    n = int(rng.integers(1, 7))
+    T = int(rng.integers(3, 61))
+    c = rng.integers(1, 400, n)
+    cfg = dict(periods=T, I0=rng.integers(0, 300, n).tolist(), p=30.0, r=np.sort(rng.uniform(0.5, 25, n + 1))[::-1].round(2).tolist(),
+               k=rng.uniform(0, 1, n + 1).round(2).tolist(), h=rng.uniform(0, 0.5, n).round(2).tolist(), c=c.tolist(),
+               L=rng.integers(0, 25, n).tolist(), dist_param={"mu": float(rng.integers(1, 80))})
+    P = pkg.InvManagementParams(backlog=bool(case % 2), **cfg)
+    keep = []
+    ccfg = P.to_c(keep)
+    xvar, xsum = C.c_double(0), C.c_double(0)
+    assert _capi.lib().orgym_invmgmt_value_bounds(C.byref(ccfg), C.byref(xvar), C.byref(xsum)) == 0
+    worst = 0.0
+    patterns = [rng.integers(0, c + 1, size=(T, n)) for _ in range(6)]
+    patterns += [np.tile(c, (T, 1)), np.zeros((T, n), np.int64),
+                 np.where((np.arange(T)[:, None] // 3) % 2 == 0, c, 0),        # bang-bang orders
+                 np.where(np.arange(n)[None, :] % 2 == 0, c, 0) * np.ones((T, 1), np.int64)]
+    for a in patterns:
+        dem = rng.poisson(cfg["dist_param"]["mu"], size=T).astype(np.int64)
+        if rng.random() < 0.3:
+            dem[:] = 0                                                            # starve the retailer too
+        o = oracle.invmgmt_episode(P, actions=a.astype(np.float64), demand=dem)
+        for key in ("I", "B", "R", "S", "LS"):
+            worst = max(worst, float(np.abs(o[key]).max()))
+        stats = [np.maximum(o["I"][1:], 0).sum(), o["LS"][:, 0].sum(), o["S"][:, 0].sum()]
+        assert max(stats) <= xsum.value
+    assert worst <= xvar.value, (worst, xvar.value, cfg)
