@@ -229,3 +229,14 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_bench_product_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: on a box without a CUDA device the product arm must stop with a clear message, not time the CPU."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
+    assert p.returncode != 0 and "CUDA device" in (p.stderr + p.stdout) and not p.stdout.strip().startswith("{")
