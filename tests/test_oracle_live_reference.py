@@ -1,6 +1,6 @@
 """CPU suite, build container only: the C oracle against the UNMODIFIED reference executed live on random configurations.
 
-The committed golden vectors (tests/golden, oracle/make_golden.py) pin the oracle on 43 fixed cases; here the reference
+The committed golden vectors (tests/golden, oracle/make_golden.py) pin the oracle on 42 fixed cases; here the reference
 itself (/root/reference, imported under the gymnasium shim exactly like make_golden.py does) is run on freshly drawn
 configurations and action sequences and the oracle must reproduce every array bit for bit, including the reference's own
 PCG64 / Poisson demand from the seed.  The GPU box has no /root/reference: the whole module is skipped there (nothing in
