@@ -138,3 +138,21 @@ def test_network_env_oracle_equals_live_reference(mg, case):
         assert np.array_equal(o["S"], g["S"][e][:, cols])
         o2 = oracle.netinv_episode(P, actions=g["actions"][e], seed=seeds[e])       # demand from the seed too
         assert np.array_equal(o2["D"], g["D"][e]) and np.array_equal(o2["reward"], g["reward"][e])
+
+
+def test_committed_golden_vectors_regenerate_identically(mg, tmp_path):
+    """tests/golden/*.npz are exactly what oracle/make_golden.py produces from the reference in this container."""
+    import glob
+    old_out = mg.OUT
+    mg.OUT = str(tmp_path)
+    try:
+        mg.main()
+    finally:
+        mg.OUT = old_out
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+    assert len(files) == len(glob.glob(os.path.join(str(tmp_path), "*.npz"))) >= 42
+    for f in files:
+        a, b = np.load(f, allow_pickle=False), np.load(os.path.join(str(tmp_path), os.path.basename(f)), allow_pickle=False)
+        assert set(a.files) == set(b.files), f
+        for k in a.files:
+            assert np.array_equal(a[k], b[k]), (f, k)
