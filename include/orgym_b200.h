@@ -11,13 +11,20 @@
  *  - plain C: opaque handle, plain pointers and sizes, no torch / C++ types;
  *  - every `*_dev` pointer is DEVICE memory owned by the CALLER (e.g. a torch
  *    CUDA tensor's data_ptr()); the library allocates only its handle and the
- *    small read-only tables uploaded by `*_create` (alias tables, alpha**t);
- *    nothing is allocated or freed on the reset/step/rollout path;
+ *    small read-only tables uploaded by `*_create` (alias tables, alpha**t,
+ *    block partial sums); no device memory is allocated or freed on the
+ *    reset/step/rollout path (the rare configurations whose working set needs
+ *    global scratch take it from the caller: *_rollout_scratch_bytes).  The
+ *    one lazy step is the NVRTC build of a specialised rollout kernel on the
+ *    first eligible orgym_invmgmt_rollout (about 1 s, cubin cached on disk);
+ *    orgym_invmgmt_specialise does it ahead of time;
  *  - all calls are asynchronous and ordered on `stream` (a cudaStream_t passed
  *    as void*; NULL = legacy default stream);
  *  - return value 0 = ok, negative = error (ORGYM_E_*), message available from
  *    orgym_last_error() (thread-local); nothing throws across the ABI;
- *  - a handle is not thread-safe; distinct handles may be used concurrently.
+ *  - a handle is not thread-safe and runs ONE rollout at a time (its block
+ *    partial-sum buffer is shared by rollouts on any stream); distinct handles
+ *    may be used concurrently.
  *  - there is NO CPU fallback: without a CUDA device every compute entry point
  *    returns ORGYM_E_CUDA.
  *
@@ -52,8 +59,9 @@ extern "C" {
 
 /* compile-time limits of this build.  Every configuration inside them runs; the fast paths additionally need the
  * per-CTA working set to fit in shared memory -- serial env step: 128 x obs_dim x (4|8) B observation tile (else the
- * rows are written directly); serial env rollout: 128 x sum(max(L_i,1)) x (4|8) B x (1|2) rings (else a device
- * scratch buffer is allocated on first use); network env: specialised kernels up to 128 reorder links. */
+ * rows are written directly); serial env rollout: 128 x sum(max(L_i,1)) x (4|8) B x (1|2) rings (else the caller
+ * provides a scratch buffer, orgym_invmgmt_rollout_scratch_bytes); network env: specialised kernels up to 128 reorder
+ * links. */
 #define ORGYM_INV_MAX_STAGES 16 /* inventory-holding stages n = m-1 */
 #define ORGYM_INV_MAX_LEAD 64
 #define ORGYM_NV_MAX_LEAD 64
@@ -162,6 +170,8 @@ typedef struct {
     /* optional demand replay: element (e, t) at demand_dev[e*stride_env + t*stride_t]; NULL = sample */
     const int64_t* demand_dev;
     int64_t dem_stride_env, dem_stride_t;
+    /* device scratch of orgym_invmgmt_rollout_scratch_bytes(h) bytes; may be NULL when that is 0 (almost always) */
+    void* scratch_dev;
 } orgym_invmgmt_rollout_in_t;
 
 /* per-episode results; every pointer may be NULL.  stats columns are the reference evaluator's metrics
@@ -182,19 +192,33 @@ int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t env_offset, u
                           const orgym_invmgmt_rollout_in_t* in, const orgym_invmgmt_rollout_out_t* out,
                           void* stream);
 
-/* The fused rollout is additionally specialised per configuration at run time: for 1..6 stages, up to 64 periods and
- * a sum of lead times up to 40, the on-device base-stock (integer levels) and random policies run kernels generated
- * as straight-line CUDA for this config (lead-time rings in registers, every index a literal) and compiled for sm_100a
- * with NVRTC on the first such rollout (cubins cached like the network env's; ORGYM_INV_JIT=0 keeps the ahead-of-time
- * kernel).  Results are bit-identical to the ahead-of-time kernel.  orgym_invmgmt_codegen returns the generated source
- * and, with compile_check != 0, runs it through NVRTC (no GPU needed). */
-int orgym_invmgmt_codegen(const orgym_invmgmt_config_t* cfg, int compile_check, char* buf, int64_t buflen,
-                          int64_t* needed);
+/* bytes of caller-owned device scratch a rollout needs (in->scratch_dev): 0 unless the lead-time rings cannot live in
+ * shared memory (sum of max(L_i,1) beyond ~100) */
+int64_t orgym_invmgmt_rollout_scratch_bytes(orgym_handle_t h);
+
+/* The fused rollout is additionally specialised per configuration AND policy at run time: for 1..6 stages, up to 64
+ * periods and a sum of lead times up to 40, the on-device base-stock (integer levels) and random policies run kernels
+ * generated as straight-line CUDA (lead-time rings in registers, every index, price and base-stock level a literal, so
+ * the compiler folds whatever does not depend on the demand; the profit in integer arithmetic when the generator can
+ * prove that no float64 operation of the reference's expression rounds) and compiled for sm_100a with NVRTC.  Results
+ * are bit-identical to the ahead-of-time kernel.
+ *   orgym_invmgmt_specialise  builds the kernel for in->policy / in->param now (ORGYM_OK), or says why it cannot:
+ *                             ORGYM_E_UNSUPPORTED = configuration / policy outside the specialiser's range,
+ *                             ORGYM_E_CUDA = NVRTC unavailable or the compile failed; orgym_last_error() has the log.
+ *                             Without this call the first eligible rollout builds it (up to 16 variants per handle).
+ *   environment ORGYM_INV_JIT 0 = ahead-of-time kernels only; 1 (default) = specialise, fall back silently to the
+ *                             ahead-of-time kernel; 2 = an eligible rollout that cannot be specialised is an error.
+ *   orgym_invmgmt_codegen     returns the generated source for `in` (NULL = the benchmark's base-stock, levels
+ *                             (L_i+1) * dist.p0) and, with compile_check != 0, runs it through NVRTC (no GPU needed). */
+int orgym_invmgmt_specialise(orgym_handle_t h, const orgym_invmgmt_rollout_in_t* in);
+int orgym_invmgmt_codegen(const orgym_invmgmt_config_t* cfg, const orgym_invmgmt_rollout_in_t* in, int compile_check,
+                          char* buf, int64_t buflen, int64_t* needed);
 /* diagnostic (no GPU needed): rigorous bounds on the integers of an episode driven by an on-device policy (requests within
- * [0, c_i]): *xvar bounds |on-hand|, |backlog|, |order|, |sales| of any stage and period, *xsum the per-episode statistics.
- * They decide between int32 and int64 rollout arithmetic and feed the specialiser's proof that the profit never rounds. */
-int orgym_invmgmt_value_bounds(const orgym_invmgmt_config_t* cfg, double* xvar, double* xsum);
-/* 1 once this handle's rollouts run the specialised kernels */
+ * [0, c_i]): *xvar bounds |on-hand|, |backlog|, |order|, |sales| of any stage and period, *xsum the per-episode statistics,
+ * *profit_mag (may be NULL) the sum of |terms| of one period's profit.  They decide between int32 and int64 rollout
+ * arithmetic and feed the specialiser's proof that the profit never rounds. */
+int orgym_invmgmt_value_bounds(const orgym_invmgmt_config_t* cfg, double* xvar, double* xsum, double* profit_mag);
+/* 1 when the most recent rollout of this handle ran a specialised kernel (or orgym_invmgmt_specialise just built one) */
 int orgym_invmgmt_is_specialised(orgym_handle_t h);
 
 /* ------------------------------------------------------------------------- *
@@ -222,7 +246,9 @@ int32_t orgym_newsvendor_obs_dim(orgym_handle_t h); /* lead_time + 5 (:76) */
 
 /* reset (newsvendor.py:100-123).  fixed_params_dev: NULL = draw (price,cost,h,k,mu) with the five-uniform
  * recipe (:105-111) from the env's Philox stream; else float64[N,5] per-env parameters
- * (options={'fixed_params':…}, benchmark_newsvendor_sb3_rllib.py:276-291). */
+ * (options={'fixed_params':...}, benchmark_newsvendor_sb3_rllib.py:276-291).  Parameters given here stay pinned:
+ * the automatic resets of orgym_newsvendor_step keep them (the benchmark's env re-applies them on every reset)
+ * until the env is reset again with fixed_params_dev == NULL. */
 int orgym_newsvendor_reset(orgym_handle_t h, void* state_dev, int reseed, uint64_t seed, int64_t env_offset,
                            const uint8_t* mask_dev, const double* fixed_params_dev, float* obs_dev, void* stream);
 

@@ -43,7 +43,7 @@ class InvInfo(C.Structure):
 class InvRolloutIn(C.Structure):
     _fields_ = [("policy", C.c_int32), ("param", C.c_double * 4), ("actions", C.c_void_p),
                 ("act_stride_env", C.c_int64), ("act_stride_t", C.c_int64), ("demand", C.c_void_p),
-                ("dem_stride_env", C.c_int64), ("dem_stride_t", C.c_int64)]
+                ("dem_stride_env", C.c_int64), ("dem_stride_t", C.c_int64), ("scratch", C.c_void_p)]
 
 
 class InvRolloutOut(C.Structure):
@@ -140,9 +140,13 @@ SYMBOLS = {
                                             C.c_void_p]),
     "orgym_netinv_rollout": (C.c_int, [_H, C.c_void_p, C.c_uint64, C.c_int64, C.c_uint32, C.POINTER(NetRolloutIn),
                                        C.POINTER(NetRolloutOut), C.c_void_p]),
-    "orgym_invmgmt_codegen": (C.c_int, [C.POINTER(InvConfig), C.c_int, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "orgym_invmgmt_rollout_scratch_bytes": (C.c_int64, [_H]),
+    "orgym_invmgmt_specialise": (C.c_int, [_H, C.POINTER(InvRolloutIn)]),
+    "orgym_invmgmt_codegen": (C.c_int, [C.POINTER(InvConfig), C.POINTER(InvRolloutIn), C.c_int, C.c_char_p, C.c_int64,
+                                        C.POINTER(C.c_int64)]),
     "orgym_invmgmt_is_specialised": (C.c_int, [_H]),
-    "orgym_invmgmt_value_bounds": (C.c_int, [C.POINTER(InvConfig), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "orgym_invmgmt_value_bounds": (C.c_int, [C.POINTER(InvConfig), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                             C.POINTER(C.c_double)]),
     "orgym_netinv_codegen": (C.c_int, [C.POINTER(NetConfig), C.c_int, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]),
     "orgym_netinv_is_specialised": (C.c_int, [_H]),
     "orgym_errors": (C.c_int, [_H, C.POINTER(C.c_uint32), C.c_int, C.c_void_p]),

@@ -135,6 +135,11 @@ int orgym_dist_pmf(const orgym_dist_t* d, std::vector<double>* pmf, int64_t* bas
                 q *= (1.0 - p);
                 tail = q;
             }
+            if (tail > TAIL) {  // numpy's geometric has unbounded support: never truncate-and-renormalise silently
+                orgym_set_error("geometric(p=%g): %.3g of the probability mass lies beyond the 4096-entry alias table "
+                                "(p must be at least about 0.0107)", p, tail);
+                return ORGYM_E_UNSUPPORTED;
+            }
             break;
         }
         default:

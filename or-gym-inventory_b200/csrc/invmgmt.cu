@@ -46,13 +46,18 @@ struct InvHandle {
     const void* hint_state;
     int hint_t;
     long long user_dmax;  // largest value of a user_D trace (0 for sampled demand)
-    void* ring_scratch = nullptr;  // rollout rings that do not fit in shared memory (allocated on first use)
-    size_t ring_scratch_bytes = 0;
-    // run-time specialised rollout kernels (invmgmt_jit.cu), built on the first eligible rollout
+    // run-time specialised rollout kernels (invmgmt_jit.cu): one per (policy, base-stock levels), built by
+    // orgym_invmgmt_specialise or on the first eligible rollout
     std::vector<double> disc_host;
-    int jit_state = 0;  // 0 = not tried, 1 = ready, -1 = unavailable (the ahead-of-time kernel is used)
-    JitKernel jit;              // module + base-stock kernel
-    cudaKernel_t jit_rnd = nullptr;  // random-policy kernel of the same module
+    struct JitVariant {
+        int policy;                 // 0 = base-stock, 1 = random
+        long long target[MAXN];     // base-stock levels baked into the kernel
+        JitKernel k;
+        int failed;                 // compile failed (reason in err): not retried
+        std::string err;
+    };
+    std::vector<JitVariant> jit_variants;
+    int last_rollout_jit = 0;       // the most recent rollout (or specialise call) used / built a specialised kernel
 };
 
 // ---- state layout: field[slot][env], env stride npad -------------------------------------------------------
@@ -919,8 +924,8 @@ extern "C" int orgym_invmgmt_destroy(orgym_handle_t h) {
     {
         DeviceGuard g(H->base.device);
         for (void* p : H->allocs) cudaFree(p);
-        if (H->ring_scratch) cudaFree(H->ring_scratch);
-        if (H->jit.lib) orgym_jit_release(&H->jit);
+        for (auto& v : H->jit_variants)
+            if (v.k.lib) orgym_jit_release(&v.k);
     }
     orgym_handle_base_free(&H->base);
     delete H;
@@ -1054,10 +1059,14 @@ extern "C" int orgym_invmgmt_export_state(orgym_handle_t h, const void* state_de
 //   Ilo_i = I0_i - min(L_i,T) * Rhi_i,   Ihi_i = I0_i - min(L_i,T) * Rlo_i,   and for the retailer 0 <= I_0 <= I0_0 + T * c_0.
 // Backlogs grow by at most (request - fulfilled) <= c_i - Rlo_i per period.  *xvar bounds every state value, order, sale
 // and unfulfilled quantity of any period; *xsum bounds the per-episode statistics (sums over periods and stages).
-static void inv_value_bounds(const InvDev& P, double dmax, double* xvar, double* xsum) {
+struct InvTermBounds {  // per stage j = 0..n: |units sold|, on-hand inventory above zero, unfulfilled quantity
+    double sale[MAXN + 1], inv[MAXN + 1], unf[MAXN + 1];
+};
+static void inv_value_bounds(const InvDev& P, double dmax, double* xvar, double* xsum, InvTermBounds* tb = nullptr) {
     const int n = P.n, T = P.T;
     double Ilo[MAXN + 1], Ihi[MAXN + 1], Rlo[MAXN + 1];
     double x = dmax;
+    if (tb) memset(tb, 0, sizeof(*tb));
     for (int i = n - 1; i >= 0; i--) {
         Rlo[i] = (i == n - 1) ? 0.0 : std::min(0.0, Ilo[i + 1]);
         const double Lp = (double)std::min(P.L[i], T);
@@ -1072,19 +1081,32 @@ static void inv_value_bounds(const InvDev& P, double dmax, double* xvar, double*
         const double Bmax = P.backlog ? (double)T * grow : 0.0;        // B[i+1]
         const double Umax = (double)P.c[i] + Bmax - Rlo[i];            // cur_i - r_i
         x = std::max({x, std::fabs(Ilo[i]), std::fabs(Ihi[i]), std::fabs(Rlo[i]), (double)P.c[i], Bmax, Umax});
+        if (tb) {
+            tb->sale[i + 1] = std::max((double)P.c[i], std::fabs(Rlo[i]));  // fulfilled order r_i in [Rlo_i, c_i]
+            tb->unf[i + 1] = Umax;
+            tb->inv[i] = std::max(0.0, Ihi[i]);
+        }
     }
     const double B0 = P.backlog ? (double)T * (dmax - Rlo[0]) : 0.0;   // retail backlog
     x = std::max({x, B0, dmax + B0 - Rlo[0]});                         // fill, U_0, s0
+    if (tb) tb->sale[0] = tb->unf[0] = dmax + B0 - Rlo[0];
     *xvar = x;
     *xsum = x * (double)T * (double)std::max(n, 1);
 }
 
 // ---- run-time specialised rollout (invmgmt_jit.cu) ------------------------------------------------------------------
-static void inv_jit_spec(const InvDev& P, const std::vector<double>& disc, InvJitSpec* S) {
+static void inv_jit_spec(const InvDev& P, const std::vector<double>& disc, int log2k, int base, int policy,
+                         const long long* target, InvJitSpec* S) {
     {
         double xv = 0.0, xs = 0.0;
-        inv_value_bounds(P, (double)P.dem.base + (double)(1LL << P.dem.log2k), &xv, &xs);
+        InvTermBounds tb;
+        inv_value_bounds(P, (double)base + (double)(1LL << log2k), &xv, &xs, &tb);
         S->xbound = xv < 9.0e15 ? (long long)xv + 1 : 0;
+        for (int j = 0; j <= P.n; j++) {
+            S->sale_bound[j] = tb.sale[j];
+            S->inv_bound[j] = tb.inv[j];
+            S->unf_bound[j] = tb.unf[j];
+        }
     }
     S->n = P.n;
     S->T = P.T;
@@ -1093,6 +1115,7 @@ static void inv_jit_spec(const InvDev& P, const std::vector<double>& disc, InvJi
         S->L[i] = P.L[i];
         S->c[i] = P.c[i];
         S->I0[i] = P.I0[i];
+        S->target[i] = target ? target[i] : 0;
     }
     for (int j = 0; j <= P.n; j++) {
         S->up[j] = P.up[j];
@@ -1101,41 +1124,57 @@ static void inv_jit_spec(const InvDev& P, const std::vector<double>& disc, InvJi
         S->hc[j] = P.hc[j];
     }
     S->disc = disc;
-    S->log2k = P.dem.log2k;
-    S->base = P.dem.base;
+    S->log2k = log2k;
+    S->base = base;
+    S->policy = policy;
 }
 
-static int inv_jit_enabled() {
+// base-stock levels (lead_times + 1) * mu * sf (benchmark_InvManagementBacklogEnv.py:186); *all_int = they are integers
+static void inv_base_stock_targets(const InvDev& P, const double* param, double* target, long long* target_int, int* all_int) {
+    *all_int = 1;
+    for (int i = 0; i < P.n; i++) {
+        target[i] = ((double)(P.L[i] + 1) * param[1]) * param[0];
+        if (!(target[i] == std::floor(target[i]) && std::fabs(target[i]) < 1073741824.0)) *all_int = 0;
+    }
+    for (int i = 0; i < P.n; i++) target_int[i] = *all_int ? (long long)target[i] : 0;
+}
+
+// ORGYM_INV_JIT: 0 = ahead-of-time kernels only, 1 (default) = specialise, fall back silently, 2 = specialise and fail
+// loudly when an eligible rollout cannot get its specialised kernel
+static int inv_jit_mode() {
     const char* v = getenv("ORGYM_INV_JIT");
-    return !(v && v[0] == '0');
+    if (!v) return 1;
+    return v[0] == '0' ? 0 : (v[0] == '2' ? 2 : 1);
 }
 
 // debugging / test aid (no GPU needed): the CUDA source generated for a config; compile_check != 0 also runs it through
 // NVRTC.  Returns ORGYM_E_UNSUPPORTED (with the reason) for configurations the generator does not cover.
-extern "C" int orgym_invmgmt_codegen(const orgym_invmgmt_config_t* cfg, int compile_check, char* buf, int64_t buflen,
-                                     int64_t* needed) {
+extern "C" int orgym_invmgmt_codegen(const orgym_invmgmt_config_t* cfg, const orgym_invmgmt_rollout_in_t* in,
+                                     int compile_check, char* buf, int64_t buflen, int64_t* needed) {
     ORGYM_REQUIRE(cfg && cfg->init_inv && cfg->capacity && cfg->lead_time && cfg->unit_price && cfg->unit_cost &&
                       cfg->demand_cost && cfg->holding_cost,
                   "null argument");
     const int n = cfg->num_stages - 1;
     ORGYM_REQUIRE(n >= 1 && n <= MAXN && cfg->periods > 0, "bad stage count / horizon");
-    InvJitSpec S;
-    S.n = n;
-    S.T = cfg->periods;
-    S.backlog = cfg->backlog ? 1 : 0;
+    InvDev Pb;
+    memset(&Pb, 0, sizeof(Pb));
+    Pb.n = n;
+    Pb.m = n + 1;
+    Pb.T = cfg->periods;
+    Pb.backlog = cfg->backlog ? 1 : 0;
     for (int i = 0; i < n; i++) {
-        S.L[i] = (int)cfg->lead_time[i];
-        S.c[i] = cfg->capacity[i];
-        S.I0[i] = cfg->init_inv[i];
+        Pb.L[i] = (int)cfg->lead_time[i];
+        Pb.c[i] = cfg->capacity[i];
+        Pb.I0[i] = cfg->init_inv[i];
     }
     for (int j = 0; j <= n; j++) {
-        S.up[j] = cfg->unit_price[j];
-        S.uc[j] = cfg->unit_cost[j];
-        S.kc[j] = cfg->demand_cost[j];
-        S.hc[j] = cfg->holding_cost[j];
+        Pb.up[j] = cfg->unit_price[j];
+        Pb.uc[j] = cfg->unit_cost[j];
+        Pb.kc[j] = cfg->demand_cost[j];
+        Pb.hc[j] = cfg->holding_cost[j];
     }
-    S.disc.resize((size_t)S.T);
-    for (int t = 0; t < S.T; t++) S.disc[(size_t)t] = std::pow(cfg->alpha, (double)t);
+    std::vector<double> disc((size_t)Pb.T);
+    for (int t = 0; t < Pb.T; t++) disc[(size_t)t] = std::pow(cfg->alpha, (double)t);
     if (cfg->dist.kind == ORGYM_DIST_USER) {
         orgym_set_error("user-trace demand runs the ahead-of-time kernel");
         return ORGYM_E_UNSUPPORTED;
@@ -1143,24 +1182,27 @@ extern "C" int orgym_invmgmt_codegen(const orgym_invmgmt_config_t* cfg, int comp
     std::vector<double> pmf;
     int64_t base = 0;
     if (int rc = orgym_dist_pmf(&cfg->dist, &pmf, &base)) return rc;
-    S.log2k = 0;
-    while ((size_t(1) << S.log2k) < pmf.size()) S.log2k++;
-    S.base = (int)base;
-    {
-        InvDev Pb;
-        memset(&Pb, 0, sizeof(Pb));
-        Pb.n = n;
-        Pb.T = S.T;
-        Pb.backlog = S.backlog;
-        for (int i = 0; i < n; i++) {
-            Pb.L[i] = S.L[i];
-            Pb.c[i] = S.c[i];
-            Pb.I0[i] = S.I0[i];
-        }
-        double xv = 0.0, xs = 0.0;
-        inv_value_bounds(Pb, (double)S.base + (double)(1LL << S.log2k), &xv, &xs);
-        S.xbound = xv < 9.0e15 ? (long long)xv + 1 : 0;
+    int log2k = 0;
+    while ((size_t(1) << log2k) < pmf.size()) log2k++;
+    // policy to bake in: the caller's, or the benchmark's default base-stock (levels (L+1) * p0, SF = 1)
+    int policy = 0;
+    double param[4] = {1.0, cfg->dist.p0, 0.0, 0.0};
+    if (in) {
+        ORGYM_REQUIRE(in->policy == ORGYM_POLICY_BASE_STOCK || in->policy == ORGYM_POLICY_RANDOM,
+                      "only the on-device base-stock and random policies are specialised");
+        policy = in->policy == ORGYM_POLICY_BASE_STOCK ? 0 : 1;
+        for (int k = 0; k < 4; k++) param[k] = in->param[k];
     }
+    double target[MAXN];
+    long long target_int[MAXN];
+    int all_int = 1;
+    if (policy == 0) inv_base_stock_targets(Pb, param, target, target_int, &all_int);
+    if (!all_int) {
+        orgym_set_error("base-stock levels are not integers: the ahead-of-time kernel evaluates them in float64");
+        return ORGYM_E_UNSUPPORTED;
+    }
+    InvJitSpec S;
+    inv_jit_spec(Pb, disc, log2k, (int)base, policy, target_int, &S);
     if (!inv_jit_eligible(S)) {
         orgym_set_error("configuration outside the specialiser's range (1..6 stages, <= 64 periods, sum of lead times <= 40)");
         return ORGYM_E_UNSUPPORTED;
@@ -1186,7 +1228,8 @@ extern "C" int orgym_invmgmt_codegen(const orgym_invmgmt_config_t* cfg, int comp
 // policy -- *xvar bounds every state value / order / sale of any period, *xsum the per-episode statistics.  They decide
 // between int32 and int64 rollouts and feed the specialiser's exactness proof; the CPU suite checks them against
 // brute-force simulation with the oracle.
-extern "C" int orgym_invmgmt_value_bounds(const orgym_invmgmt_config_t* cfg, double* xvar, double* xsum) {
+extern "C" int orgym_invmgmt_value_bounds(const orgym_invmgmt_config_t* cfg, double* xvar, double* xsum,
+                                          double* profit_mag) {
     ORGYM_REQUIRE(cfg && xvar && xsum && cfg->init_inv && cfg->capacity && cfg->lead_time, "null argument");
     const int n = cfg->num_stages - 1;
     ORGYM_REQUIRE(n >= 1 && n <= MAXN && cfg->periods > 0, "bad stage count / horizon");
@@ -1211,33 +1254,114 @@ extern "C" int orgym_invmgmt_value_bounds(const orgym_invmgmt_config_t* cfg, dou
         while ((size_t(1) << log2k) < pmf.size()) log2k++;
         dmax = (double)base + (double)(1LL << log2k);
     }
-    inv_value_bounds(Pb, dmax, xvar, xsum);
+    InvTermBounds tb;
+    inv_value_bounds(Pb, dmax, xvar, xsum, &tb);
+    if (profit_mag) {  // bound on the sum of |terms| of one period's profit (the specialiser's exactness proof)
+        ORGYM_REQUIRE(cfg->unit_price && cfg->unit_cost && cfg->demand_cost && cfg->holding_cost, "null argument");
+        double mag = 0.0;
+        for (int j = 0; j <= n; j++)
+            mag += (cfg->unit_price[j] + cfg->unit_cost[j]) * tb.sale[j] + cfg->holding_cost[j] * tb.inv[j] +
+                   cfg->demand_cost[j] * tb.unf[j];
+        *profit_mag = mag;
+    }
     return ORGYM_OK;
 }
 
-// 1 once the handle's rollouts run the specialised kernels (they are built on the first eligible rollout)
+// 1 when the most recent rollout ran a specialised kernel (or orgym_invmgmt_specialise just built one)
 extern "C" int orgym_invmgmt_is_specialised(orgym_handle_t h) {
     if (orgym_check_handle(h, FAM_INVMGMT)) return ORGYM_E_INVALID;
-    return ((InvHandle*)h)->jit_state > 0 ? 1 : 0;
+    return ((InvHandle*)h)->last_rollout_jit ? 1 : 0;
 }
 
-// builds the specialised kernels on first use; returns true when they are ready
-static bool inv_jit_ready(InvHandle* H) {
-    if (H->jit_state != 0) return H->jit_state > 0;
-    H->jit_state = -1;
-    if (!inv_jit_enabled() || H->dev.dem.kind == ORGYM_DIST_USER) return false;
-    InvJitSpec S;
-    inv_jit_spec(H->dev, H->disc_host, &S);
-    if (!inv_jit_eligible(S)) return false;
-    std::string err;
-    if (orgym_jit_compile(inv_jit_source(S), "inv_jit_rollout_bs", &H->jit, &err) != 0) return false;
-    if (cudaLibraryGetKernel(&H->jit_rnd, H->jit.lib, "inv_jit_rollout_rnd") != cudaSuccess) {
-        cudaGetLastError();
-        orgym_jit_release(&H->jit);
-        return false;
+// The specialised kernel for (policy, levels): looked up in the handle's small cache, else generated and compiled.
+// Returns ORGYM_OK with *fn set; ORGYM_E_UNSUPPORTED when the configuration / policy is outside the specialiser's range
+// and ORGYM_E_CUDA when NVRTC failed -- both with the reason (NVRTC log included) in orgym_last_error().
+static int inv_jit_get(InvHandle* H, int policy, const long long* target_int, cudaKernel_t* fn) {
+    const InvDev& P = H->dev;
+    for (auto& v : H->jit_variants) {
+        if (v.policy != policy) continue;
+        bool same = true;
+        if (policy == 0)
+            for (int i = 0; i < P.n; i++) same = same && v.target[i] == target_int[i];
+        if (!same) continue;
+        if (v.failed) {
+            orgym_set_error("%s", v.err.c_str());
+            return ORGYM_E_CUDA;
+        }
+        *fn = v.k.fn;
+        return ORGYM_OK;
     }
-    H->jit_state = 1;
-    return true;
+    if (P.dem.kind == ORGYM_DIST_USER) {
+        orgym_set_error("user-trace demand runs the ahead-of-time kernel");
+        return ORGYM_E_UNSUPPORTED;
+    }
+    InvJitSpec S;
+    inv_jit_spec(P, H->disc_host, P.dem.log2k, P.dem.base, policy, target_int, &S);
+    if (!inv_jit_eligible(S)) {
+        orgym_set_error("configuration outside the specialiser's range (1..6 stages, <= 64 periods, sum of lead times <= 40)");
+        return ORGYM_E_UNSUPPORTED;
+    }
+    if (H->jit_variants.size() >= 16) {  // bounded: drop the oldest variant (e.g. a sweep over safety factors)
+        if (H->jit_variants.front().k.lib) orgym_jit_release(&H->jit_variants.front().k);
+        H->jit_variants.erase(H->jit_variants.begin());
+    }
+    InvHandle::JitVariant v;
+    v.policy = policy;
+    for (int i = 0; i < MAXN; i++) v.target[i] = (policy == 0 && i < P.n) ? target_int[i] : 0;
+    v.failed = 0;
+    std::string err;
+    if (orgym_jit_compile(inv_jit_source(S), inv_jit_kernel_name(policy), &v.k, &err) != 0) {
+        v.failed = 1;
+        v.err = "specialising the rollout kernel failed: " + err.substr(0, 800);
+        H->jit_variants.push_back(v);
+        orgym_set_error("%s", v.err.c_str());
+        return ORGYM_E_CUDA;
+    }
+    H->jit_variants.push_back(v);
+    *fn = v.k.fn;
+    return ORGYM_OK;
+}
+
+// true when this request can run a specialised kernel at all (policy, outputs, arithmetic width)
+static bool inv_jit_policy_ok(const orgym_invmgmt_rollout_in_t* in, int target_is_int) {
+    return (in->policy == ORGYM_POLICY_BASE_STOCK && target_is_int) || in->policy == ORGYM_POLICY_RANDOM;
+}
+
+extern "C" int orgym_invmgmt_specialise(orgym_handle_t h, const orgym_invmgmt_rollout_in_t* in) {
+    if (orgym_check_handle(h, FAM_INVMGMT)) return ORGYM_E_INVALID;
+    InvHandle* H = (InvHandle*)h;
+    ORGYM_REQUIRE(in, "null argument");
+    DeviceGuard g(H->base.device);
+    const InvDev& P = H->dev;
+    double target[MAXN];
+    long long target_int[MAXN];
+    int all_int = 1;
+    if (in->policy == ORGYM_POLICY_BASE_STOCK) inv_base_stock_targets(P, in->param, target, target_int, &all_int);
+    if (!inv_jit_policy_ok(in, all_int)) {
+        orgym_set_error("only the on-device base-stock policy with integer levels and the random policy are specialised");
+        return ORGYM_E_UNSUPPORTED;
+    }
+    if (H->wide) {
+        orgym_set_error("wide_state handles run the ahead-of-time int64 kernel");
+        return ORGYM_E_UNSUPPORTED;
+    }
+    cudaKernel_t fn = nullptr;
+    int rc = inv_jit_get(H, in->policy == ORGYM_POLICY_BASE_STOCK ? 0 : 1, target_int, &fn);
+    H->last_rollout_jit = rc == ORGYM_OK;
+    return rc;
+}
+
+// bytes of caller-owned device scratch orgym_invmgmt_rollout needs through in->scratch_dev: 0 unless the lead-time rings
+// of the ahead-of-time kernel cannot live in shared memory (worst case: int64 arithmetic, both rings)
+extern "C" int64_t orgym_invmgmt_rollout_scratch_bytes(orgym_handle_t h) {
+    if (orgym_check_handle(h, FAM_INVMGMT)) return -1;
+    InvHandle* H = (InvHandle*)h;
+    const InvDev& P = H->dev;
+    int64_t rslots = 0;
+    for (int i = 0; i < P.n; i++) rslots += P.L[i] > 0 ? P.L[i] : 1;
+    const size_t tab = P.dem.kind == ORGYM_DIST_USER ? 0 : (size_t(8) << P.dem.log2k);
+    if (tab + (size_t)rslots * ROLL_THREADS * 8 * 2 <= 200 * 1024) return 0;
+    return rslots * round_up(H->base.num_envs, ROLL_THREADS) * 8 * 2;
 }
 
 extern "C" int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t env_offset, uint32_t episode,
@@ -1260,14 +1384,8 @@ extern "C" int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t en
     A.seed = seed;
     A.episode = episode;
     A.policy = in->policy;
-    if (in->policy == ORGYM_POLICY_BASE_STOCK) {
-        A.target_is_int = 1;
-        for (int i = 0; i < P.n; i++) {
-            A.target[i] = ((double)(P.L[i] + 1) * in->param[1]) * in->param[0];  // (lead_times + 1) * mu * sf (:186)
-            if (!(A.target[i] == std::floor(A.target[i]) && std::fabs(A.target[i]) < 1073741824.0)) A.target_is_int = 0;
-            A.target_int[i] = A.target_is_int ? (long long)A.target[i] : 0;
-        }
-    }
+    if (in->policy == ORGYM_POLICY_BASE_STOCK)  // (lead_times + 1) * mu * sf (:186)
+        inv_base_stock_targets(P, in->param, A.target, A.target_int, &A.target_is_int);
     for (int i = 0; i < P.n; i++) {
         A.rroff[i] = A.rslots;
         A.rslots += P.L[i] > 0 ? P.L[i] : 1;
@@ -1301,54 +1419,53 @@ extern "C" int orgym_invmgmt_rollout(orgym_handle_t h, uint64_t seed, int64_t en
     const bool bounded = xvar < 1073741824.0 && xsum < 2147483648.0;
     const bool wide = H->wide || in->policy == ORGYM_POLICY_ACTIONS || in->demand_dev != nullptr || !bounded;
     // fast path: kernels specialised for this configuration (register-resident rings, straight-line periods)
-    const bool jit_policy = (in->policy == ORGYM_POLICY_BASE_STOCK && A.target_is_int) || in->policy == ORGYM_POLICY_RANDOM;
-    if (!wide && jit_policy && !A.reward_traj && !A.final_I && !A.final_B && inv_jit_ready(H)) {
-        InvJitArgs J;
-        memset(&J, 0, sizeof(J));
-        J.N = A.N;
-        J.env_offset = A.env_offset;
-        J.seed = A.seed;
-        J.episode = A.episode;
-        for (int i = 0; i < P.n; i++) J.target[i] = (int32_t)A.target_int[i];
-        J.table = P.dem.table;
-        J.ep_return = A.ep_return;
-        J.stats = A.stats;
-        J.stats32 = A.stats32;
-        J.partials = A.partials;
-        void* args[] = {(void*)&J};
-        const unsigned grid = (unsigned)((A.N + INV_JIT_THREADS - 1) / INV_JIT_THREADS);
-        cudaKernel_t fn = in->policy == ORGYM_POLICY_BASE_STOCK ? H->jit.fn : H->jit_rnd;
-        cudaError_t le = cudaLaunchKernel((const void*)fn, dim3(grid), dim3(INV_JIT_THREADS), args, 0, (cudaStream_t)stream);
-        if (le != cudaSuccess) {
-            orgym_set_error("specialised rollout kernel launch failed: %s", cudaGetErrorString(le));
-            return ORGYM_E_CUDA;
+    H->last_rollout_jit = 0;
+    const int jit_mode = inv_jit_mode();
+    if (jit_mode && !wide && inv_jit_policy_ok(in, A.target_is_int) && !A.reward_traj && !A.final_I && !A.final_B) {
+        cudaKernel_t fn = nullptr;
+        const int jrc = inv_jit_get(H, in->policy == ORGYM_POLICY_BASE_STOCK ? 0 : 1, A.target_int, &fn);
+        if (jrc != ORGYM_OK && jit_mode == 2) return jrc;  // strict: the reason is in orgym_last_error()
+        if (jrc == ORGYM_OK) {
+            InvJitArgs J;
+            memset(&J, 0, sizeof(J));
+            J.N = A.N;
+            J.env_offset = A.env_offset;
+            J.seed = A.seed;
+            J.episode = A.episode;
+            for (int i = 0; i < P.n; i++) J.target[i] = (int32_t)A.target_int[i];
+            J.table = P.dem.table;
+            J.ep_return = A.ep_return;
+            J.stats = A.stats;
+            J.stats32 = A.stats32;
+            J.partials = A.partials;
+            void* args[] = {(void*)&J};
+            const unsigned grid = (unsigned)((A.N + INV_JIT_THREADS - 1) / INV_JIT_THREADS);
+            cudaError_t le = cudaLaunchKernel((const void*)fn, dim3(grid), dim3(INV_JIT_THREADS), args, 0, (cudaStream_t)stream);
+            if (le != cudaSuccess) {
+                orgym_set_error("specialised rollout kernel launch failed: %s", cudaGetErrorString(le));
+                return ORGYM_E_CUDA;
+            }
+            H->last_rollout_jit = 1;
+            if (out->summary_dev) {
+                int nblocks = (int)grid;
+                int rrc = orgym_launch_reduce(H->partials, nblocks, out->summary_dev, (cudaStream_t)stream);
+                if (rrc != ORGYM_OK) return rrc;
+            }
+            return ORGYM_OK;
         }
-        if (out->summary_dev) {
-            int nblocks = (int)grid;
-            int rrc = orgym_launch_reduce(H->partials, nblocks, out->summary_dev, (cudaStream_t)stream);
-            if (rrc != ORGYM_OK) return rrc;
-        }
-        return ORGYM_OK;
     }
     size_t ring = (size_t)A.rslots * ROLL_THREADS * (wide ? 8 : 4);
     size_t smem = (P.dem.kind == ORGYM_DIST_USER ? 0 : (size_t(8) << P.dem.log2k)) +
                   ring * (in->policy == ORGYM_POLICY_BASE_STOCK ? 2 : 1);
-    if (smem > 200 * 1024) {  // rings too long for shared memory: global scratch, generic kernel (correct, not fast)
+    if (smem > 200 * 1024) {  // rings too long for shared memory: caller-owned global scratch, generic kernel (correct, not fast)
         const int64_t stride = round_up(A.N, ROLL_THREADS);
-        const size_t need = (size_t)A.rslots * (size_t)stride * 8 * 2;
-        if (H->ring_scratch_bytes < need) {
-            if (H->ring_scratch) cudaFree(H->ring_scratch);
-            H->ring_scratch = nullptr;
-            H->ring_scratch_bytes = 0;
-            if (cudaMalloc(&H->ring_scratch, need) != cudaSuccess) {
-                cudaGetLastError();
-                orgym_set_error("lead-time rings (sum of lead times = %d) need a %zu-byte device scratch buffer: allocation failed",
-                                P.sumL, need);
-                return ORGYM_E_CUDA;
-            }
-            H->ring_scratch_bytes = need;
+        if (!in->scratch_dev) {
+            orgym_set_error("lead-time rings (sum of lead times = %d) do not fit in shared memory: pass a scratch_dev buffer of "
+                            "orgym_invmgmt_rollout_scratch_bytes() = %lld bytes", P.sumL,
+                            (long long)orgym_invmgmt_rollout_scratch_bytes(h));
+            return ORGYM_E_INVALID;
         }
-        A.ring_scratch = H->ring_scratch;
+        A.ring_scratch = in->scratch_dev;
         A.ring_stride = stride;
         smem = P.dem.kind == ORGYM_DIST_USER ? 0 : (size_t(8) << P.dem.log2k);
     }

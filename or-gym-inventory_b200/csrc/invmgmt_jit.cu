@@ -44,41 +44,68 @@ int env_int(const char* name, int dflt, int lo, int hi) {
     return x < lo || x > hi ? dflt : x;
 }
 
-// policy: 0 = base-stock with integer levels, 1 = uniform random orders on {0..c_i}
+// integer form of a coefficient: c / 2^qexp (exact by construction of qexp)
+long long coef_int(double c, int qexp) { return (long long)std::ldexp(c, -qexp); }
+
+// policy: 0 = base-stock with integer levels (literals: everything that does not depend on the demand -- under
+// base-stock that is the whole trajectory of the stages above the retailer, reference quirk :300 -- is folded by the
+// compiler), 1 = uniform random orders on {0..c_i}
 void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int min_blocks) {
-    const int n = S.n, T = S.T;
+    const int n = S.n, T = S.T, K = 1 << S.log2k;
     const bool bs = policy == 0, bl = S.backlog != 0;
-    const bool exact = inv_jit_profit_is_exact(S) && env_int("ORGYM_INV_JIT_FMA", 1, 0, 1) != 0;
+    int qexp = 0;
+    const bool fma_ok = env_int("ORGYM_INV_JIT_FMA", 1, 0, 1) != 0;
+    const bool exact = fma_ok && inv_jit_profit_is_exact(S) && inv_jit_quantum(S, &qexp);
+    // integer profit (exact only): sum_j (c_j / Q) * x_j in int64, one conversion per period -- or, when the rewards
+    // are undiscounted and even the running sum over all periods provably never rounds, one conversion per episode
+    bool disc_ok = true, undiscounted = true;
+    for (int t = 0; t < T; t++) {
+        const double dq = std::ldexp(S.disc[(size_t)t], qexp);
+        if (S.disc[(size_t)t] != 1.0) undiscounted = false;
+        if (!(dq == 0.0 || std::fabs(dq) > 1e-290)) disc_ok = false;  // scaling by Q must stay exact (no subnormals)
+    }
+    const bool iprofit = exact && disc_ok && env_int("ORGYM_INV_JIT_INT", 1, 0, 1) != 0;
+    const bool episode_sum = iprofit && undiscounted && inv_jit_profit_is_exact(S, T);
     const char* W4[4] = {"w.x", "w.y", "w.z", "w.w"};
     const char* A4[4] = {"a4.x", "a4.y", "a4.z", "a4.w"};
     o("extern \"C\" __global__ void __launch_bounds__(NTHR, %d) %s(const InvJitArgs A) {", min_blocks, name);
-    o("  __shared__ uint2 tab[%d];", 1 << S.log2k);
+    // alias table, one 32-bit word per bucket: (ceil(threshold / K) << log2k) | alias.  The acceptance test of
+    // alias_draw, frac < threshold with frac = w << log2k (low log2k bits zero), is equivalent to
+    // (frac | (K-1)) < packed word; buckets that always accept store their own index as alias.
+    if (S.log2k > 0) {
+        o("  __shared__ unsigned int tab[%d];", K);
+        o("  for (int i = threadIdx.x; i < %d; i += NTHR) {", K);
+        o("    const uint2 te = A.table[i];");
+        o("    const unsigned long long tq = ((unsigned long long)te.x + %uull) >> %d;", (unsigned)(K - 1), S.log2k);
+        o("    tab[i] = tq >= %lluull ? (unsigned int)i : (((unsigned int)tq << %d) | te.y);", 1ull << (32 - S.log2k), S.log2k);
+        o("  }");
+        o("  __syncthreads();");
+    }
     o("  const int tid = threadIdx.x;");
     o("  const long long e = (long long)blockIdx.x * NTHR + tid;");
     o("  const bool valid = e < A.N;");
-    o("  for (int i = tid; i < %d; i += NTHR) tab[i] = A.table[i];", 1 << S.log2k);
-    o("  __syncthreads();");
     o("  const unsigned long long key = A.seed + (unsigned long long)(A.env_offset + e);");
     o("  const unsigned int ep = A.episode;");
     for (int i = 0; i < n; i++) o("  int I_%d = %lld;", i, S.I0[i]);
     if (bl)
         for (int j = 0; j <= n; j++) o("  int B_%d = 0;", j);
     for (int i = 0; i < n; i++) {
-        if (bs) o("  int ps_%d = 0; const int tg_%d = A.target[%d];", i, i, i);
+        if (bs) o("  int ps_%d = 0;", i);
         for (int s = 0; s < S.L[i]; s++) {
             o("  int rr%d_%d = 0;", i, s);
             if (bs) o("  int ar%d_%d = 0;", i, s);
         }
     }
     o("  double ret = 0.0; int s_sales = 0, s_dem = 0, s_stock = 0, s_inv = 0;");
+    if (episode_sum) o("  long long acc = 0;");
     o("  uint4 w = make_uint4(0u, 0u, 0u, 0u);");
     for (int t = 0; t < T; t++) {
         o("  {  // ---- period %d", t);
         // policy
         if (bs) {
             for (int i = 0; i < n; i++) {
-                o("    int q_%d = tg_%d - (I_%d + ps_%d); q_%d = q_%d > 0 ? q_%d : 0; q_%d = q_%d < %lld ? q_%d : %lld;", i, i, i,
-                  i, i, i, i, i, i, S.c[i], i, S.c[i]);
+                o("    int q_%d = %lld - (I_%d + ps_%d); q_%d = q_%d > 0 ? q_%d : 0; q_%d = q_%d < %lld ? q_%d : %lld;", i,
+                  S.target[i], i, i, i, i, i, i, i, S.c[i], i, S.c[i]);
             }
         } else {
             o("    uint4 a4;");
@@ -88,8 +115,14 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
             }
         }
         // demand
-        if ((t & 3) == 0) o("    w = philox_block(key, %uu, ep, STREAM_DEMAND, 0u);", (unsigned)(t >> 2));
-        o("    const int dl = alias_draw(tab, %d, %d, %s);", S.log2k, S.base, W4[t & 3]);
+        if (S.log2k > 0) {
+            if ((t & 3) == 0) o("    w = philox_block(key, %uu, ep, STREAM_DEMAND, 0u);", (unsigned)(t >> 2));
+            o("    int dl; { const unsigned int wv = %s, pe = tab[wv >> %d];", W4[t & 3], 32 - S.log2k);
+            o("      dl = %d + (int)((((wv << %d) | %uu) < pe) ? (wv >> %d) : (pe & %uu)); }", S.base, S.log2k, (unsigned)(K - 1),
+              32 - S.log2k, (unsigned)(K - 1));
+        } else {
+            o("    const int dl = %d;", S.base);
+        }
         // dynamics (:253-312)
         for (int i = 0; i < n; i++) {
             if (bl)
@@ -105,7 +138,10 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
             else
                 o("    int Ic_%d = I_%d + rr%d_%d;", i, i, i, t % S.L[i]);
         }
-        o("    const int d = dl > 0 ? dl : 0;");
+        if (S.base >= 0)
+            o("    const int d = dl;");  // the alias table's support starts at base >= 0: max(0, .) is the identity
+        else
+            o("    const int d = dl > 0 ? dl : 0;");
         if (bl)
             o("    const int fill = d + B_0;");
         else
@@ -116,7 +152,60 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
         o("    const int U_0 = fill - s0;");
         for (int i = 0; i < n; i++) o("    const int U_%d = cur_%d - r_%d;", i + 1, i, i);
         // profit (:315-321): elementwise float64, np.sum over m < 8 stages = sequential sum starting from 0.0
-        if (exact) {
+        if (iprofit) {
+            // every float64 operation of the reference's expression is exact (inv_jit_profit_is_exact), so the profit
+            // equals Q * sum_j (c_j / Q) * x_j with integer coefficients c_j / Q: IMADs instead of I2F + DFMA
+            o("    long long pa = %s;", episode_sum ? "acc" : "0");
+            // terms with the same integer coefficient are summed first (int32, bounded by the sum of their bounds)
+            struct Term { long long c; std::string x; double bound; };
+            std::vector<Term> terms;
+            auto add = [&](long long c, const std::string& x, double bound) {
+                if (c == 0) return;
+                for (auto& tm : terms)
+                    if (tm.c == c && tm.bound + bound < 2147483647.0) {
+                        tm.x += " + " + x;
+                        tm.bound += bound;
+                        return;
+                    }
+                terms.push_back({c, x, bound});
+            };
+            char nm[64];
+            for (int j = 0; j <= n; j++) {
+                snprintf(nm, sizeof(nm), "U_%d", j);
+                add(-coef_int(S.kc[j], qexp), nm, S.unf_bound[j]);
+                if (j < n) {
+                    snprintf(nm, sizeof(nm), "(Ic_%d > 0 ? Ic_%d : 0)", j, j);
+                    add(-coef_int(S.hc[j], qexp), nm, S.inv_bound[j]);
+                }
+                if (j == 0)
+                    snprintf(nm, sizeof(nm), "s0");
+                else
+                    snprintf(nm, sizeof(nm), "r_%d", j - 1);
+                add(coef_int(S.up[j], qexp) - coef_int(S.uc[j], qexp), nm, S.sale_bound[j]);
+            }
+            for (const auto& tm : terms) {
+                const long long ac = tm.c < 0 ? -tm.c : tm.c;
+                const char* op = tm.c < 0 ? "-=" : "+=";
+                if (ac < 2147483648LL) {
+                    o("    pa %s %lldLL * (long long)(%s);", op, ac, tm.x.c_str());  // one IMAD.WIDE
+                    continue;
+                }
+                // coefficient beyond 32 bits: odd part times the integer (int32, by the bound), then a power of two
+                int tz = 0;
+                while (tz < 30 && ((ac >> tz) & 1) == 0) tz++;
+                const long long odd = ac >> tz;
+                if ((double)odd * tm.bound < 2147483647.0)
+                    o("    pa %s %lldLL * (long long)(%lld * (%s));", op, 1LL << tz, odd, tm.x.c_str());
+                else
+                    o("    pa %s %lldLL * (long long)(%s);", op, ac, tm.x.c_str());
+            }
+            if (episode_sum)
+                o("    acc = pa;");
+            else  // |pa| < 2^51 (the proof leaves one bit of head-room): exact int64 -> float64 through the 2^52 + 2^51
+                  // offset (two integer adds and one DADD instead of an I2F.F64.S64 on the quarter-rate pipe)
+                o("    ret += %s * (__longlong_as_double(pa + 0x4338000000000000LL) - 0x1.8p52);",
+                  lit(std::ldexp(S.disc[(size_t)t], qexp)).c_str());
+        } else if (exact) {
             // every operation is exact (inv_jit_profit_is_exact): one fused chain, (up - uc) folded into one coefficient
             o("    double pr = 0.0;");
             for (int j = n; j >= 0; j--) {
@@ -127,6 +216,7 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
                 else
                     o("    pr = fma(%s, (double)r_%d, pr);", lit(S.up[j] - S.uc[j]).c_str(), j - 1);
             }
+            o("    ret += %s * pr;", lit(S.disc[(size_t)t]).c_str());
         } else {
             for (int j = 0; j <= n; j++) {
                 if (j == 0)
@@ -143,8 +233,8 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
             }
             o("    double pr = 0.0;");
             for (int j = 0; j <= n; j++) o("    pr = pr + tm_%d;", j);
+            o("    ret += %s * pr;", lit(S.disc[(size_t)t]).c_str());
         }
-        o("    ret += %s * pr;", lit(S.disc[(size_t)t]).c_str());
         // statistics and state
         o("    s_sales += s0; s_dem += d; s_stock += U_0;");
         for (int i = 0; i < n; i++) o("    I_%d = Ic_%d; s_inv += I_%d > 0 ? I_%d : 0;", i, i, i, i);
@@ -159,6 +249,7 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
         }
         o("  }");
     }
+    if (episode_sum) o("  ret = (double)acc * %s;", lit(std::ldexp(1.0, qexp)).c_str());
     // outputs: identical to the ahead-of-time kernel
     o("  if (valid) {");
     o("    if (A.ep_return) A.ep_return[e] = ret;");
@@ -184,18 +275,16 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
 // The profit of a period is a sum of products coefficient x integer.  Every coefficient is a float32 value, i.e. an
 // integer multiple of some power of two; let Q be the smallest such quantum over all coefficients.  Then every product,
 // partial sum and difference that can occur is an integer multiple of Q, and float64 represents all multiples of Q below
-// 2^53 * Q exactly.  If the largest possible magnitude  xbound * sum_j (|up_j| + |uc_j| + |hc_j| + |kc_j|)  stays below
-// that, no operation ever rounds: the reference's evaluation order, any re-association and fused multiply-adds all give
-// the same float64 value, and the generator may use the cheapest form (3 DFMA per stage instead of 4 DMUL + 3 DADD).
-bool inv_jit_profit_is_exact(const InvJitSpec& S) {
-    if (S.xbound <= 0) return false;
+// 2^53 * Q exactly.  If the largest possible magnitude (with two bits of head-room: below 2^51 * Q)  sum_j (|up_j| + |uc_j|) * |sold_j| + |hc_j| * inv_j + |kc_j| * unf_j
+// (per-term bounds from inv_value_bounds) stays below that, no operation ever rounds: the reference's evaluation order,
+// any re-association, fused multiply-adds and plain integer arithmetic on the coefficients / Q all give the same value,
+// and the generator may use the cheapest form.
+bool inv_jit_quantum(const InvJitSpec& S, int* qexp_out) {
     int qexp = 1 << 20;  // exponent of the finest quantum
-    double mag = 0.0;
     for (int j = 0; j <= S.n; j++) {
         const double cs[4] = {S.up[j], S.uc[j], S.hc[j], S.kc[j]};
         for (double c : cs) {
             if (!(c >= 0.0) || !std::isfinite(c)) return false;
-            mag += c;
             if (c == 0.0) continue;
             if ((double)(float)c != c) return false;  // not a float32 value: no 24-bit significand guarantee
             int e;
@@ -206,9 +295,26 @@ bool inv_jit_profit_is_exact(const InvJitSpec& S) {
             qexp = std::min(qexp, e - 53 + tz);       // c = odd * 2^(e - 53 + tz)
         }
     }
-    if (qexp == (1 << 20)) return true;               // all coefficients zero
-    const double limit = std::ldexp(1.0, 52 + qexp);  // half of 2^53 * Q: one bit of head-room
-    return mag * (double)S.xbound < limit;
+    if (qexp == (1 << 20)) qexp = 0;                  // all coefficients zero
+    *qexp_out = qexp;
+    return true;
+}
+
+double inv_jit_profit_mag(const InvJitSpec& S) {
+    double mag = 0.0;
+    for (int j = 0; j <= S.n; j++)
+        mag += (S.up[j] + S.uc[j]) * S.sale_bound[j] + S.hc[j] * S.inv_bound[j] + S.kc[j] * S.unf_bound[j];
+    return mag;
+}
+
+bool inv_jit_profit_is_exact(const InvJitSpec& S, int periods) {
+    if (S.xbound <= 0) return false;
+    int qexp = 0;
+    if (!inv_jit_quantum(S, &qexp)) return false;
+    for (int j = 0; j <= S.n; j++)
+        if (!(S.sale_bound[j] >= 0.0 && S.inv_bound[j] >= 0.0 && S.unf_bound[j] >= 0.0)) return false;
+    const double limit = std::ldexp(1.0, 51 + qexp);  // a quarter of 2^53 * Q: |profit / Q| < 2^51, two bits of head-room
+    return inv_jit_profit_mag(S) * (double)(periods > 1 ? periods : 1) < limit;
 }
 
 bool inv_jit_eligible(const InvJitSpec& S) {
@@ -223,13 +329,15 @@ bool inv_jit_eligible(const InvJitSpec& S) {
     return sumL <= 40;  // two register-resident rings of sum(L) entries each
 }
 
+const char* inv_jit_kernel_name(int policy) { return policy == 0 ? "inv_jit_rollout_bs" : "inv_jit_rollout_rnd"; }
+
 std::string inv_jit_source(const InvJitSpec& S) {
     Src o;
     o.s += orgym_jit_device_rng_src();
     o.s += orgym_jit_inv_args_src();
     o("#define NTHR %d", INV_JIT_THREADS);
-    const int mb = env_int("ORGYM_INV_JIT_MINBLOCKS", 4, 1, 8);
-    emit_kernel(o, S, "inv_jit_rollout_bs", 0, mb);
-    emit_kernel(o, S, "inv_jit_rollout_rnd", 1, mb);
+    // base-stock keeps only the retailer's state per thread (the rest is folded): room for more resident CTAs
+    const int mb = env_int("ORGYM_INV_JIT_MINBLOCKS", S.policy == 0 ? 8 : 4, 1, 12);
+    emit_kernel(o, S, inv_jit_kernel_name(S.policy), S.policy, mb);
     return o.s;
 }

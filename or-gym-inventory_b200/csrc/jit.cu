@@ -8,6 +8,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -28,6 +29,7 @@ struct Nvrtc {
     int (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
     int (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
     int (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    int (*Version)(int*, int*) = nullptr;
     bool ok = false;
 };
 Nvrtc g_nvrtc;
@@ -51,6 +53,7 @@ void load_nvrtc() {
     SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
     SYM(GetProgramLog, "nvrtcGetProgramLog")
     SYM(DestroyProgram, "nvrtcDestroyProgram")
+    SYM(Version, "nvrtcVersion")
 #undef SYM
     g_nvrtc.ok = true;
 }
@@ -84,21 +87,39 @@ int orgym_jit_compile(const std::string& src, const char* name, JitKernel* out, 
     return 0;
 }
 
-// ---- cubin cache: in-process map + files under $ORGYM_JIT_CACHE (default ~/.cache/orgym_b200), keyed by a 64-bit
-// FNV-1a hash of the generated source (which embeds every constant of the config) and the NVRTC version ------------
+// ---- cubin cache: in-process map + files under $ORGYM_JIT_CACHE (default ~/.cache/orgym_b200) -----------------------
+// Key: 64-bit FNV-1a hash of the generated source (which embeds every constant of the config), its length, the NVRTC
+// version actually loaded and the compile options.  A cache file starts with a header repeating hash / source length /
+// cubin length, checked on load; the directory is created 0700 and ignored unless it belongs to the current user and is
+// not writable by anyone else (a cubin is code that will run on the GPU: never load one somebody else could have planted).
+static const char* const k_nvrtc_opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "-lineinfo", "--std=c++17",
+                                           "-default-device"};
+static const int k_nvrtc_nopts = 5;
 static std::mutex g_cache_mu;
 static std::map<std::string, std::vector<char>> g_cubin_cache;
 
-static std::string cache_key(const std::string& src) {
-    uint64_t h = 1469598103934665603ULL;
+static uint64_t fnv1a(const std::string& src, uint64_t h = 1469598103934665603ULL) {
     for (unsigned char c : src) {
         h ^= c;
         h *= 1099511628211ULL;
     }
-    char buf[64];
-    snprintf(buf, sizeof(buf), "%016llx_%zu_nvrtc12", (unsigned long long)h, src.size());
+    return h;
+}
+static std::string cache_key(const std::string& src) {
+    std::call_once(g_once, load_nvrtc);
+    int vmaj = 0, vmin = 0;
+    if (g_nvrtc.ok) g_nvrtc.Version(&vmaj, &vmin);
+    std::string opts;
+    for (int i = 0; i < k_nvrtc_nopts; i++) opts += std::string(k_nvrtc_opts[i]) + " ";
+    char buf[96];
+    snprintf(buf, sizeof(buf), "%016llx_%zu_nvrtc%d.%d_%08x", (unsigned long long)fnv1a(src), src.size(), vmaj, vmin,
+             (unsigned)(fnv1a(opts) & 0xffffffffu));
     return buf;
 }
+struct CacheHeader {
+    char magic[8];  // "ORGYMJIT"
+    uint64_t src_hash, src_len, cubin_len;
+};
 static std::string cache_dir() {
     const char* d = getenv("ORGYM_JIT_CACHE");
     if (d && d[0]) return d[0] == '0' && d[1] == 0 ? std::string() : std::string(d);
@@ -106,7 +127,13 @@ static std::string cache_dir() {
     if (!home || !home[0]) return std::string();
     return std::string(home) + "/.cache/orgym_b200";
 }
-static bool cache_load(const std::string& key, std::vector<char>* out) {
+// the directory exists, belongs to us and nobody else may write into it
+static bool cache_dir_trusted(const std::string& dir) {
+    struct stat st;
+    if (stat(dir.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) return false;
+    return st.st_uid == geteuid() && (st.st_mode & (S_IWGRP | S_IWOTH)) == 0;
+}
+static bool cache_load(const std::string& key, const std::string& src, std::vector<char>* out) {
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         auto it = g_cubin_cache.find(key);
@@ -116,16 +143,15 @@ static bool cache_load(const std::string& key, std::vector<char>* out) {
         }
     }
     std::string dir = cache_dir();
-    if (dir.empty()) return false;
+    if (dir.empty() || !cache_dir_trusted(dir)) return false;
     FILE* f = fopen((dir + "/" + key + ".cubin").c_str(), "rb");
     if (!f) return false;
-    fseek(f, 0, SEEK_END);
-    long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    bool ok = n > 0;
+    CacheHeader hd;
+    bool ok = fread(&hd, 1, sizeof(hd), f) == sizeof(hd) && memcmp(hd.magic, "ORGYMJIT", 8) == 0 &&
+              hd.src_hash == fnv1a(src) && hd.src_len == src.size() && hd.cubin_len > 0 && hd.cubin_len < (1u << 28);
     if (ok) {
-        out->resize((size_t)n);
-        ok = fread(out->data(), 1, (size_t)n, f) == (size_t)n;
+        out->resize((size_t)hd.cubin_len);
+        ok = fread(out->data(), 1, out->size(), f) == out->size() && fgetc(f) == EOF;
     }
     fclose(f);
     if (ok) {
@@ -134,7 +160,7 @@ static bool cache_load(const std::string& key, std::vector<char>* out) {
     }
     return ok;
 }
-static void cache_store(const std::string& key, const std::vector<char>& cubin) {
+static void cache_store(const std::string& key, const std::string& src, const std::vector<char>& cubin) {
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         g_cubin_cache[key] = cubin;
@@ -142,12 +168,18 @@ static void cache_store(const std::string& key, const std::vector<char>& cubin) 
     std::string dir = cache_dir();
     if (dir.empty()) return;
     std::string parent = dir.substr(0, dir.find_last_of('/'));
-    mkdir(parent.c_str(), 0755);
-    mkdir(dir.c_str(), 0755);
+    mkdir(parent.c_str(), 0700);
+    mkdir(dir.c_str(), 0700);
+    if (!cache_dir_trusted(dir)) return;
     std::string tmp = dir + "/" + key + ".tmp" + std::to_string((long)getpid());
     FILE* f = fopen(tmp.c_str(), "wb");
     if (!f) return;
-    bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    CacheHeader hd;
+    memcpy(hd.magic, "ORGYMJIT", 8);
+    hd.src_hash = fnv1a(src);
+    hd.src_len = src.size();
+    hd.cubin_len = cubin.size();
+    bool ok = fwrite(&hd, 1, sizeof(hd), f) == sizeof(hd) && fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
     fclose(f);
     if (ok)
         rename(tmp.c_str(), (dir + "/" + key + ".cubin").c_str());  // atomic publish
@@ -159,9 +191,9 @@ static int nvrtc_compile(const std::string& src, std::vector<char>* cubin_out, s
 
 static int compile_to_cubin(const std::string& src, std::vector<char>* cubin_out, std::string* err) {
     const std::string key = cache_key(src);
-    if (cache_load(key, cubin_out)) return 0;
+    if (cache_load(key, src, cubin_out)) return 0;
     int rc = nvrtc_compile(src, cubin_out, err);
-    if (rc == 0) cache_store(key, *cubin_out);
+    if (rc == 0) cache_store(key, src, *cubin_out);
     return rc;
 }
 
@@ -176,8 +208,7 @@ static int nvrtc_compile(const std::string& src, std::vector<char>* cubin_out, s
         *err = "nvrtcCreateProgram failed";
         return 2;
     }
-    const char* opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "-lineinfo", "--std=c++17", "-default-device"};
-    int rc = g_nvrtc.CompileProgram(prog, 5, opts);
+    int rc = g_nvrtc.CompileProgram(prog, k_nvrtc_nopts, k_nvrtc_opts);
     if (rc != 0) {
         size_t n = 0;
         g_nvrtc.GetProgramLogSize(prog, &n);

@@ -36,6 +36,10 @@ struct NvHandle {
 };
 
 // state layout (field[slot][env], stride npad): [key u64][params f64 x5][pipe f32 x L][step i32][episode u32]
+// Bit 31 of the episode word marks an env whose parameters were pinned by reset(options={'fixed_params': ...}): its
+// automatic resets keep them (benchmark_newsvendor_sb3_rllib.py:276-291 re-applies fixed_params on every reset)
+// instead of drawing new ones.  The Philox counters use the low 31 bits only.
+#define NV_EP_FIXED 0x80000000u
 struct NvState {
     uint64_t* key;
     double* par;
@@ -183,9 +187,9 @@ __global__ void __launch_bounds__(256) nv_reset_kernel(const __grid_constant__ N
             st.key[e] = key;
         } else {
             key = st.key[e];
-            ep = st.episode[e] + 1;
+            ep = ((st.episode[e] & ~NV_EP_FIXED) + 1) & ~NV_EP_FIXED;
         }
-        st.episode[e] = ep;
+        st.episode[e] = ep | (fixed ? NV_EP_FIXED : 0u);
         NvParams q;
         if (fixed) {
             q.price = fixed[e * 5 + 0]; q.cost = fixed[e * 5 + 1]; q.h = fixed[e * 5 + 2]; q.k = fixed[e * 5 + 3];
@@ -251,7 +255,9 @@ __global__ void __launch_bounds__(ORGYM_TILE, NV_STEP_MINB) nv_step_kernel(const
             for (int j = 0; j < P.L; j++) cp_async4(row + 5 + j, pp + (size_t)j * A.npad);
         }
         int sc = st.step[e];
-        uint32_t ep = st.episode[e];
+        const uint32_t epw = st.episode[e];
+        const uint32_t pinned = epw & NV_EP_FIXED;
+        uint32_t ep = epw & ~NV_EP_FIXED;
         uint64_t key = st.key[e];
         NvParams q;
         q.price = st.par[0 * A.npad + e]; q.cost = st.par[1 * A.npad + e]; q.h = st.par[2 * A.npad + e];
@@ -261,10 +267,12 @@ __global__ void __launch_bounds__(ORGYM_TILE, NV_STEP_MINB) nv_step_kernel(const
             do_step = false;
             cp_async_wait_all();
             if (A.autoreset == ORGYM_AUTORESET_NEXT_STEP) {
-                ep += 1;
-                q = nv_draw_params(P, key, ep);
-                st.episode[e] = ep;
-                for (int z = 0; z < 5; z++) st.par[(size_t)z * A.npad + e] = (&q.price)[z];
+                ep = (ep + 1) & ~NV_EP_FIXED;
+                if (!pinned) {
+                    q = nv_draw_params(P, key, ep);
+                    for (int z = 0; z < 5; z++) st.par[(size_t)z * A.npad + e] = (&q.price)[z];
+                }
+                st.episode[e] = ep | pinned;
                 for (int j = 0; j < P.L; j++) st.pipe[(size_t)j * A.npad + e] = 0.0f;
                 st.step[e] = 0;
                 for (int z = 0; z < 5; z++) row[z] = (float)(&q.price)[z];
@@ -303,10 +311,12 @@ __global__ void __launch_bounds__(ORGYM_TILE, NV_STEP_MINB) nv_step_kernel(const
             } else {
                 if (A.final_obs)
                     for (int z = 0; z < W; z++) A.final_obs[e * W + z] = row[z];
-                ep += 1;
-                q = nv_draw_params(P, key, ep);
-                st.episode[e] = ep;
-                for (int z = 0; z < 5; z++) st.par[(size_t)z * A.npad + e] = (&q.price)[z];
+                ep = (ep + 1) & ~NV_EP_FIXED;
+                if (!pinned) {
+                    q = nv_draw_params(P, key, ep);
+                    for (int z = 0; z < 5; z++) st.par[(size_t)z * A.npad + e] = (&q.price)[z];
+                }
+                st.episode[e] = ep | pinned;
                 for (int j = 0; j < P.L; j++) st.pipe[(size_t)j * A.npad + e] = 0.0f;
                 st.step[e] = 0;
                 for (int z = 0; z < 5; z++) row[z] = (float)(&q.price)[z];

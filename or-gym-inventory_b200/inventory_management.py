@@ -275,9 +275,31 @@ class InvManagementMasterEnv(BatchedEnv):
 
     @property
     def rollout_specialised(self):
-        """True once `rollout` runs the kernels generated for this configuration (built on the first eligible rollout:
-        on-device base-stock with integer levels or random policy, sampled demand, no trajectory outputs)."""
+        """True when the most recent `rollout` ran a kernel generated for this configuration and policy (on-device
+        base-stock with integer levels or random policy, sampled demand, no trajectory outputs)."""
         return bool(_capi.lib().orgym_invmgmt_is_specialised(self._h))
+
+    def _policy_struct(self, policy, safety_factor=1.0, mu=None):
+        rin = _capi.InvRolloutIn()
+        if policy == "base_stock":
+            rin.policy = POLICY_BASE_STOCK
+            rin.param[0] = float(safety_factor)
+            rin.param[1] = float(self.params.dist_param.get("mu", 10) if mu is None else mu)
+        elif policy == "random":
+            rin.policy = POLICY_RANDOM
+        elif policy == "actions":
+            rin.policy = POLICY_ACTIONS
+        else:
+            raise ValueError(f"unknown policy {policy!r}")
+        return rin
+
+    def specialise(self, policy="base_stock", *, safety_factor=1.0, mu=None):
+        """Build the rollout kernel specialised for this configuration and policy now (NVRTC, about a second; cached on
+        disk) instead of inside the first rollout.  Raises OrgymError with the reason (NVRTC log included) when the
+        configuration or policy is outside the specialiser's range or the compile fails."""
+        rin = self._policy_struct(policy, safety_factor, mu)
+        _capi.check(_capi.lib().orgym_invmgmt_specialise(self._h, C.byref(rin)))
+        return True
 
     # -- batched views of the attributes the reference agents read ---------------------------------------------------
     def export_state(self):
@@ -311,23 +333,19 @@ class InvManagementMasterEnv(BatchedEnv):
         torch = _torch()
         P = self.params
         N, T, n, m = self.num_envs, int(P.num_periods), P.num_stages - 1, P.num_stages
-        rin = _capi.InvRolloutIn()
+        rin = self._policy_struct(policy, safety_factor, mu)
         keep = []
-        if policy == "base_stock":
-            rin.policy = POLICY_BASE_STOCK
-            rin.param[0] = float(safety_factor)
-            rin.param[1] = float(P.dist_param.get("mu", 10) if mu is None else mu)
-        elif policy == "random":
-            rin.policy = POLICY_RANDOM
-        elif policy == "actions":
-            rin.policy = POLICY_ACTIONS
+        if "_ring_scratch" not in self.__dict__:      # caller-owned scratch for very long lead-time rings (rare)
+            nb = int(_capi.lib().orgym_invmgmt_rollout_scratch_bytes(self._h))
+            self._ring_scratch = torch.empty(nb, dtype=torch.uint8, device=self.device) if nb > 0 else None
+        if self._ring_scratch is not None:
+            rin.scratch = self._ring_scratch.data_ptr()
+        if policy == "actions":
             shape = (T, N, n) if time_major else (N, T, n)
             a = self._to_dev(actions, torch.int64, shape)
             keep.append(a)
             rin.actions = a.data_ptr()
             rin.act_stride_env, rin.act_stride_t = (n, N * n) if time_major else (T * n, n)
-        else:
-            raise ValueError(f"unknown policy {policy!r}")
         if demand is not None:
             d = self._to_dev(demand, torch.int64, (T, N) if time_major else (N, T))
             keep.append(d)

@@ -285,7 +285,7 @@ YIELD_SPEC = {  # factories with yield < 1, fractional I0, a retailer serving tw
 }
 
 
-def run_net(make_env, seeds, policy, rng_seed=0, user_trace=None):
+def run_net(make_env, seeds, policy, rng_seed=0, extra_meta=None):
     eps = []
     arng = np.random.default_rng(rng_seed)
     spec = None
@@ -305,8 +305,8 @@ def run_net(make_env, seeds, policy, rng_seed=0, user_trace=None):
                 if const is None:
                     const = (high.copy() * float(policy[5:])).astype(np.float32)
                 a = const
-            elif policy == "random":
-                a = arng.uniform(0, 0.12, size=E).astype(np.float32) * high
+            elif policy.startswith("random"):
+                a = arng.uniform(0, float(policy[6:] or 0.12), size=E).astype(np.float32) * high
             elif policy == "wild":
                 a = (arng.uniform(-0.05, 0.25, size=E) * high).astype(np.float32)
                 a[arng.random(E) < 0.3] = np.float32(arng.integers(0, 60)) + np.float32(0.5)  # banker's-rounding ties
@@ -330,7 +330,8 @@ def run_net(make_env, seeds, policy, rng_seed=0, user_trace=None):
         retail_links=[[int(a), int(b)] for a, b in e0.retail_links],
         network_links=[[int(a), int(b)] for a, b in e0.network_links], obs_dim=int(e0.obs_dim),
         action_high=float(e0.action_space.high[0]),
-        obs_low=[float(x) for x in e0.observation_space.low], obs_high=[float(x) for x in e0.observation_space.high])))
+        obs_low=[float(x) for x in e0.observation_space.low], obs_high=[float(x) for x in e0.observation_space.high],
+        **(extra_meta or {}))))
     return out
 
 
@@ -358,6 +359,57 @@ def net_cases():
         return f
     cases["net_yield_backlog_random"] = (mk_yield(True), [4, 5], "random")
     cases["net_yield_lost_wild"] = (mk_yield(False), [4, 5], "wild")
+
+    # user_D / sample_path (network_management.py:240-267): a recorded trace drives the market link unless
+    # sample_path is set, in which case the link samples from its demand_dist_func as usual.  Fractional trace
+    # entries exercise the max(0, int(round(.))) of step (:540); the trace repeats its last entry past its end (:255).
+    trace = [17, 0, 23.5, 8, 31, 4.5, 12, 12, 0, 40, 19, 22, 6, 2.5, 27, 15, 9, 33, 18, 1, 0, 21, 14, 29, 7, 11, 25, 3, 16, 20]
+    ud = [[1, 0, trace]]
+
+    def mk_user(backlog, sp):
+        return lambda: M(backlog=backlog, user_D={(1, 0): list(trace)}, sample_path={(1, 0): sp})
+    cases["net_userD_backlog_random"] = (mk_user(True, False), [31, 32], "random", dict(user_D=ud, sample_path=[[1, 0, False]]))
+    cases["net_userD_lost_const0.1"] = (mk_user(False, False), [33], "const0.1", dict(user_D=ud, sample_path=[[1, 0, False]]))
+    cases["net_userD_samplepath_backlog_random"] = (mk_user(True, True), [34, 35], "random",
+                                                    dict(user_D=ud, sample_path=[[1, 0, True]]))
+
+    def mk_yield_user():  # four retail links: two replay traces (one of them with sample_path -> sampled), two sample
+        holder = [None]
+        g = build_graph(YIELD_SPEC, holder)
+        env = M(graph=g, backlog=True, num_periods=16, alpha=0.98,
+                user_D={(2, 9): list(trace[:16]), (1, 9): list(trace[3:19])}, sample_path={(2, 9): False, (1, 9): True})
+        holder[0] = env
+        return env
+    cases["net_yield_userD_backlog_wild"] = (mk_yield_user, [36, 37], "wild",
+                                             dict(user_D=[[2, 9, trace[:16]], [1, 9, trace[3:19]]],
+                                                  sample_path=[[2, 9, False], [1, 9, True]]))
+
+    # BASELINE config 5's synthetic 64-node network, built by the product's own generator and handed to the reference
+    # as a networkx graph (classification :146-195 and the step at 88 reorder links / 44 nodes)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from or_gym_inventory_b200.network_management import synthetic_graph
+
+    def spec_of(g):
+        nodes = [[int(j), {k: float(v) for k, v in g.nodes[j].items()}] for j in g.nodes()]
+        edges = []
+        for u, v in g.edges():
+            d = g.edges[u, v]
+            a = {k: float(d[k]) for k in ("L", "p", "g", "b") if k in d}
+            if "dist_param" in d:
+                a["dist_param"] = {k: float(x) for k, x in d["dist_param"].items()}
+            edges.append([int(u), int(v), a])
+        return {"nodes": nodes, "edges": edges}
+
+    def mk_synth(backlog):
+        def f():
+            holder = [None]
+            g = build_graph(spec_of(synthetic_graph(64)), holder)   # Poisson samplers bound to the env's own RNG
+            env = M(graph=g, backlog=backlog, num_periods=30)
+            holder[0] = env
+            return env
+        return f
+    cases["net_synth64_lost_random"] = (mk_synth(False), [12000, 12001], "random0.08", dict(synthetic_graph_seed=64))
+    cases["net_synth64_backlog_const0.05"] = (mk_synth(True), [12002], "const0.05", dict(synthetic_graph_seed=64))
     return cases
 
 
@@ -378,8 +430,8 @@ def main():
         out = run_newsvendor(cfg, seeds, pol, fixed=fixed)
         out["meta"] = np.array(json.dumps(dict(cfg=cfg, policy=pol, fixed=fixed)))
         total += save(name, out)
-    for name, (mk, seeds, pol) in net_cases().items():
-        total += save(name, run_net(mk, seeds, pol))
+    for name, (mk, seeds, pol, *extra) in net_cases().items():
+        total += save(name, run_net(mk, seeds, pol, extra_meta=extra[0] if extra else None))
     # known-answer values quoted in SURVEY.md §8c (sanity: this script reproduces them)
     g = np.load(os.path.join(OUT, "invmgmt_default_backlog_basestock.npz"))
     assert g["D"][0].tolist() == [19, 16, 16, 27, 25, 17, 16, 11, 19, 26, 20, 31, 24, 22, 19, 19, 16, 15, 23, 19, 20,

@@ -100,13 +100,16 @@ def test_serial_rollout_specialiser_compiles_without_gpu(lib, kind):
     P = pkg.InvManagementParams(**cfgs[kind])
     keep = []
     cfg = P.to_c(keep)
-    need = C.c_int64(0)
-    buf = C.create_string_buffer(1 << 20)
-    rc = lib.orgym_invmgmt_codegen(C.byref(cfg), 1, buf, len(buf), C.byref(need))
-    assert rc == 0, lib.orgym_last_error()
-    src = buf.value.decode()
-    assert len(src) == need.value and "inv_jit_rollout_bs" in src and "inv_jit_rollout_rnd" in src
-    assert src.count("// ---- period") == 2 * P.num_periods
+    rnd = _capi.InvRolloutIn()
+    rnd.policy = 2
+    for rin, name in ((None, "inv_jit_rollout_bs"), (C.byref(rnd), "inv_jit_rollout_rnd")):
+        need = C.c_int64(0)
+        buf = C.create_string_buffer(1 << 20)
+        rc = lib.orgym_invmgmt_codegen(C.byref(cfg), rin, 1, buf, len(buf), C.byref(need))
+        assert rc == 0, lib.orgym_last_error()
+        src = buf.value.decode()
+        assert len(src) == need.value and name in src
+        assert src.count("// ---- period") == P.num_periods
 
 
 def test_serial_rollout_specialiser_reports_unsupported_configs(lib):
@@ -115,7 +118,7 @@ def test_serial_rollout_specialiser_reports_unsupported_configs(lib):
     keep = []
     cfg = P.to_c(keep)
     need = C.c_int64(0)
-    rc = lib.orgym_invmgmt_codegen(C.byref(cfg), 0, None, 0, C.byref(need))
+    rc = lib.orgym_invmgmt_codegen(C.byref(cfg), None, 0, None, 0, C.byref(need))
     assert rc == -3 and b"specialiser" in lib.orgym_last_error()
 
 
@@ -194,22 +197,35 @@ def test_c_host_example_matches_the_python_host(lib, tmp_path):
     e.close()
 
 
-def test_serial_rollout_specialiser_uses_fused_profit_only_when_provably_exact(lib):
-    """Defaults: float32 coefficients on a 2^-29 grid and values below ~7e4 -> no float64 operation can round -> the
-    generator emits the fused multiply-add chain.  Capacities of a million push the bound past 2^52 * quantum -> it must
-    keep the reference's operation order (4 products + 3 subtractions per stage, sequential sum)."""
-    def source(**kw):
-        P = pkg.InvManagementParams(backlog=True, **kw)
+def test_serial_rollout_specialiser_uses_integer_profit_only_when_provably_exact(lib, monkeypatch):
+    """Defaults: float32 coefficients on a 2^-29 grid and small integers -> no float64 operation of the reference's profit
+    can round -> the generator emits integer multiply-adds on coefficient / 2^-29 (and, the rewards being undiscounted
+    and the 30-period running sum exact as well, converts once per episode).  With discounting: one conversion per
+    period.  Capacities of a million push the bound past 2^52 * quantum -> it must keep the reference's operation order
+    (4 products + 3 subtractions per stage, sequential sum)."""
+    rin = None
+
+    def source(backlog=True, **kw):
+        P = pkg.InvManagementParams(backlog=backlog, **kw)
         keep = []
         cfg = P.to_c(keep)
         need = C.c_int64(0)
         buf = C.create_string_buffer(4 << 20)
-        assert lib.orgym_invmgmt_codegen(C.byref(cfg), 0, buf, len(buf), C.byref(need)) == 0, lib.orgym_last_error()
+        assert lib.orgym_invmgmt_codegen(C.byref(cfg), rin, 0, buf, len(buf), C.byref(need)) == 0, lib.orgym_last_error()
         return buf.value.decode()
-    exact = source()
-    assert "fma(" in exact and "tm_0" not in exact
+    exact = source(backlog=False, alpha=1.0)
+    assert "long long acc = 0;" in exact and "pa -= 13421773LL * (long long)(U_3);" in exact      # 0.025f = 13421773 * 2^-29
+    assert "pa += 536870912LL * (long long)(5 * (s0 + r_0));" in exact                             # (20 - 15) * 2^29 in two steps
+    assert "fma(" not in exact and "tm_0" not in exact and "ret = (double)acc * 0x1p-29;" in exact
+    disc = source()                                                                                # default alpha = 0.97
+    assert "long long acc" not in disc and "(__longlong_as_double(pa + 0x4338000000000000LL) - 0x1.8p52);" in disc
+    assert "tm_0" not in disc
+    monkeypatch.setenv("ORGYM_INV_JIT_INT", "0")
+    fused = source()
+    assert "fma(" in fused and "tm_0" not in fused and "long long pa" not in fused
+    monkeypatch.delenv("ORGYM_INV_JIT_INT")
     big = source(c=[1_000_000, 2_000_000, 2_300_000])
-    assert "fma(" not in big and "tm_0" in big and "pr = pr + tm_3;" in big
+    assert "fma(" not in big and "long long pa" not in big and "tm_0" in big and "pr = pr + tm_3;" in big
 
 
 def test_bench_reference_arm_prints_the_contract_line():
@@ -240,3 +256,18 @@ def test_bench_product_arm_refuses_to_run_without_a_gpu():
         pytest.skip("GPU present")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
     assert p.returncode != 0 and "CUDA device" in (p.stderr + p.stdout) and not p.stdout.strip().startswith("{")
+
+
+def test_geometric_demand_with_a_long_tail_is_refused_not_truncated(lib):
+    """numpy's geometric has unbounded support; the 4096-entry alias table covers it only for p >= ~0.0107.  Below
+    that the library must return ORGYM_E_UNSUPPORTED instead of cutting the tail and renormalising (which would bias
+    the mean well below 1/p)."""
+    def bounds(p):
+        P = pkg.InvManagementParams(dist=4, dist_param={"p": p})
+        keep = []
+        cfg = P.to_c(keep)
+        xv, xs = C.c_double(0), C.c_double(0)
+        return lib.orgym_invmgmt_value_bounds(C.byref(cfg), C.byref(xv), C.byref(xs), None)
+    assert bounds(0.12) == 0 and bounds(0.011) == 0
+    assert bounds(0.01) == _capi.E_UNSUPPORTED and b"geometric" in lib.orgym_last_error()
+    assert bounds(0.001) == _capi.E_UNSUPPORTED

@@ -331,6 +331,49 @@ def test_specialised_rollout_matches_ahead_of_time_kernel(case, monkeypatch):
             assert np.array_equal(a[k], b[k]), (case, k)
 
 
+@pytest.mark.parametrize("cls_name", ["InvManagementLostSalesEnv", "InvManagementBacklogEnv"])
+def test_specialised_rollout_kernels_vs_oracle_at_bench_config(cls_name, monkeypatch):
+    """The kernels bench.py times (inv_jit_rollout_bs / inv_jit_rollout_rnd at the env defaults, seed 5000) checked
+    DIRECTLY against the oracle: the device's demand is recovered through the step API, the random policy's actions
+    from an independent numpy restatement of its Philox stream, and the oracle replays both.  Only outputs the
+    specialised kernels produce are requested, and ORGYM_INV_JIT=2 makes a failed specialisation an error."""
+    from oracle import oracle
+    from helpers import device_random_actions
+    torch = _torch()
+    monkeypatch.setenv("ORGYM_INV_JIT", "2")
+    N, seed, off, ep = 8192, 5000, 3 << 20, 0
+    env = getattr(pkg, cls_name)(num_envs=N, device="cuda:0", env_offset=off, autoreset_mode="disabled")
+    T, n = env.num_periods, env.num_stages - 1
+    env.reset(seed=seed)
+    dem = torch.zeros((N, T), dtype=torch.int64, device="cuda")
+    zero = torch.zeros((N, n), dtype=torch.int64, device="cuda")
+    for t in range(T):
+        dem[:, t] = env.step(zero)[4]["demand_realized"]
+    dem = dem.cpu().numpy()
+    pick = np.r_[0:16, np.random.default_rng(1).choice(N, 80, replace=False), N - 16:N]
+    want = ("ep_return", "stats", "stats32", "summary")
+
+    def check(out, episodes):
+        ret, st = out["ep_return"].cpu().numpy(), out["stats"].cpu().numpy()
+        assert np.array_equal(st, out["stats32"].cpu().numpy().astype(np.int64))
+        for e, o in zip(pick, episodes):
+            assert ret[e] == seq_sum(o["reward"]), e
+            unf0 = (o["B"][1:, 0] if env.params.backlog else o["LS"][:, 0]).sum()
+            assert st[e].tolist() == [o["S"][:, 0].sum(), dem[e].sum(), unf0, np.maximum(o["I"][1:], 0).sum()], e
+        summ = out["summary"].cpu().numpy()
+        assert summ[0] == N and np.isclose(summ[1], ret.sum(), rtol=1e-12) and summ[4] == dem.sum()
+
+    out = env.rollout("base_stock", seed=seed, episode=ep, safety_factor=1.0, want=want)
+    assert env.rollout_specialised
+    check(out, [oracle.invmgmt_episode(env.params, policy="base_stock", demand=dem[e]) for e in pick])
+    out = env.rollout("random", seed=seed, episode=ep, want=want)
+    acts = device_random_actions(seed, off + pick, ep, T, env.params.supply_capacity)
+    assert acts.min() >= 0 and (acts.max(axis=(0, 1)) <= np.asarray(env.params.supply_capacity)).all()
+    check(out, [oracle.invmgmt_episode(env.params, actions=acts[i].astype(np.float64), demand=dem[e])
+                for i, e in enumerate(pick)])
+    env.close()
+
+
 def test_evaluation_report_reproduces_the_reference_summary_row():
     """The reference's per-agent summary (mean / median / std / min / max of TotalReward, mean service level, stock-out
     quantity and ending inventory -- benchmark_InvManagementBacklogEnv.py:493-504) from one fused rollout, on device."""

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import or_gym_inventory_b200 as pkg
-from helpers import golden_files, ids, load_golden, net_S_columns, seq_sum
+from helpers import golden_files, ids, load_golden, net_kwargs, net_S_columns, seq_sum
 
 pytestmark = pytest.mark.gpu
 NET = golden_files("net_")
@@ -25,8 +25,7 @@ def kernel_mode(request, monkeypatch):
 
 
 def _mk(meta, n, **kw):
-    return pkg.NetInvMgmtMasterEnv(graph=meta["graph"], num_periods=meta["num_periods"], backlog=meta["backlog"],
-                                   alpha=meta["alpha"], num_envs=n, device="cuda:0", **kw)
+    return pkg.NetInvMgmtMasterEnv(**net_kwargs(meta), num_envs=n, device="cuda:0", **kw)
 
 
 @pytest.mark.parametrize("path", NET, ids=ids(NET))
@@ -77,6 +76,65 @@ def test_rollout_replay_matches_reference(path, kernel_mode):
     out2 = env.rollout("actions", actions=np.ascontiguousarray(g["actions"].transpose(1, 0, 2)),
                        demand=np.ascontiguousarray(g["D"].transpose(1, 0, 2)), time_major=True, want=("ep_return",))
     assert np.array_equal(out2["ep_return"].cpu().numpy(), ret)
+    env.close()
+
+
+USER_D = [p for p in NET if "userD" in p]
+
+
+@pytest.mark.parametrize("path", USER_D, ids=ids(USER_D))
+def test_user_D_trace_drives_the_market_link(path, kernel_mode):
+    """network_management.py:250-255: a retail link with a user_D trace (sum > 0) and sample_path False replays the
+    trace (rounded, clamped at 0, last entry repeated); with sample_path True it samples from its distribution.  No
+    `demand=` override here: the trace lives in the handle.  Sampled links get the recorded demand replayed through
+    the override only where the trace does not apply, so the whole episode can be compared with the reference."""
+    torch = _torch()
+    g, meta = load_golden(path)
+    n = len(g["seeds"])
+    rt = [tuple(x) for x in meta["retail_links"]]
+    sp = {(u, v): bool(f) for u, v, f in meta["sample_path"]}
+    traced = [i for i, e in enumerate(rt) if e in sp and not sp[e]]
+    sampled = [i for i in range(len(rt)) if i not in traced]
+    assert traced or "samplepath" in path
+    env = _mk(meta, n, autoreset_mode="disabled")
+    T = env.num_periods
+    # (1) device-side demand: traced links equal the reference's D column, sampled links do not replay the trace
+    env.reset(seed=77)
+    D = np.zeros((n, T, len(rt)))
+    for t in range(T):
+        _, _, _, _, info = env.step(torch.from_numpy(g["actions"][:, t]).cuda())
+        D[:, t] = info["demand"].cpu().numpy()
+    assert np.array_equal(D[:, :, traced], g["D"][:, :, traced])
+    for i in sampled:
+        assert (D[:, :, i] >= 0).all() and D[:, :, i].std() > 0
+        tr = dict(((u, v), t_) for u, v, t_ in meta["user_D"]).get(rt[i])
+        if tr is not None:
+            assert not np.array_equal(D[0, :, i], np.maximum(0, np.round(np.asarray(tr[:T]))))
+    # (2) the fused rollout reads the same trace
+    out = env.rollout("actions", actions=g["actions"], seed=77, want=("stats", "reward_traj"))
+    assert np.array_equal(out["stats"].cpu().numpy()[:, 1], D.sum(axis=(1, 2)))
+    if not sampled:      # every market link traced: the whole episode is the reference's, without any override
+        assert np.array_equal(out["reward_traj"].cpu().numpy(), g["reward"])
+    env.close()
+
+
+def test_synthetic_64_generator_matches_golden_topology(kernel_mode):
+    """The product's synthetic_graph(64) is the graph the reference ran for the net_synth64 goldens; stepping an env
+    built from the generator directly (not from the recorded spec) reproduces the reference."""
+    torch = _torch()
+    path = [p for p in NET if "synth64_lost_random" in p][0]
+    g, meta = load_golden(path)
+    G = pkg.synthetic_graph(meta["synthetic_graph_seed"])
+    env = pkg.NetInvMgmtMasterEnv(graph=G, backlog=meta["backlog"], num_periods=meta["num_periods"],
+                                  num_envs=len(g["seeds"]), device="cuda:0", autoreset_mode="disabled")
+    assert [int(j) for j in env.main_nodes] == meta["main_nodes"]
+    assert [list(e) for e in env.reorder_links] == meta["reorder_links"]
+    assert [list(e) for e in env.retail_links] == meta["retail_links"]
+    env.reset(seed=0)
+    for t in range(env.num_periods):
+        obs, r, *_ = env.step(torch.from_numpy(g["actions"][:, t]).cuda(), demand=torch.from_numpy(g["D"][:, t]).cuda())
+        assert np.array_equal(obs.cpu().numpy(), g["obs"][:, t + 1]), t
+        assert np.array_equal(r.cpu().numpy(), g["reward"][:, t]), t
     env.close()
 
 

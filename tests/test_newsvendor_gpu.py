@@ -135,3 +135,43 @@ def test_autoreset_next_step_draws_new_parameters():
     assert (r == 0).all() and not trunc.any() and (obs[:, 5:] == 0).all()
     assert not torch.equal(obs[:, :5], obs0[:, :5])   # a new episode draws new economics
     env.close()
+
+
+@pytest.mark.parametrize("mode", ["next_step", "same_step"])
+def test_fixed_params_survive_autoreset(mode):
+    """reset(options={'fixed_params': ...}) pins the instance for every later episode of the step API
+    (CustomizableNewsvendorEnv re-applies them on each reset, benchmark_newsvendor_sb3_rllib.py:276-291); an env reset
+    without them keeps drawing fresh parameters per episode.  The pinned demand stream still advances per episode."""
+    torch = _torch()
+    N, T = 70, 6
+    fixed = dict(price=50.0, cost=30.0, h=2.5, k=7.25, mu=45.5)
+    env = pkg.NewsvendorEnv(num_envs=N, device="cuda:0", autoreset_mode=mode, step_limit=T)
+    a = torch.full((N, 1), 40.0, device="cuda")
+    env.reset(seed=11, options={"fixed_params": fixed})
+    p0 = env.export_params().cpu().numpy()
+    assert np.array_equal(p0, np.tile([50.0, 30.0, 2.5, 7.25, 45.5], (N, 1)))
+    dem = []
+    for _ in range(3 * T + 3):
+        obs, r, term, trunc, info = env.step(a)
+        dem.append(info["demand"].cpu().numpy().copy())
+        assert np.array_equal(obs[:, :5].cpu().numpy(), p0.astype(np.float32))
+    assert np.array_equal(env.export_params().cpu().numpy(), p0)
+    stride = T + 1 if mode == "next_step" else T
+    assert not np.array_equal(dem[0], dem[stride])          # episode 1 draws its own demand path
+    # masked re-reset without fixed_params un-pins exactly those envs
+    mask = np.zeros(N, bool)
+    mask[::2] = True
+    env.reset(options={"reset_mask": mask})
+    for _ in range(2 * T + 2):
+        env.step(a)
+    p1 = env.export_params().cpu().numpy()
+    assert np.array_equal(p1[1::2], p0[1::2]) and not np.array_equal(p1[::2], p0[::2])
+    env.close()
+    # without pinning: parameters change from episode to episode (reference reset :105-111)
+    env = pkg.NewsvendorEnv(num_envs=N, device="cuda:0", autoreset_mode=mode, step_limit=T)
+    env.reset(seed=11)
+    q0 = env.export_params().cpu().numpy()
+    for _ in range(T + 1):
+        env.step(a)
+    assert not np.array_equal(env.export_params().cpu().numpy(), q0)
+    env.close()

@@ -176,8 +176,11 @@ def test_value_bounds_hold_under_brute_force(case):
     keep = []
     ccfg = P.to_c(keep)
     xvar, xsum = C.c_double(0), C.c_double(0)
-    assert _capi.lib().orgym_invmgmt_value_bounds(C.byref(ccfg), C.byref(xvar), C.byref(xsum)) == 0
-    worst = 0.0
+    pmag = C.c_double(0)
+    assert _capi.lib().orgym_invmgmt_value_bounds(C.byref(ccfg), C.byref(xvar), C.byref(xsum), C.byref(pmag)) == 0
+    worst, worst_mag = 0.0, 0.0
+    up, uc = np.asarray(P.unit_price, np.float64), np.asarray(P.unit_cost, np.float64)
+    kc, hc = np.asarray(P.demand_cost, np.float64), np.asarray(P.holding_cost, np.float64)
     patterns = [rng.integers(0, c + 1, size=(T, n)) for _ in range(6)]
     patterns += [np.tile(c, (T, 1)), np.zeros((T, n), np.int64),
                  np.where((np.arange(T)[:, None] // 3) % 2 == 0, c, 0),        # bang-bang orders
@@ -191,4 +194,10 @@ def test_value_bounds_hold_under_brute_force(case):
             worst = max(worst, float(np.abs(o[key]).max()))
         stats = [np.maximum(o["I"][1:], 0).sum(), o["LS"][:, 0].sum(), o["S"][:, 0].sum()]
         assert max(stats) <= xsum.value
+        # sum of |terms| of every period's profit (the specialiser's exactness proof bounds it by profit_mag)
+        unf = o["B"][1:] if P.backlog else o["LS"]
+        inv = np.concatenate([np.maximum(o["I"][1:], 0), np.zeros((T, 1), np.int64)], axis=1)
+        mag = (np.abs(o["S"]) * (up + uc) + inv * hc + np.abs(unf) * kc).sum(axis=1)
+        worst_mag = max(worst_mag, float(mag.max()))
     assert worst <= xvar.value, (worst, xvar.value, cfg)
+    assert worst_mag <= pmag.value, (worst_mag, pmag.value, cfg)
