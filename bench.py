@@ -1,23 +1,37 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/sec of the batched simulator on N B200s (one process per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload invmgmt|newsvendor|netinv]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--inner R]
 
-Headline workload (BASELINE.json configs[2], the env the north-star target is quoted on):
-InvManagementLostSalesEnv defaults (4-stage serial chain, periods=30, Poisson mu=20), 2^24 instances per GPU,
-fused 30-period rollout with the on-device base-stock policy (SF=1.0), Philox seed 5000.  One bench "step" is one
-fused rollout of the whole batch = 2^24 * 30 env-steps per GPU (+ the 64-byte NCCL allreduce of the episode
-statistics when N > 1).  Prints ONE JSON line (see the task contract); extra keys:
-  roofline           dominant kernel (inv_jit_rollout_bs, the rollout kernel specialised for the config at run time;
-                     inv_rollout_kernel when NVRTC is unavailable): issue-slot roofline (the kernel keeps its state on chip,
-                     so HBM traffic is ~1 B/env-step by construction) + its HBM figures
-  roofline_step_api  the HBM-bound one-period kernel (inv_step_kernel) at the same batch size, 466 B/env-step
-  cpu_baseline       the C oracle port of the reference's evaluation loop on all host cores (bounded sample)
-  e2e                the same rollout through the public Python API with per-episode results copied to pinned host
-                     memory every step
-  e2e_step_api       the host-driven policy loop: actions H2D, observation/reward/flags D2H every period (2^20 instances)
-`--impl reference` times the CPU port itself (the reference is pure Python and cannot travel to the GPU box; its
-in-container rates are recorded in DESIGN.md).
+Workloads (BASELINE.json configs; every one prints the contract line with its own `roofline`):
+  invmgmt          (default, headline) cfg 3: InvManagementLostSalesEnv defaults, 2^24 instances / GPU, fused 30-period
+                   rollout, on-device base-stock SF=1.0, Philox seed 5000
+  invmgmt_random   cfg 3's second driver: uniform random orders
+  invmgmt_backlog  the env the north-star target is quoted on (InvManagementBacklogEnv, base-stock), same batch
+  invmgmt_wide     cfg 3 with int64 state end to end (wide_state=True): the int32-vs-int64 question as a number
+  newsvendor       cfg 2: NewsvendorEnv defaults, 2^20 instances, classic-newsvendor policy
+  netinv           cfg 4: NetInvMgmtBacklogEnv default graph, 2^22 instances, constant-order 10 % policy
+  netinv64_mlp     cfg 5: NetInvMgmtLostSalesEnv(G64, backlog=False), 2^17 instances / GPU (1M over 8 GPUs), torch MLP
+                   policy through the STEP API, one 30-period episode (reset + 30 x (MLP, step)) replayed as a CUDA
+                   graph; observations / actions / rewards are written straight into the PPO-style trajectory buffers
+One bench "step" = `inner` fused rollouts (or MLP-driven episodes) of the whole batch, so that the timed region of the
+driver's short runs still lasts about half a second and the clock sampler sees it.  N > 1: instances are sharded by
+global id, no collective on the data path; the episode statistics are accumulated on the device and all-reduced ONCE,
+inside the timed region, after the K steps.  Prints ONE JSON line (see the task contract); extra keys:
+  roofline           dominant kernel of the workload: issue-slot roofline for the fused rollouts (state on chip, ~1 B of
+                     HBM traffic per env-step by construction; instruction count per env-step from the committed ncu
+                     capture, tied to the kernel sources by sha1, duration measured live with CUDA events), HBM roofline
+                     for the step-API kernels
+  roofline_step_api  the HBM-bound one-period kernel at the same batch size (fused-rollout workloads)
+  cpu_baseline       the C oracle port of the reference's evaluation loop on all host cores (bounded sample), plus
+                     `python_reference`: the unmodified Python reference timed in the build container
+                     (profiles/python_reference_rates.json, written by oracle/ref_rates.py)
+  e2e                the public `env.evaluate()` API: per step the reference's summary row (mean / median / std / min /
+                     max of the episode returns, service level, stock-outs, ending inventory) is computed on the device
+                     and copied to pinned host memory, the host reads it; variants with per-episode tensors alongside
+  e2e_step_api       host-driven policy loop with actions / observations crossing PCIe, double-buffered
+  other_configs      (1 GPU, default workload) the remaining BASELINE configs, each with its own roofline object
+`--impl reference` times the CPU port itself (the reference is pure Python and cannot travel to the GPU box).
 """
 import argparse
 import json
@@ -25,50 +39,75 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALG_BYTES_STEP_API = {"invmgmt": 466, "newsvendor": 222, "netinv": 1598}  # SURVEY.md §8d, per env-step
 SM_COUNT, SCHED_PER_SM = 148, 4
-
-
-def parse():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="invmgmt", choices=["invmgmt", "newsvendor", "netinv"])
-    ap.add_argument("--envs-per-gpu", type=int, default=0, help="override the instance count (default per workload)")
-    ap.add_argument("--no-extras", action="store_true", help="skip step-API roofline, e2e and cpu baseline legs")
-    return ap.parse_args()
-
+CSRC = os.path.join(ROOT, "or-gym-inventory_b200", "csrc")
 
 WORKLOADS = {
     "invmgmt": dict(name="InvManagementLostSalesEnv defaults, fused 30-period rollout, on-device base-stock SF=1.0",
-                    envs=1 << 24, seed=5000, periods=30),
+                    family="invmgmt", envs=1 << 24, seed=5000, periods=30, inner=25, count_key="invmgmt",
+                    cpu=("invmgmt", "base_stock", False)),
+    "invmgmt_random": dict(name="InvManagementLostSalesEnv defaults, fused 30-period rollout, on-device uniform random orders",
+                           family="invmgmt", envs=1 << 24, seed=5000, periods=30, inner=10, count_key="invmgmt_random",
+                           cpu=("invmgmt", "random", False)),
+    "invmgmt_backlog": dict(name="InvManagementBacklogEnv defaults, fused 30-period rollout, on-device base-stock SF=1.0",
+                            family="invmgmt", envs=1 << 24, seed=5000, periods=30, inner=25, count_key="invmgmt_backlog",
+                            cpu=("invmgmt", "base_stock", True)),
+    "invmgmt_wide": dict(name="InvManagementLostSalesEnv defaults, wide_state=True (int64 state end to end), fused rollout, "
+                              "base-stock SF=1.0", family="invmgmt", envs=1 << 24, seed=5000, periods=30, inner=5,
+                         count_key="invmgmt_wide", cpu=("invmgmt", "base_stock", False)),
     "newsvendor": dict(name="NewsvendorEnv defaults (lead_time=5, step_limit=40), fused rollout, classic-newsvendor policy",
-                       envs=1 << 20, seed=2000, periods=40),
+                       family="newsvendor", envs=1 << 20, seed=2000, periods=40, inner=50, count_key="newsvendor",
+                       cpu=("newsvendor", "classic", None)),
     "netinv": dict(name="NetInvMgmtBacklogEnv default 9-node network, fused 30-period rollout, constant-order 10% policy",
-                   envs=1 << 22, seed=6000, periods=30),
+                   family="netinv", envs=1 << 22, seed=6000, periods=30, inner=8, count_key="netinv",
+                   cpu=("netinv", "constant", None)),
+    "netinv64_mlp": dict(name="NetInvMgmtLostSalesEnv synthetic 64-node network (backlog=False), torch MLP policy "
+                              "(obs->64->64->88, tanh) through the step API, PPO-style trajectory collection, CUDA graph",
+                         family="netinv64", envs=1 << 17, seed=12000, periods=30, inner=2, count_key=None,
+                         cpu=("netinv64", "constant", None)),
 }
-
+# algorithmic bytes per env-step, step-API mode
+ALG_BYTES_STEP_API = {"invmgmt": 466, "newsvendor": 222, "netinv": 1598}
+ALG_BYTES_ROLLOUT_OUT = 40.0   # per episode: 8 B return + 32 B statistics
 
 KERNEL_SOURCES = {"invmgmt": ("invmgmt.cu", "invmgmt_jit.cu", "invmgmt_jit_args.cuh", "common.cuh", "device_rng.cuh"),
                   "newsvendor": ("newsvendor.cu", "poisson_mu.cuh", "common.cuh", "device_rng.cuh"),
                   "netinv": ("netinv.cu", "netinv.cuh", "netinv_jit.cu", "netinv_args.cuh", "common.cuh", "device_rng.cuh")}
 
 
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="invmgmt", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="override the instance count (default per workload)")
+    ap.add_argument("--inner", type=int, default=0, help="rollouts per bench step (default per workload)")
+    ap.add_argument("--no-extras", action="store_true", help="skip step-API roofline, e2e, cpu baseline, other configs")
+    return ap.parse_args()
+
+
 def kernel_source_hash(workload):
     """sha1 over the CUDA sources of one env family: ties profiles/inst_counts.json to the kernels it was captured from."""
     import hashlib
+    fam = workload.split("_")[0]
     h = hashlib.sha1()
-    for f in KERNEL_SOURCES[workload]:
-        h.update(open(os.path.join(ROOT, "or-gym-inventory_b200", "csrc", f), "rb").read())
+    for f in KERNEL_SOURCES[fam]:
+        h.update(open(os.path.join(CSRC, f), "rb").read())
     return h.hexdigest()
+
+
+def net_alg_bytes(env):
+    """4E + 4(M+J+sumL) + 8 + 2 + 2*8*(J+E+M+sumL) + 8."""
+    E, M, J = len(env.reorder_links), len(env.retail_links), len(env.main_nodes)
+    sl = int(env.pipeline_obs_length)
+    return 4 * E + 4 * (M + J + sl) + 8 + 2 + 16 * (J + E + M + sl) + 8
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -128,31 +167,63 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # CPU baseline (C oracle port of the reference's evaluation loop), all host threads
 # ---------------------------------------------------------------------------------------------------------
-def cpu_port_rate(workload, seconds=10.0, threads=None):
-    """env-steps/s of the oracle port on `threads` host threads over a bounded sample of about `seconds`."""
+def _cpu_runner(cpu_spec, threads):
+    """-> f(episodes, seed0) -> env-steps, for the workload's env / policy on `threads` host threads."""
+    import numpy as np
     import or_gym_inventory_b200 as pkg
     from oracle import oracle
-    threads = threads or os.cpu_count() or 1
+    fam, pol, backlog = cpu_spec
+    if fam == "invmgmt":
+        P = pkg.InvManagementParams(backlog=bool(backlog))
+        return lambda eps, s0: oracle.invmgmt_bench(P, pol, eps, threads, seed0=s0)[0]
+    if fam == "newsvendor":
+        P = pkg.NewsvendorParams()
+        return lambda eps, s0: oracle.newsvendor_bench(P, pol, eps, threads, seed0=s0)[0]
+    if fam == "netinv":
+        P = pkg.NetInvMgmtParams()
+        a = (P.spaces()[1].high * 0.1).astype(np.float32)
+    else:  # netinv64: the port has no MLP; the env's own cost is what is timed (constant orders at 5 % of the bound)
+        P = pkg.NetInvMgmtParams(graph=pkg.synthetic_graph(64), backlog=False)
+        a = (P.spaces()[1].high * 0.05).astype(np.float32)
+    return lambda eps, s0: oracle.netinv_bench(P, a, eps, threads, seed0=s0)[0]
 
-    def run(episodes):
+
+def python_reference_rates(cpu_spec):
+    """The unmodified Python reference, timed in the build container (it cannot run on the GPU box)."""
+    try:
+        J = json.load(open(os.path.join(ROOT, "profiles", "python_reference_rates.json")))
+    except Exception:  # noqa: BLE001
+        return None
+    key = cpu_spec[0] + ("_backlog" if cpu_spec[0] == "invmgmt" and cpu_spec[2] else "")
+    r = J.get("rates", {}).get(key)
+    if not r:
+        return None
+    return {"single_process_loop": r["1proc"], "all_cores_pool": r["allcore"], "cores": r["cores"], "unit": J.get("unit"),
+            "cpu_model": J.get("cpu_model"), "numpy": J.get("numpy"), "pandas": J.get("pandas"), "python": J.get("python"),
+            "where": J.get("where"), "method": J.get("method")}
+
+
+def cpu_port_rate(cpu_spec, seconds=10.0, threads=None):
+    """env-steps/s of the oracle port on `threads` host threads over a bounded sample of about `seconds`."""
+    threads = threads or os.cpu_count() or 1
+    run = _cpu_runner(cpu_spec, threads)
+    base = 2000 * threads if cpu_spec[0] != "netinv64" else 50 * threads
+
+    def timed(episodes):
         t0 = time.perf_counter()
-        if workload == "invmgmt":
-            steps, _ = oracle.invmgmt_bench(pkg.InvManagementParams(backlog=False), "base_stock", episodes, threads, seed0=5000)
-        elif workload == "newsvendor":
-            steps, _ = oracle.newsvendor_bench(pkg.NewsvendorParams(), "classic", episodes, threads, seed0=2000)
-        else:
-            P = pkg.NetInvMgmtParams()
-            import numpy as np
-            a = (P.spaces()[1].high * 0.1).astype(np.float32)
-            steps, _ = oracle.netinv_bench(P, a, episodes, threads, seed0=6000)
+        steps = run(episodes, 5000)
         return steps, time.perf_counter() - t0
 
-    steps, dt = run(2000 * threads)          # calibration
-    episodes = max(2000 * threads, int(2000 * threads * seconds / max(dt, 1e-3)))
-    steps, dt = run(episodes)
-    return dict(value=steps / dt, unit="env-steps/s", cores=threads, kind="port",
-                sample=f"{episodes} episodes ({steps} env-steps) of the same env/policy, reference-style PCG64+PTRS "
-                       f"Poisson demand, {dt:.1f} s on {threads} threads")
+    steps, dt = timed(base)          # calibration
+    episodes = max(base, int(base * seconds / max(dt, 1e-3)))
+    steps, dt = timed(episodes)
+    out = dict(value=steps / dt, unit="env-steps/s", cores=threads, kind="port",
+               sample=f"{episodes} episodes ({steps} env-steps) of the same env/policy, reference-style PCG64+PTRS "
+                      f"Poisson demand, {dt:.1f} s on {threads} threads")
+    pr = python_reference_rates(cpu_spec)
+    if pr:
+        out["python_reference"] = pr
+    return out
 
 
 def main_reference(args, emit):
@@ -163,40 +234,406 @@ def main_reference(args, emit):
         return
     W = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
-    import or_gym_inventory_b200 as pkg  # noqa: F401
-    from oracle import oracle  # noqa: F401
+    run = _cpu_runner(W["cpu"], threads)
     per_step_s = 1.0
-    r = cpu_port_rate(args.workload, seconds=per_step_s, threads=threads)     # warm caches, calibrate
-    eps_per_step = max(1000, int(r["value"] * per_step_s / W["periods"]))
-    import numpy as np
-
-    def one(seed0):
-        if args.workload == "invmgmt":
-            return oracle.invmgmt_bench(pkg.InvManagementParams(backlog=False), "base_stock", eps_per_step, threads, seed0=seed0)[0]
-        if args.workload == "newsvendor":
-            return oracle.newsvendor_bench(pkg.NewsvendorParams(), "classic", eps_per_step, threads, seed0=seed0)[0]
-        P = pkg.NetInvMgmtParams()
-        return oracle.netinv_bench(P, (P.spaces()[1].high * 0.1).astype(np.float32), eps_per_step, threads, seed0=seed0)[0]
-
+    r = cpu_port_rate(W["cpu"], seconds=per_step_s, threads=threads)     # warm caches, calibrate
+    eps_per_step = max(50, int(r["value"] * per_step_s / W["periods"]))
     for w in range(args.warmup):
-        one(W["seed"] + w)
+        run(eps_per_step, W["seed"] + w)
     t0 = time.perf_counter()
     steps = 0
     for k in range(args.steps):
-        steps += one(W["seed"] + 1000 + k * eps_per_step)
+        steps += run(eps_per_step, W["seed"] + 1000 + k * eps_per_step)
     dt = time.perf_counter() - t0
     val = steps / dt
+    cb = {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port",
+          "sample": f"{eps_per_step} episodes per step x {args.steps} steps, all {threads} host threads"}
+    pr = python_reference_rates(W["cpu"])
+    if pr:
+        cb["python_reference"] = pr
     line = {"impl": "reference", "metric": "env-steps/sec", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64",
-            "data": "synthetic", "config": {"workload": W["name"], "sample_episodes_per_step": eps_per_step},
-            "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                             "sample": f"{eps_per_step} episodes per step x {args.steps} steps, all {threads} host threads"},
+            "data": "synthetic",
+            "config": {"workload": W["name"], "instances_per_gpu": args.envs_per_gpu or W["envs"], "periods": W["periods"],
+                       "seed": W["seed"], "sample_episodes_per_step": eps_per_step},
+            "cpu_baseline": cb,
             "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
+# workloads on the GPU
+# ---------------------------------------------------------------------------------------------------------
+class Rollout:
+    """A fused-rollout workload: `call(ep)` enqueues one rollout of the whole batch and returns its output dict."""
+
+    def __init__(self, wname, dev, N, offset):
+        import or_gym_inventory_b200 as pkg
+        W = WORKLOADS[wname]
+        self.W, self.N, self.T, self.wname = W, N, W["periods"], wname
+        self.want = ("ep_return", "stats", "summary")
+        if W["family"] == "invmgmt":
+            cls = pkg.InvManagementBacklogEnv if wname == "invmgmt_backlog" else pkg.InvManagementLostSalesEnv
+            self.env = cls(num_envs=N, device=dev, env_offset=offset, wide_state=(wname == "invmgmt_wide"))
+            if wname == "invmgmt_random":
+                self.policy, self.kw = "random", {}
+            else:
+                self.policy, self.kw = "base_stock", dict(safety_factor=1.0)
+            self.dtype = "int64 state + f64 reward" if wname == "invmgmt_wide" else "int32 state (proven range) + f64 reward"
+        elif W["family"] == "newsvendor":
+            self.env = pkg.NewsvendorEnv(num_envs=N, device=dev, env_offset=offset)
+            self.policy, self.kw = "classic", {}
+            self.dtype = "f32 state + mixed f32/f64 reward"
+        else:
+            self.env = pkg.NetInvMgmtBacklogEnv(num_envs=N, device=dev, env_offset=offset)
+            self.policy, self.kw = "constant", dict(order_fraction=0.1)
+            self.dtype = "f64"
+        self.launches_per_call = 2      # rollout kernel + the fixed-order reduction of the block partial sums
+        self.env_steps_per_call = N * self.T
+
+    def call(self, ep):
+        return self.env.rollout(self.policy, seed=self.W["seed"], episode=ep, want=self.want, **self.kw)
+
+    def kernel_name(self):
+        fam = self.W["family"]
+        if fam == "invmgmt":
+            if self.env.rollout_specialised:
+                return ("inv_jit_rollout_rnd" if self.policy == "random" else "inv_jit_rollout_bs") + " (specialised at run time, NVRTC)"
+            return "inv_rollout_kernel<3,true,%s>" % ("long long" if self.wname == "invmgmt_wide" else "int")
+        if fam == "newsvendor":
+            return "nv_rollout_kernel<5>"
+        return "net_jit_rollout" if self.env.specialised else "net_sim_kernel<128> (generic)"
+
+    def count_key(self):
+        if self.W["family"] == "invmgmt" and self.wname != "invmgmt_wide" and not self.env.rollout_specialised:
+            return "invmgmt_aot"
+        return self.W["count_key"]
+
+    def close(self):
+        self.env.close()
+
+
+class MlpEpisode:
+    """cfg 5: one PPO-style collection episode of the 64-node lost-sales network driven by a torch MLP through the step
+    API -- reset + T x (policy forward, env.step) captured once as a CUDA graph and replayed.  The env writes each
+    observation / reward directly into the trajectory buffers (zero-copy), the MLP reads obs[t] and writes act[t]."""
+
+    def __init__(self, wname, dev, N, offset):
+        import torch
+        import or_gym_inventory_b200 as pkg
+        W = WORKLOADS[wname]
+        self.W, self.N, self.T, self.wname = W, N, W["periods"], wname
+        self.env = env = pkg.NetInvMgmtLostSalesEnv(graph=pkg.synthetic_graph(64), backlog=False, num_envs=N, device=dev,
+                                                    env_offset=offset, autoreset_mode="disabled", info_level=0)
+        E, T = len(env.reorder_links), self.T
+        torch.manual_seed(0)
+        self.mlp = torch.nn.Sequential(torch.nn.Linear(env.obs_dim, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64),
+                                       torch.nn.Tanh(), torch.nn.Linear(64, E), torch.nn.Sigmoid()).to(dev)
+        self.high = torch.from_numpy(env.single_action_space.high).to(dev) * 0.05
+        self.obs = torch.zeros((T + 1, N, env.obs_dim), dtype=torch.float32, device=dev)
+        self.act = torch.zeros((T, N, E), dtype=torch.float32, device=dev)
+        self.rew = torch.zeros((T, N), dtype=torch.float64, device=dev)
+        self.summary = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.dtype = "f64 env state + f32 policy"
+        self.launches_per_call = 1 + 2 * T    # reset + (net_jit_step, net_obs_kernel) per period
+        self.env_steps_per_call = N * T
+        self.alg_bytes = net_alg_bytes(env)
+        self.graph = None
+        env.reset(seed=W["seed"])
+        self._episode()                       # eager once (lazy initialisation, cuBLAS workspaces)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        try:
+            with torch.cuda.stream(side):
+                self._episode()
+                side.synchronize()
+                with torch.cuda.graph(g, stream=side):
+                    self._episode()
+            self.graph = g
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"[bench] CUDA graph capture failed ({e}); running the episode eagerly\n")
+            self.graph = None
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+
+    def _episode(self):
+        import torch
+        env, T = self.env, self.T
+        env.reset(obs_out=self.obs[0])        # next episode of the same keys (episode counter += 1 on the device)
+        with torch.no_grad():
+            for t in range(T):
+                torch.mul(self.mlp(self.obs[t] * 1e-3), self.high, out=self.act[t])
+                env.step(self.act[t], obs_out=self.obs[t + 1], reward_out=self.rew[t])
+            ret = self.rew.sum(dim=0)
+            self.summary[0:1].fill_(float(self.N))
+            self.summary[1:2].copy_(ret.sum().reshape(1))
+            self.summary[2:3].copy_((ret * ret).sum().reshape(1))
+
+    def call(self, ep):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._episode()
+        return {"summary": self.summary}
+
+    def kernel_name(self):
+        return "net_jit_step (streaming, specialised per topology) + net_obs_kernel" if self.env.specialised else "net_sim_kernel (generic)"
+
+    def count_key(self):
+        return None
+
+    def close(self):
+        self.env.close()
+
+
+def make_workload(wname, dev, N, offset):
+    return (MlpEpisode if WORKLOADS[wname]["family"] == "netinv64" else Rollout)(wname, dev, N, offset)
+
+
+def time_calls(fn, reps, warm=3):
+    """average CUDA-event duration (ms) of `reps` back-to-back calls on torch's current stream."""
+    import torch
+    for k in range(warm):
+        fn(k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(reps):
+        fn(100 + k)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def load_counts():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "inst_counts.json")))
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+def load_peaks():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        peaks = {}
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    return hbm, src
+
+
+def rollout_roofline(wl, kms, sm_mhz, counts, hbm_peak, peak_src):
+    """issue-slot roofline of a fused rollout kernel (+ its HBM figures): kms = live CUDA-event duration of one launch."""
+    N, T = wl.N, wl.T
+    issue_peak = SM_COUNT * SCHED_PER_SM * sm_mhz * 1e6
+    alg_bytes = N * ALG_BYTES_ROLLOUT_OUT
+    ckey = wl.count_key()
+    c = counts.get(ckey, {}) if ckey else {}
+    src_now = kernel_source_hash(wl.wname)
+    stale = bool(c) and c.get("src_sha1") not in (None, src_now)
+    roof = {"kernel": wl.kernel_name(), "bound": "issue", "unit": "warp-inst/s", "peak": issue_peak,
+            "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)",
+            "kernel_ms": kms, "achieved": None, "frac": None,
+            "traffic": (c["dram_bytes_per_env_step"] * N * T) if c.get("dram_bytes_per_env_step") else None,
+            "hbm": {"achieved_gbs": alg_bytes / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                    "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": alg_bytes,
+                    "peak_source": peak_src}}
+    if stale:
+        roof["note"] = ("instruction count in profiles/inst_counts.json was captured for different kernel sources "
+                        "(sha1 mismatch): issue-roofline fraction withheld until the capture is redone")
+    elif not c.get("warp_inst_per_env_step"):
+        roof["note"] = f"no committed instruction count for {ckey!r}: issue-roofline fraction withheld"
+    if c.get("warp_inst_per_env_step") and not stale:
+        inst = c["warp_inst_per_env_step"] * N * T
+        roof["achieved"] = inst / (kms * 1e-3)
+        roof["frac"] = roof["achieved"] / issue_peak
+        roof["warp_inst_per_launch"] = inst
+        roof["warp_inst_per_warp_step"] = c["warp_inst_per_env_step"] * 32
+        roof["inst_source"] = c.get("source")
+    return roof
+
+
+def step_api_roofline(family, dev, N, offset, seed, counts, hbm_peak, peak_src, graph64=False):
+    """HBM roofline of the one-period kernel(s) through env.step at batch size N: info_level=0 moves exactly the
+    algorithmic bytes of SURVEY 8(d); the default (info tensors on) is reported alongside with its bytes counted."""
+    import torch
+    import or_gym_inventory_b200 as pkg
+    res = {}
+    for info_level in (0, 1):
+        if family == "invmgmt":
+            env = pkg.InvManagementLostSalesEnv(num_envs=N, device=dev, env_offset=offset, info_level=info_level)
+            a = torch.randint(0, 100, (N, 3), dtype=torch.int64, device=dev)
+            sk, ab, ib = "inv_step_kernel<3,true,int>", ALG_BYTES_STEP_API["invmgmt"], 8 + 8 * 4 + 8 * 4 + 8
+        elif family == "newsvendor":
+            env = pkg.NewsvendorEnv(num_envs=N, device=dev, env_offset=offset, info_level=info_level)
+            a = torch.rand((N, 1), device=dev) * 100
+            sk, ab, ib = "nv_step_kernel", ALG_BYTES_STEP_API["newsvendor"], 8 + 8 * 4
+        else:
+            if graph64:
+                env = pkg.NetInvMgmtLostSalesEnv(graph=pkg.synthetic_graph(64), backlog=False, num_envs=N, device=dev,
+                                                 env_offset=offset, info_level=info_level)
+                ab = net_alg_bytes(env)
+                sk = ("net_jit_step (streaming) + net_obs_kernel" if env.specialised else "net_sim_kernel<128> (generic, STEP)")
+            else:
+                env = pkg.NetInvMgmtBacklogEnv(num_envs=N, device=dev, env_offset=offset, info_level=info_level)
+                ab = ALG_BYTES_STEP_API["netinv"]
+                sk = "net_jit_step" if env.specialised else "net_sim_kernel<128> (generic, STEP)"
+            nE, nM, nJ = len(env.reorder_links), len(env.retail_links), len(env.main_nodes)
+            a = torch.rand((N, nE), device=dev) * 100
+            ib = 8 * (nM + (nE + nM) + nJ + 1)
+        env.reset(seed=seed)
+        ms = time_calls(lambda k: env.step(a), 20)
+        res[info_level] = ms
+        env.close()
+        del env, a
+        torch.cuda.empty_cache()
+    ach = N * ab / (res[0] * 1e-3) / 1e9
+    ach_i = N * (ab + ib) / (res[1] * 1e-3) / 1e9
+    ckey = ("netinv64_step" if graph64 else family + "_step")
+    return {"kernel": sk, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+            "traffic": (counts.get(ckey, {}).get("dram_bytes_per_env_step") or 0) * N or None,
+            "kernel_ms": res[0], "env_steps_per_s": N / (res[0] * 1e-3), "algorithmic_bytes_per_env_step": ab,
+            "instances": N, "peak_source": peak_src,
+            "note": "env built with info_level=0: the kernel(s) move the algorithmic bytes (actions, observation, reward, "
+                    "flags, state read+write); `traffic` is the ncu DRAM byte count of the committed capture",
+            "with_info_tensors": {"kernel_ms": res[1], "bytes_per_env_step": ab + ib, "achieved": ach_i,
+                                  "frac": ach_i / hbm_peak, "env_steps_per_s": N / (res[1] * 1e-3),
+                                  "frac_counting_algorithmic_bytes_only": N * ab / (res[1] * 1e-3) / 1e9 / hbm_peak}}
+
+
+def host_step_loop(family, dev, N, offset, seed, graph64=False):
+    """Host-driven policy loop: actions from pinned host memory, observation / reward / flags back to pinned host
+    memory every period.  Double-buffered: while the host "policy" consumes the results of period t (two pinned
+    buffer sets), the H2D copy of the next actions, the step kernel and the D2H copies of period t+1 are already
+    queued on the GPU -- the host never waits for a copy it does not need yet."""
+    import torch
+    import or_gym_inventory_b200 as pkg
+    Ns = min(N, 1 << 20)
+    if family == "invmgmt":
+        env = pkg.InvManagementLostSalesEnv(num_envs=Ns, device=dev, env_offset=offset, info_level=0)
+        mk = lambda: torch.randint(0, 100, (Ns, 3), dtype=torch.int64).pin_memory()  # noqa: E731
+    elif family == "newsvendor":
+        env = pkg.NewsvendorEnv(num_envs=Ns, device=dev, env_offset=offset, info_level=0)
+        mk = lambda: (torch.rand((Ns, 1)) * 100).pin_memory()  # noqa: E731
+    else:
+        if graph64:
+            Ns = min(N, 1 << 17)
+            env = pkg.NetInvMgmtLostSalesEnv(graph=pkg.synthetic_graph(64), backlog=False, num_envs=Ns, device=dev,
+                                             env_offset=offset, info_level=0)
+        else:
+            env = pkg.NetInvMgmtBacklogEnv(num_envs=Ns, device=dev, env_offset=offset, info_level=0)
+        nE = len(env.reorder_links)
+        mk = lambda: (torch.rand((Ns, nE)) * 100).pin_memory()  # noqa: E731
+    obs_d, _ = env.reset(seed=seed)
+    a_h = [mk(), mk()]
+    a_d = [torch.empty_like(a_h[0], device=dev) for _ in range(2)]
+    obs_h = [torch.empty(obs_d.shape, dtype=obs_d.dtype).pin_memory() for _ in range(2)]
+    rew_h = [torch.empty(Ns, dtype=torch.float64).pin_memory() for _ in range(2)]
+    tr_h = [torch.empty(Ns, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+
+    def enqueue(b):
+        a_d[b].copy_(a_h[b], non_blocking=True)
+        o, r, _, tr, _ = env.step(a_d[b])
+        obs_h[b].copy_(o, non_blocking=True)
+        rew_h[b].copy_(r.view(-1), non_blocking=True)
+        tr_h[b].copy_(tr.view(-1).view(torch.uint8), non_blocking=True)
+        done[b].record()
+
+    def run(steps):
+        chk = 0.0
+        enqueue(0)
+        for t in range(steps):
+            b = t & 1
+            if t + 1 < steps:
+                enqueue(b ^ 1)        # period t+1 is queued before the host touches the results of period t
+            done[b].synchronize()
+            chk += float(rew_h[b][0]) + float(obs_h[b].view(-1)[0])      # the host policy reads what came back
+        return chk
+
+    run(4)
+    hs = 20
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run(hs)
+    torch.cuda.synchronize()
+    hdt = time.perf_counter() - t0
+    out = {"value": Ns * hs / hdt, "unit": "env-steps/s", "instances": Ns, "steps": hs,
+           "h2d_bytes_per_step": a_h[0].numel() * a_h[0].element_size(),
+           "d2h_bytes_per_step": obs_h[0].numel() * obs_h[0].element_size() + Ns * 9,
+           "note": "host-driven policy loop on rank 0: actions from pinned host memory, observation + reward + truncated "
+                   "flags back to pinned host memory every period; double-buffered (period t+1 is queued while the host "
+                   "reads period t), still PCIe-bound -- the fused on-device policies exist to avoid exactly this"}
+    env.close()
+    return out
+
+
+def run_e2e(wl, args, world, dev, dist, barrier, reps):
+    """e2e through the public evaluate() API, measured on every rank (max over ranks)."""
+    import torch
+    N, T = wl.N, wl.T
+    pol, kw, seed, env = wl.policy, wl.kw, wl.W["seed"], wl.env
+
+    def timed(want, first, check):
+        d2h = 0
+        for res in env.evaluate(pol, episodes=3, seed=seed, first_episode=first, want=want, **kw):
+            d2h = sum(v.numel() * v.element_size() for v in res.values())
+        barrier()
+        t0 = time.perf_counter()
+        chk = 0.0
+        for res in env.evaluate(pol, episodes=reps, seed=seed, first_episode=first + 100, want=want, **kw):
+            chk += check(res)             # the host reads the copies
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert chk == float(N) * reps, (chk, N, reps)
+        return float(N) * T * reps * world / float(dt.item()), d2h * world
+
+    v0, b0 = timed(("report",), 300, lambda r: float(r["report"][0]))
+    v1, b1 = timed(("ep_return", "summary"), 600, lambda r: float(r["summary"][0]) + float(r["ep_return"][-1]) * 0.0)
+    full = ("ep_return", "stats32", "summary") if wl.W["family"] == "invmgmt" else ("ep_return", "stats", "summary")
+    v2, b2 = timed(full, 900, lambda r: float(r["summary"][0]) + float(r["ep_return"][-1]) * 0.0)
+    return {"value": v0, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": b0, "steps": reps,
+            "note": "public API env.evaluate(): per step one fused rollout of the whole batch, then the reference's "
+                    "evaluation summary row (mean / median / std / min / max of the 2^24 episode returns by radix select, "
+                    "mean service level, stock-outs, ending inventory -- csrc/report.cu) computed on the device; the "
+                    "16-number report is copied to pinned host memory on a second stream and read by the host inside "
+                    "the timed region.  This workload has no input tensors (policy and seed are kernel parameters; "
+                    "demand is Philox-sampled on the device), hence h2d 0.  Per-rank reports under N > 1.",
+            "with_per_episode_returns": {"value": v1, "d2h_bytes_per_step": b1,
+                                         "note": "every episode's float64 return + the aggregate sums cross PCIe "
+                                                 "(8 B per episode: PCIe-bound)"},
+            "with_per_episode_statistics": {"value": v2, "d2h_bytes_per_step": b2,
+                                            "note": "additionally the four per-episode statistics of the reference's "
+                                                    "evaluate_agent rows (24-40 B per episode: PCIe-bound)"}}
+
+
+def measure_other(wname, dev, counts, hbm_peak, peak_src, sm_mhz, reps=10):
+    """One of the other BASELINE configs on rank 0: kernel time by CUDA events + its roofline object."""
+    import torch
+    W = WORKLOADS[wname]
+    wl = make_workload(wname, dev, W["envs"], 0)
+    ms = time_calls(lambda k: wl.call(k), reps)
+    out = {"workload": W["name"], "instances": wl.N, "periods": wl.T, "ms_per_rollout": ms,
+           "env_steps_per_s": wl.env_steps_per_call / (ms * 1e-3), "dtype": wl.dtype}
+    if isinstance(wl, Rollout):
+        kms = time_calls(lambda k: wl.env.rollout(wl.policy, seed=W["seed"], episode=k, want=("ep_return", "stats"), **wl.kw), reps)
+        out["roofline"] = rollout_roofline(wl, kms, sm_mhz, counts, hbm_peak, peak_src)
+        if W["family"] == "invmgmt":
+            out["specialised_kernel"] = wl.env.rollout_specialised
+    else:
+        out["graph_replay"] = wl.graph is not None
+        out["ms_per_period"] = ms / wl.T
+    wl.close()
+    del wl
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     args = parse()
     # keep stdout clean for the ONE JSON line: libraries (e.g. NCCL's version banner) write to fd 1
@@ -210,7 +647,6 @@ def main():
         return main_reference(args, emit)
     import torch
     import torch.distributed as dist
-    import or_gym_inventory_b200 as pkg
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -229,39 +665,25 @@ def main():
     W = WORKLOADS[args.workload]
     N = args.envs_per_gpu or W["envs"]
     T = W["periods"]
-    offset = rank * N
-
-    if args.workload == "invmgmt":
-        env = pkg.InvManagementLostSalesEnv(num_envs=N, device=dev, env_offset=offset)
-        roll = lambda ep, want: env.rollout("base_stock", seed=W["seed"], episode=ep, safety_factor=1.0, want=want)  # noqa: E731
-        kernel, dtype = "inv_jit_rollout_bs | inv_rollout_kernel<3,true,int>", "int32 state + f64 reward"
-    elif args.workload == "newsvendor":
-        env = pkg.NewsvendorEnv(num_envs=N, device=dev, env_offset=offset)
-        roll = lambda ep, want: env.rollout("classic", seed=W["seed"], episode=ep, want=want)  # noqa: E731
-        kernel, dtype = "nv_rollout_kernel", "f32 state + mixed f32/f64 reward"
-    else:
-        env = pkg.NetInvMgmtBacklogEnv(num_envs=N, device=dev, env_offset=offset)
-        roll = lambda ep, want: env.rollout("constant", order_fraction=0.1, seed=W["seed"], episode=ep, want=want)  # noqa: E731
-        kernel, dtype = ("net_jit_rollout" if env.specialised else "net_sim_kernel<128> (generic)"), "f64"
-    want = ("ep_return", "stats", "summary")
-
-    def step(ep):
-        out = roll(ep, want)
-        if world > 1:
-            dist.all_reduce(out["summary"])      # the only collective: 8 float64 episode statistics
-        return out
+    inner = args.inner or W["inner"]
+    warm = max(args.warmup, 3)
+    wl = make_workload(args.workload, dev, N, rank * N)
+    acc = torch.zeros(8, dtype=torch.float64, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for w in range(max(args.warmup, 3)):
+    def step(k):          # one bench step = `inner` rollouts; statistics accumulate on the device
+        for r in range(inner):
+            out = wl.call(k * inner + r)
+            acc.add_(out["summary"])
+
+    for w in range(warm):
         step(w)
     barrier()
-    if args.workload == "invmgmt":
-        kernel = ("inv_jit_rollout_bs (specialised at run time, NVRTC)" if env.rollout_specialised
-                  else "inv_rollout_kernel<3,true,int>")
+    acc.zero_()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -270,7 +692,9 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
-        out = step(100 + k)
+        step(100 + k)
+    if world > 1:
+        dist.all_reduce(acc)          # the only collective: 8 float64 episode statistics, once per run
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -279,294 +703,95 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
-    steps_total = float(N) * T * args.steps * world
+    steps_total = float(wl.env_steps_per_call) * inner * args.steps * world
     value = steps_total / (ms * 1e-3)
-    summ = out["summary"].cpu().numpy()
+    summ = acc.cpu().numpy()
 
     line = {"metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
             "config": {"workload": W["name"], "instances_per_gpu": N, "periods": T, "seed": W["seed"],
-                       "env_steps_per_bench_step": N * T * world,
+                       "rollouts_per_bench_step": inner, "env_steps_per_bench_step": wl.env_steps_per_call * inner * world,
                        "host_cores_per_rank": host_cores or None,
+                       "collective": "one 64-byte all-reduce of the accumulated episode statistics after the K steps (inside "
+                                     "the timed region); none on the step path",
                        "l2": "no input tensors (on-device policy + Philox demand); the per-episode outputs written "
-                             f"every step ({N * 40 / 1e6:.0f} MB) exceed the 126 MB L2"},
-            "gpu_launches": 2 * args.steps,
+                             f"every rollout ({N * 40 / 1e6:.0f} MB) exceed the 126 MB L2" if W["family"] != "netinv64" else
+                             "state + trajectory buffers touched per period exceed the 126 MB L2 (1.1 GB of state)"},
+            "gpu_launches": wl.launches_per_call * inner * args.steps,
             "episode_stats": {"episodes": summ[0], "mean_return": summ[1] / max(summ[0], 1),
-                              "service_level": summ[3] / max(summ[4], 1)}}
+                              "service_level": (summ[3] / summ[4]) if summ[4] else None}}
+    if W["family"] == "netinv64":
+        line["config"]["graph_replay"] = wl.graph is not None
     if clocks is not None:
         line["clocks"] = {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                           "samples": clocks["samples"]}
+    hbm_peak, peak_src = load_peaks()
+    counts = load_counts()
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    is_rollout = isinstance(wl, Rollout)
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:  # noqa: BLE001
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-
-    # ---- e2e (every rank): the public evaluate() API -- per-episode results land in pinned host memory every step;
-    # the copy of step k overlaps the kernel of step k+1 (two buffer sets, second stream); host waits for every result
-    if not args.no_extras:
-        pol = {"invmgmt": ("base_stock", dict(safety_factor=1.0)), "newsvendor": ("classic", {}),
-               "netinv": ("constant", dict(order_fraction=0.1))}[args.workload]
-        reps = max(4, min(args.steps, 20))
-
-        def run_e2e(e2e_want, first):
-            d2h = 0
-            for res in env.evaluate(pol[0], episodes=3, seed=W["seed"], first_episode=first, want=e2e_want, **pol[1]):
-                d2h = sum(v.numel() * v.element_size() for v in res.values())
+    if args.no_extras:
+        line["e2e"] = None
+    elif is_rollout:
+        line["e2e"] = run_e2e(wl, args, world, dev, dist, barrier, max(6, min(args.steps * inner // 4, 40)))
+    else:
+        # cfg 5: observations and actions never leave the GPU; per episode the host reads back the 3 episode sums
+        def timed_mlp(reps):
+            pinned = torch.empty(8, dtype=torch.float64).pin_memory()
+            for k in range(2):
+                wl.call(k)
             barrier()
             t0 = time.perf_counter()
             chk = 0.0
-            for res in env.evaluate(pol[0], episodes=reps, seed=W["seed"], first_episode=first + 100, want=e2e_want, **pol[1]):
-                chk += float(res["summary"][0]) + float(res["ep_return"][-1]) * 0.0      # touch the host copies
-            torch.cuda.synchronize()
-            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            assert chk == float(N) * reps
-            return float(N) * T * reps * world / float(dt.item()), d2h * world
-
-        # headline: what the reference's evaluation report needs -- every episode's return (histograms, quantiles) and
-        # the 8 aggregate statistics (mean / std of return, service level, stock-outs, inventory: process_results)
-        v1, b1 = run_e2e(("ep_return", "summary"), 300)
-        # everything the reference keeps per episode (return + sales / demand / stock-out / inventory sums): PCIe-bound
-        full_want = ("ep_return", "stats32", "summary") if args.workload == "invmgmt" else want
-        v2, b2 = run_e2e(full_want, 600)
-        # only the 8 aggregate statistics (what the reference's benchmark scripts finally print): kernel-bound
-        def run_summary_only():
-            for res in env.evaluate(pol[0], episodes=3, seed=W["seed"], first_episode=900, want=("summary",), **pol[1]):
-                pass
-            barrier()
-            t0 = time.perf_counter()
-            chk = 0.0
-            for res in env.evaluate(pol[0], episodes=reps, seed=W["seed"], first_episode=1000, want=("summary",), **pol[1]):
-                chk += float(res["summary"][0])
-            torch.cuda.synchronize()
+            for k in range(reps):
+                out = wl.call(k)
+                pinned.copy_(out["summary"], non_blocking=True)
+                torch.cuda.synchronize()
+                chk += float(pinned[0])
             dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             assert chk == float(N) * reps
             return float(N) * T * reps * world / float(dt.item())
-        v3 = run_summary_only()
-        line["e2e"] = {"value": v1, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": b1, "steps": reps,
-                       "summary_only": {"value": v3, "d2h_bytes_per_step": 64 * world,
-                                        "note": "only the 8 aggregate statistics cross PCIe (kernel-bound)"},
-                       "note": "public API env.evaluate(): this workload's inputs are the policy/seed scalars passed as "
-                               "kernel parameters (no input tensors); every episode's float64 return and the 8 aggregate "
-                               "statistics are copied to pinned host memory each step and consumed by the host inside the "
-                               "timed region; copy of step k overlaps the kernel of step k+1",
-                       "with_per_episode_statistics": {"value": v2, "d2h_bytes_per_step": b2,
-                                                       "note": "additionally the four per-episode statistics of the "
-                                                               "reference's evaluate_agent rows (PCIe-bound)"}}
-    else:
-        line["e2e"] = None
+        line["e2e"] = {"value": timed_mlp(6), "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64 * world,
+                       "steps": 6,
+                       "note": "the PPO-style collection loop through the public step API (reset + 30 x (MLP forward, "
+                               "env.step) replayed as one CUDA graph): observations, actions and rewards stay in HBM (zero-"
+                               "copy trajectory buffers), the host reads the episode sums from pinned memory every episode"}
 
     if rank == 0 and not args.no_extras:
-        # ---- roofline of the dominant kernel (fused rollout): issue-slot bound ---------------------------------
-        counts = {}
-        try:
-            counts = json.load(open(os.path.join(ROOT, "profiles", "inst_counts.json")))
-        except Exception:  # noqa: BLE001
-            pass
-        for _ in range(3):
-            roll(0, want)
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        reps = max(5, args.steps)
-        for k in range(reps):
-            roll(200 + k, want)
-        k1.record()
-        torch.cuda.synchronize()
-        kms = k0.elapsed_time(k1) / reps
-        alg_bytes = N * 40.0           # per launch: 8 B return + 32 B statistics per episode
-        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        issue_peak = SM_COUNT * SCHED_PER_SM * sm_mhz * 1e6           # warp-instructions / s at the observed clock
-        ckey = args.workload
-        if args.workload == "invmgmt" and "inv_jit" not in kernel:
-            ckey = "invmgmt_aot"       # NVRTC unavailable: the ahead-of-time kernel ran (its own instruction count)
-        c = counts.get(ckey, {})
-        src_now = kernel_source_hash(args.workload)
-        stale = bool(c) and c.get("src_sha1") not in (None, src_now)
-        roof = {"kernel": kernel, "bound": "issue", "unit": "warp-inst/s", "peak": issue_peak,
-                "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)",
-                "kernel_ms": kms, "achieved": None, "frac": None,
-                "traffic": (c["dram_bytes_per_env_step"] * N * T) if c.get("dram_bytes_per_env_step") else None,
-                "hbm": {"achieved_gbs": alg_bytes / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                        "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": alg_bytes,
-                        "peak_source": peak_src}}
-        if stale:
-            roof["note"] = ("instruction count in profiles/inst_counts.json was captured for different kernel sources "
-                            "(sha1 mismatch): issue-roofline fraction withheld until the capture is redone")
-        if c.get("warp_inst_per_env_step") and not stale:
-            inst = c["warp_inst_per_env_step"] * N * T
-            roof["achieved"] = inst / (kms * 1e-3)
-            roof["frac"] = roof["achieved"] / issue_peak
-            roof["warp_inst_per_launch"] = inst
-            roof["inst_source"] = c.get("source")
-        line["roofline"] = roof
-
-        # ---- HBM-bound one-period kernel (step API) at the same batch size ---------------------------------------
-        if args.workload == "invmgmt":
-            a = torch.randint(0, 100, (N, 3), dtype=torch.int64, device=dev)
-            sk = "inv_step_kernel<3,true,int>"
-        elif args.workload == "newsvendor":
-            a = torch.rand((N, 1), device=dev) * 100
-            sk = "nv_step_kernel"
-        else:
-            a = torch.rand((N, len(env.reorder_links)), device=dev) * 100
-            sk = "net_jit_step" if env.specialised else "net_sim_kernel<128> (generic, STEP)"
-        env.reset(seed=W["seed"])
-        for _ in range(3):
-            env.step(a)
-        torch.cuda.synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(20):
-            env.step(a)
-        s1.record()
-        torch.cuda.synchronize()
-        sms = s0.elapsed_time(s1) / 20
-        ab = ALG_BYTES_STEP_API[args.workload]
-        # optional info tensors written on top of the algorithmic bytes (Python host default, info_level=1)
-        if args.workload == "invmgmt":
-            ib = 8 + 8 * 4 + 8 * 4 + 8                      # demand, sales[m], unfulfilled[m], period profit
-        elif args.workload == "newsvendor":
-            ib = 8 + 8 * 4                                  # demand, four reward parts
-        else:
-            nE, nM, nJ = len(env.reorder_links), len(env.retail_links), len(env.main_nodes)
-            ib = 8 * (nM + (nE + nM) + nJ + 1)              # demand, sales, node profit, period profit
-        # the same kernel without the optional info tensors = exactly the algorithmic bytes of SURVEY.md §8d
-        env.close()
-        del env
+        fam = "netinv" if W["family"] == "netinv64" else W["family"]
+        g64 = W["family"] == "netinv64"
+        if is_rollout:
+            kms = time_calls(lambda k: wl.env.rollout(wl.policy, seed=W["seed"], episode=k, want=("ep_return", "stats"), **wl.kw),
+                             max(5, min(args.steps, 20)))
+            line["roofline"] = rollout_roofline(wl, kms, sm_mhz, counts, hbm_peak, peak_src)
+        wl.close()
+        del wl
         torch.cuda.empty_cache()
-        cls0 = {"invmgmt": pkg.InvManagementLostSalesEnv, "newsvendor": pkg.NewsvendorEnv,
-                "netinv": pkg.NetInvMgmtBacklogEnv}[args.workload]
-        env0 = cls0(num_envs=N, device=dev, env_offset=offset, info_level=0)
-        env0.reset(seed=W["seed"])
-        for _ in range(3):
-            env0.step(a)
-        torch.cuda.synchronize()
-        s0.record()
-        for _ in range(20):
-            env0.step(a)
-        s1.record()
-        torch.cuda.synchronize()
-        sms0 = s0.elapsed_time(s1) / 20
-        ach = N * ab / (sms0 * 1e-3) / 1e9
-        ach_i = N * (ab + ib) / (sms * 1e-3) / 1e9
-        line["roofline_step_api"] = {"kernel": sk, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                                     "frac": ach / hbm_peak,
-                                     "traffic": (counts.get(args.workload + "_step", {}).get("dram_bytes_per_env_step") or 0) * N or None,
-                                     "kernel_ms": sms0, "env_steps_per_s": N / (sms0 * 1e-3),
-                                     "algorithmic_bytes_per_env_step": ab, "instances": N, "peak_source": peak_src,
-                                     "note": "env built with info_level=0: the kernel moves exactly the algorithmic bytes "
-                                             "(actions, observation, reward, flags, state read+write); `traffic` is the "
-                                             "ncu DRAM byte count of the capture WITH info tensors",
-                                     "with_info_tensors": {"kernel_ms": sms, "bytes_per_env_step": ab + ib,
-                                                           "achieved": ach_i, "frac": ach_i / hbm_peak,
-                                                           "env_steps_per_s": N / (sms * 1e-3),
-                                                           "frac_counting_algorithmic_bytes_only": N * ab / (sms * 1e-3) / 1e9 / hbm_peak}}
-        env0.close()
-        del a, env0
-        # ---- the host-driven loop (a policy on the CPU: numpy actions in, observations out every period) ------------
-        # Same step kernel, but the Gymnasium tensors cross PCIe both ways each period and the host waits for them:
-        # this is what the reference's agent loop costs when only the env moves to the GPU.
-        Ns = min(N, 1 << 20)
-        envh = cls0(num_envs=Ns, device=dev, env_offset=offset, info_level=0)
-        obs_d, _ = envh.reset(seed=W["seed"])
-        if args.workload == "invmgmt":
-            a_h = torch.randint(0, 100, (Ns, 3), dtype=torch.int64).pin_memory()
-        elif args.workload == "newsvendor":
-            a_h = (torch.rand((Ns, 1)) * 100).pin_memory()
+        rs = step_api_roofline(fam, dev, N, rank * N, W["seed"], counts, hbm_peak, peak_src, graph64=g64)
+        if is_rollout:
+            line["roofline_step_api"] = rs
         else:
-            a_h = (torch.rand((Ns, len(envh.reorder_links))) * 100).pin_memory()
-        a_d = torch.empty_like(a_h, device=dev)
-        obs_h = torch.empty(obs_d.shape, dtype=obs_d.dtype).pin_memory()
-        rew_h = torch.empty(Ns, dtype=torch.float64).pin_memory()
-        tr_h = torch.empty(Ns, dtype=torch.uint8).pin_memory()
-
-        def host_step():
-            a_d.copy_(a_h, non_blocking=True)
-            o, r, _, tr, _ = envh.step(a_d)
-            obs_h.copy_(o, non_blocking=True)
-            rew_h.copy_(r.view(-1), non_blocking=True)
-            tr_h.copy_(tr.view(-1).view(torch.uint8), non_blocking=True)
-            torch.cuda.synchronize()
-            return float(rew_h[0]) + float(obs_h.view(-1)[0])      # the host policy reads what came back
-
-        for _ in range(3):
-            host_step()
-        hs = 10
-        t0 = time.perf_counter()
-        for _ in range(hs):
-            host_step()
-        hdt = time.perf_counter() - t0
-        line["e2e_step_api"] = {"value": Ns * hs / hdt, "unit": "env-steps/s", "instances": Ns, "steps": hs,
-                                "h2d_bytes_per_step": a_h.numel() * a_h.element_size(),
-                                "d2h_bytes_per_step": obs_h.numel() * obs_h.element_size() + Ns * 9,
-                                "note": "host-driven policy loop on rank 0: actions from pinned host memory, observation + "
-                                        "reward + truncated flags back to pinned host memory, host waits every period "
-                                        "(PCIe-bound; the fused on-device policies exist to avoid exactly this)"}
-        envh.close()
-        del envh, a_d, a_h, obs_h
+            line["roofline"] = rs       # cfg 5 IS the step API: its dominant kernels are the HBM-bound step pair
+        line["e2e_step_api"] = host_step_loop(fam, dev, N, rank * N, W["seed"], graph64=g64)
         torch.cuda.empty_cache()
         if world == 1:
-            line["cpu_baseline"] = cpu_port_rate(args.workload, seconds=10.0)
-            # the other BASELINE.json configs, measured briefly with the same method (fused rollout, CUDA events)
-            others = {}
-            for wname in ("newsvendor", "netinv"):
-                if wname == args.workload:
-                    continue
-                Wo = WORKLOADS[wname]
-                No, To = Wo["envs"], Wo["periods"]
-                if wname == "newsvendor":
-                    eo = pkg.NewsvendorEnv(num_envs=No, device=dev)
-                    ro = lambda ep: eo.rollout("classic", seed=Wo["seed"], episode=ep)  # noqa: E731
-                else:
-                    eo = pkg.NetInvMgmtBacklogEnv(num_envs=No, device=dev)
-                    ro = lambda ep: eo.rollout("constant", order_fraction=0.1, seed=Wo["seed"], episode=ep)  # noqa: E731
-                for k in range(3):
-                    ro(k)
-                torch.cuda.synchronize()
-                o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                o0.record()
-                for k in range(20):
-                    ro(10 + k)
-                o1.record()
-                torch.cuda.synchronize()
-                oms = o0.elapsed_time(o1) / 20
-                others[wname] = {"workload": Wo["name"], "instances": No, "periods": To, "ms_per_rollout": oms,
-                                 "env_steps_per_s": No * To / (oms * 1e-3)}
-                eo.close()
-                del eo
-                torch.cuda.empty_cache()
+            line["cpu_baseline"] = cpu_port_rate(W["cpu"], seconds=10.0)
             if args.workload == "invmgmt":
-                # the north-star target is quoted on InvManagementBacklogEnv; the random policy is cfg 3's second driver
-                for label, cls_o, pol_o, kw_o in (
-                        ("invmgmt_backlog_base_stock", pkg.InvManagementBacklogEnv, "base_stock", dict(safety_factor=1.0)),
-                        ("invmgmt_lost_sales_random", pkg.InvManagementLostSalesEnv, "random", {})):
-                    eo = cls_o(num_envs=N, device=dev)
-                    for k in range(3):
-                        eo.rollout(pol_o, seed=W["seed"], episode=k, **kw_o)
-                    torch.cuda.synchronize()
-                    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    o0.record()
-                    for k in range(20):
-                        eo.rollout(pol_o, seed=W["seed"], episode=10 + k, **kw_o)
-                    o1.record()
-                    torch.cuda.synchronize()
-                    oms = o0.elapsed_time(o1) / 20
-                    others[label] = {"workload": f"{cls_o.__name__} defaults, fused rollout, {pol_o} policy", "instances": N,
-                                     "periods": T, "ms_per_rollout": oms, "env_steps_per_s": N * T / (oms * 1e-3),
-                                     "specialised_kernel": eo.rollout_specialised}
-                    eo.close()
-                    del eo
-                    torch.cuda.empty_cache()
-            line["other_configs"] = others
+                others = {}
+                for wname in ("invmgmt_backlog", "invmgmt_random", "invmgmt_wide", "newsvendor", "netinv", "netinv64_mlp"):
+                    try:
+                        others[wname] = measure_other(wname, dev, counts, hbm_peak, peak_src, sm_mhz)
+                    except Exception as e:  # noqa: BLE001
+                        others[wname] = {"error": repr(e)[:300]}
+                try:
+                    others["netinv64_mlp"]["roofline"] = step_api_roofline("netinv", dev, WORKLOADS["netinv64_mlp"]["envs"], 0,
+                                                                           12000, counts, hbm_peak, peak_src, graph64=True)
+                except Exception as e:  # noqa: BLE001
+                    others["netinv64_mlp"]["roofline_error"] = repr(e)[:300]
+                line["other_configs"] = others
     if rank == 0:
         emit(line)
     if world > 1:

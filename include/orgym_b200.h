@@ -412,6 +412,26 @@ int orgym_sample_demand(const orgym_dist_t* dist, uint64_t seed, int64_t env_off
 int orgym_sample_poisson_mu(const double* mu_dev, uint64_t seed, int64_t env_offset, int64_t count, int32_t period,
                             int device, int64_t* out_dev, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Evaluation report: the summary row of process_and_report_results
+ * (benchmark_InvManagementBacklogEnv.py:493-504, benchmark_NetInvMgmtBacklogEnv.py:320-330) for one batch of
+ * episodes, computed on the device from the per-episode outputs of a rollout -- exact order statistics by radix
+ * select, two-pass variance, sums reduced in a fixed order (bitwise reproducible).  Nothing synchronises the host.
+ *   ep_return_dev  float64[n] episode returns (TotalReward)
+ *   stats_dev      [n,4] (sales, demand, unfulfilled / lost, on-hand sum) as int64 (stats_kind 0), int32 (1) or
+ *                  float64 (2); NULL = reward columns only
+ *   scratch_dev    orgym_report_scratch_bytes(n) bytes, 256-byte aligned
+ *   report_dev     float64[ORGYM_REPORT_LEN]: [0] episodes, [1] mean, [2] median (pandas: midpoint of the two central
+ *                  order statistics), [3] std (ddof = 1), [4] min, [5] max of the returns, [6] mean service level
+ *                  sales/demand (1.0 for an episode without demand, :425), [7] mean unfulfilled quantity, [8] mean of
+ *                  on-hand sum / periods, [9] sum of returns, [10] sum of squared deviations, [11] candidates the
+ *                  select kept after its second pass (diagnostic)
+ * ------------------------------------------------------------------------- */
+#define ORGYM_REPORT_LEN 16
+int64_t orgym_report_scratch_bytes(int64_t num_episodes);
+int orgym_evaluation_report(int device, const double* ep_return_dev, const void* stats_dev, int stats_kind,
+                            int64_t num_episodes, int32_t periods, void* scratch_dev, double* report_dev, void* stream);
+
 /* device timing of the most recent rollout/step launch of this handle is not part of the ABI:
  * time with CUDA events on `stream`. */
 

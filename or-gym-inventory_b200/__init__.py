@@ -23,6 +23,7 @@ from . import network_management_custom  # noqa: F401
 from .adapters import SB3VecEnvAdapter, rllib_env_creator  # noqa: F401
 from .sampling import sample_demand, sample_poisson_mu  # noqa: F401
 from .sharding import allreduce_summary, describe_summary, shard_range  # noqa: F401
-from .metrics import evaluation_report, kth_smallest  # noqa: F401
+from .metrics import (REPORT_FIELDS, evaluation_report, evaluation_report_device, kth_smallest,  # noqa: F401
+                      report_to_dict)
 
 __version__ = "0.1.0"

@@ -149,6 +149,9 @@ SYMBOLS = {
                                              C.POINTER(C.c_double)]),
     "orgym_netinv_codegen": (C.c_int, [C.POINTER(NetConfig), C.c_int, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]),
     "orgym_netinv_is_specialised": (C.c_int, [_H]),
+    "orgym_report_scratch_bytes": (C.c_int64, [C.c_int64]),
+    "orgym_evaluation_report": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
     "orgym_errors": (C.c_int, [_H, C.POINTER(C.c_uint32), C.c_int, C.c_void_p]),
     "orgym_sample_demand": (C.c_int, [C.POINTER(Dist), C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_int,
                                       C.c_void_p, C.c_void_p]),

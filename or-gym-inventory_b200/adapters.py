@@ -40,22 +40,52 @@ class SB3VecEnvAdapter:
         self._seed = None
         return obs.cpu().numpy().astype(self.obs_dtype, copy=False)
 
+    def _buffers(self, obs, rew):
+        """Pinned host staging (allocated once): one batch of asynchronous copies and ONE synchronisation per step."""
+        import torch
+        if getattr(self, "_pin", None) is None:
+            dev = obs.device
+            self._pin = dict(act=torch.empty((self.num_envs,) + tuple(self.action_space.shape),
+                                             dtype=getattr(torch, np.dtype(self.action_space.dtype).name)).pin_memory(),
+                             obs=torch.empty(obs.shape, dtype=obs.dtype).pin_memory(),
+                             rew=torch.empty(rew.shape, dtype=rew.dtype).pin_memory(),
+                             done=torch.empty(self.num_envs, dtype=torch.bool).pin_memory(),
+                             trunc=torch.empty(self.num_envs, dtype=torch.bool).pin_memory())
+            self._act_dev = torch.empty_like(self._pin["act"], device=dev)
+        return self._pin
+
     def step_async(self, actions):
         self._actions = np.asarray(actions).astype(self.action_space.dtype, copy=False)
 
     def step_wait(self):
-        obs, rew, term, trunc, info = self.env.step(self._actions)
-        dones = (term | trunc).cpu().numpy()
-        obs_h = obs.cpu().numpy().astype(self.obs_dtype, copy=False)
-        infos = [{} for _ in range(self.num_envs)]
+        import torch
+        env = self.env
+        if getattr(self, "_pin", None) is not None:       # pinned staging exists after the first step
+            self._pin["act"].numpy()[...] = self._actions.reshape(self._pin["act"].shape)
+            self._act_dev.copy_(self._pin["act"], non_blocking=True)
+            obs, rew, term, trunc, info = env.step(self._act_dev)
+        else:
+            obs, rew, term, trunc, info = env.step(self._actions)
+        pin = self._buffers(obs, rew)
+        pin["obs"].copy_(obs, non_blocking=True)
+        pin["rew"].copy_(rew, non_blocking=True)
+        pin["done"].copy_(term | trunc, non_blocking=True)
+        pin["trunc"].copy_(trunc, non_blocking=True)
+        torch.cuda.current_stream(obs.device).synchronize()
+        dones = pin["done"].numpy().copy()
+        obs_h = pin["obs"].numpy().astype(self.obs_dtype, copy=True)
+        # infos: one shared empty dict for the instances that go on (a list of N references, no Python loop over the
+        # batch); only finished instances get a dict of their own (terminal observation, like DummyVecEnv).  Consumers
+        # such as VecMonitor write into the infos of finished instances only.
+        infos = [{}] * self.num_envs
         idx = np.flatnonzero(dones)
         if idx.size:
-            final = info["final_obs"].cpu().numpy().astype(self.obs_dtype, copy=False)
-            tr = trunc.cpu().numpy()
-            for i in idx:
-                infos[i]["terminal_observation"] = final[i]
-                infos[i]["TimeLimit.truncated"] = bool(tr[i])
-        return obs_h, rew.cpu().numpy().astype(np.float32), dones, infos
+            sel = torch.as_tensor(idx, device=obs.device)
+            final = info["final_obs"].index_select(0, sel).cpu().numpy().astype(self.obs_dtype, copy=False)
+            tr = pin["trunc"].numpy()
+            for k, i in enumerate(idx):
+                infos[i] = {"terminal_observation": final[k], "TimeLimit.truncated": bool(tr[i])}
+        return obs_h, pin["rew"].numpy().astype(np.float32), dones, infos
 
     def step(self, actions):
         self.step_async(actions)

@@ -13,6 +13,7 @@ struct NetDev {
     const double* disc;  // [T] alpha**t
     double I0[NJ], h[NJ], C[NJ], v[NJ], o[NJ];
     uint8_t is_factory[NJ], is_retail[NJ];
+    uint8_t has_seg[NJ];  // the node supplies at least one reorder link (its `consumed` scratch row is written every period)
     int16_t sup[NE], pur[NE], L[NE];
     int32_t roff[NE];
     uint32_t Lmagic[NE];  // ceil(2^32 / L): t % L by multiply-high (0 encodes L <= 1)
@@ -36,6 +37,8 @@ struct NetHandle {
     cudaKernel_t jit_rollout;  // ROLLOUT kernel of the same module
     int jit_threads;
     int jit_stream;            // STEP kernel is the streaming variant (large graphs)
+    int stream_aot;            // large graphs: STEP runs the table-driven ahead-of-time streaming kernel (netinv.cu)
+    int jit_obs_split;         // streaming variant without its observation pass: net_obs_kernel (TMA-staged) follows it
     AliasDev* dem_dev;  // device copy of dev.dem[] for the specialised kernel
 };
 
@@ -81,3 +84,5 @@ int net_jit_build(NetHandle* H, std::string* err);
 int net_jit_launch(const NetHandle* H, const struct NetSimArgs& A, cudaStream_t s);
 std::string net_jit_source(const NetDev& P, int nthr);
 int net_jit_uses_stream(const NetDev& P);
+size_t net_obs_smem(const NetDev& P);    // netinv.cu: shared memory of the TMA-staged observation kernel
+int net_jit_obs_split(const NetDev& P);  // ORGYM_NET_OBS_TMA (default 1) and the observation rows fit in shared memory

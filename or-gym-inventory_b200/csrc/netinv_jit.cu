@@ -49,6 +49,11 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
     const int x = atoi(v);
     return x < lo || x > hi ? dflt : x;
 }
+// 1 (default): the streaming STEP kernel stops after the state update and netinv.cu's TMA-staged net_obs_kernel writes
+// the observation; 0: the kernel's own observation pass (round-1 form, kept for comparison)
+int net_jit_obs_split(const NetDev& P) {
+    return env_int("ORGYM_NET_OBS_TMA", 1, 0, 1) && net_obs_smem(P) <= 200 * 1024;
+}
 // measured on the 64-node graph: the register-staged pass (0) beats the cp.async one (1) by 6 % -- kept as a knob
 static int stream_async() { return env_int("ORGYM_NET_JIT_ASYNC", 0, 0, 1); }
 static int stream_cw() {
@@ -324,9 +329,13 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     if (const char* mb = getenv("ORGYM_NET_JIT_MINBLOCKS_STEP")) mb_step = atoi(mb) > 0 ? atoi(mb) : 1;
     if (const char* mb = getenv("ORGYM_NET_JIT_MINBLOCKS_ROLLOUT")) mb_roll = atoi(mb) > 0 ? atoi(mb) : 1;
     const int stream = net_jit_uses_stream(P);  // large graphs: state stays in HBM, coalesced 32-column tiles
-    if (stream) {
-        int mb = 4;
-        if (const char* mbv = getenv("ORGYM_NET_JIT_MINBLOCKS_STEP")) mb = atoi(mbv) > 0 ? atoi(mbv) : 4;
+    const char* aotv = getenv("ORGYM_NET_STREAM_AOT");
+    if (stream && !(aotv && aotv[0] == '0') && net_obs_smem(P) <= 200 * 1024) {
+        // STEP runs netinv.cu's ahead-of-time streaming kernel: only the fused rollout is generated for this topology
+        o("extern \"C\" __global__ void net_jit_step(const NetSimArgs A, const double* __restrict__ disc, const AliasDev* __restrict__ dem) {}");
+    } else if (stream) {
+        int mb = nthr >= 512 ? 1 : (nthr >= 256 ? 2 : 4);  // 128 registers per thread at any CTA size
+        if (const char* mbv = getenv("ORGYM_NET_JIT_MINBLOCKS_STEP")) mb = atoi(mbv) > 0 ? atoi(mbv) : mb;
         emit_step_stream(o, P, mb);
     }
     else
@@ -392,13 +401,38 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
     o("      }");
     o("    }");
     o("  }");
+    // Software prefetch into L2 (ORGYM_NET_JIT_PREFETCH: 0 = off, 1 = every row this instance will read, issued before
+    // pass A, d >= 2 = the rows of node group g + d - 1 issued before group g): the kernel is bound by the latency of
+    // dependent global loads at 16 warps per SM; a prefetch costs one instruction and no register or scoreboard slot.
+    const int PF = env_int("ORGYM_NET_JIT_PREFETCH", 1, 0, 8);
+    int GROUP = 4;
+    if (const char* gv = getenv("ORGYM_NET_JIT_GROUP")) GROUP = atoi(gv) > 0 ? atoi(gv) : 4;
+    auto emit_prefetch_node = [&](int j, const char* ind) {  // rows pass B reads for node j that pass A does not produce
+        for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
+            const int i = P.pred_idx[z], L = P.L[i];
+            o("%sPF_L2(s_Y + %d * NP + el);", ind, i);
+            if (L > 0) o("%sPF_L2(ring + (%d + t %% %d) * NP + el);", ind, P.roff[i], L);
+        }
+        for (int r = 0; r < M; r++)
+            if (P.rt_node[r] == j) o("%sPF_L2(s_U + %d * NP + el);", ind, r);
+    };
+    if (PF) {
+        o("#define PF_L2(p) asm volatile(\"prefetch.global.L2 [%%0];\" ::\"l\"(p))");
+        o("  if (do_step) {");
+        for (int j = 0; j < J; j++) o("    PF_L2(s_X + %d * NP + el);", j);
+        if (PF == 1)
+            for (int j = 0; j < J; j++) emit_prefetch_node(j, "    ");
+        else
+            for (int j = 0; j < std::min(J, GROUP * (PF - 1)); j++) emit_prefetch_node(j, "    ");
+        o("  }");
+    }
     // ---- pass A: orders, 32 links per action chunk
     o("  double cons = 0.0;");
     for (int j = 0; j < J; j++)
         if (has_seg[j]) o("  double xs%d = 0.0;", j);
     for (int c0 = 0; c0 < E; c0 += 32) {
         const int c1 = std::min(E, c0 + 32);
-        o("  __syncwarp();");
+        o(env_int("ORGYM_NET_JIT_SYNC", 0, 0, 1) ? "  __syncthreads();" : "  __syncwarp();");
         o("  for (int r = wrow0; r < wrow1; r++)");
         o("    if (%d + ln < NE) tile[r * 33 + ln] = A.actions[(e0 + r) * NE + %d + ln];", c0, c0);
         o("  __syncwarp();");
@@ -434,17 +468,21 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
         o("  }");
     }
     // ---- pass B: nodes
+    // ORGYM_NET_JIT_SYNC=1: a CTA-wide barrier after every node group keeps the warps of a CTA inside the same few hundred
+    // instructions, so that a line of this long straight-line kernel is fetched into the instruction cache once per CTA
+    // instead of once per warp (ncu: 7 of 18 stall cycles per issue were instruction fetch).
+    const int SYNC = env_int("ORGYM_NET_JIT_SYNC", 0, 0, 1);
+    o("  double total = 0.0;");
     o("  if (do_step) {");
-    o("    double total = 0.0;");
     std::vector<int> link_done(E, 0);
     // Nodes are independent of each other in this pass (every link has one purchaser, every market link one retailer;
     // R_t / consumed are read-only here), so they are processed in groups: all loads of a group are issued first
     // (dozens of independent loads in flight), then the group's arithmetic and stores.
-    int GROUP = 4;
-    if (const char* gv = getenv("ORGYM_NET_JIT_GROUP")) GROUP = atoi(gv) > 0 ? atoi(gv) : 4;
     for (int j0 = 0; j0 < J; j0 += GROUP) {
         const int j1 = std::min(J, j0 + GROUP);
         o("    {");
+        if (PF >= 2)
+            for (int j = j0 + GROUP * (PF - 1); j < std::min(J, j0 + GROUP * PF); j++) emit_prefetch_node(j, "      ");
         for (int j = j0; j < j1; j++) {  // load phase
             o("      double x%d = s_X[%d * NP + el];", j, j);
             if (has_seg[j]) o("      const double c%d = sc_C[%d * NP + el];", j, j);
@@ -518,6 +556,11 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
             o("        if (A.info_profit) A.info_profit[NET_IIDX(A, e, NJ, %d)] = pj; }", j);
         }
         o("    }");
+        if (SYNC && j1 < J) {
+            o("  }");
+            o("  __syncthreads();");
+            o("  if (do_step) {");
+        }
     }
     for (int i = 0; i < E; i++) {  // reorder links whose purchaser holds no inventory: pipeline bookkeeping only
         if (link_done[i]) continue;
@@ -544,7 +587,11 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
     o("      s_period[el] = 0; s_episode[el] = episode + 1;");
     o("    } else s_period[el] = tn;");
     o("  }");
-    // ---- pass C: observation of the final state, 32 columns at a time
+    // ---- pass C: observation of the final state, 32 columns at a time (only when net_obs_kernel does not follow)
+    if (net_jit_obs_split(P)) {
+        o("}");
+        return;
+    }
     o("  const int tobs = valid ? s_period[el] : 0;");
     {
         // column -> source expression
@@ -638,10 +685,11 @@ int net_jit_build(NetHandle* H, std::string* err) {
     H->jit_threads = 128;
     if (const char* tv = getenv("ORGYM_NET_JIT_THREADS")) {  // tuning knob: 64 / 128 / 256 threads per CTA
         const int t = atoi(tv);
-        if (t == 64 || t == 128 || t == 256) H->jit_threads = t;
+        if (t == 64 || t == 128 || t == 256 || t == 512) H->jit_threads = t;
     }
     std::string src = net_jit_source(P, H->jit_threads);
     H->jit_stream = net_jit_uses_stream(P);
+    H->jit_obs_split = H->jit_stream && net_jit_obs_split(P);
     int rc = orgym_jit_compile(src, "net_jit_step", &H->jit, err);
     if (rc != 0) return rc;
     if (cudaLibraryGetKernel(&H->jit_rollout, H->jit.lib, "net_jit_rollout") != cudaSuccess) {

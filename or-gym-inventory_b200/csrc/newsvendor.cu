@@ -17,7 +17,7 @@
 #define NV_STEP_MINB 8
 #endif
 #ifndef NV_ROLL_MINB
-#define NV_ROLL_MINB 6
+#define NV_ROLL_MINB 5
 #endif
 
 struct NvDev {
@@ -170,6 +170,65 @@ __device__ __forceinline__ double nv_period(const NvDev& P, const NvParams& q, f
     return rew.v;
 }
 
+// The same period for lead_time > 0 with the kind logic resolved by hand instead of carried through every operation.
+// With L > 0 the operand kinds are fixed up to four predicates (Sc notation of nv_period above):
+//   inv = F32 (state[5]);  order = F64;  cap = F32;  dem = PY
+//   capped = cap < order            -> order_qty is cap (F32) instead of order (F64);   pos = min(.) > 0 else PY 0
+//   B      = dem < inv              -> sales is dem (PY: revenue = dem * price in float64) else inv (F32: float32 product)
+//   excess = inv - dem, short = dem - inv are float32 differences; the positive one stays F32, the other becomes PY 0
+// so purchase cost is a float64 product (not capped), a float32 product (capped) or 0.0; holding cost / penalty are
+// float32 products or 0.0.  reward = ((rev - pc) - hc) - lp then evaluates
+//   * entirely in float64 when pc is F64 (float64 wins every promotion),
+//   * otherwise in float32 from the first F32 operand on -- subtracting a PY 0 never changes a value, so that is the
+//     float32 chain started from float32(rev) -- and stays the float64 rev when every operand is PY.
+// qf holds float32(price, cost, h, k), which is what NumPy uses when a Python float meets a float32 scalar (NEP 50).
+struct NvPar32 {
+    float price, cost, h, k;
+};
+__device__ __forceinline__ double nv_period_lt(const NvDev& P, const NvParams& q, const NvPar32& qf, float action,
+                                               long long demand, float pipe0, float psum, float* oq_out, double* parts,
+                                               double* su_out, double* ex_out, double* sh_out) {
+    double a64 = (double)action;                                  // .item() -> Python float (:131)
+    a64 = a64 < 0.0 ? 0.0 : (a64 > P.max_q ? P.max_q : a64);      // np.clip -> np.float64 (:132)
+    const float capf = (float)P.max_inv - psum;                   // int - np.float32 -> float32 (:143)
+    const double capd = (double)capf;
+    const bool capped = capd < a64;                               // min(order_qty, cap)
+    const double mnv = capped ? capd : a64;
+    const bool pos = mnv > 0.0;                                   // max(0, .)
+    const bool pcF32 = pos && capped, pcF64 = pos && !capped;
+    *oq_out = pos ? (capped ? capf : (float)a64) : 0.0f;          // new_pipeline[-1] = order_qty (:179)
+    const double dd = (double)demand;
+    const float df = (float)dd, invf = pipe0;
+    const double invd = (double)invf;
+    const bool B = dd < invd;                                     // min(inv_on_hand, demand) (:149)
+    const double revd = dd * q.price;                             // PY * PY
+    const float revf = invf * qf.price;                           // F32 * PY
+    const float exf = invf - df, shf = df - invf;                 // :152-153
+    const bool exP = exf > 0.0f, shP = shf > 0.0f;
+    const double pcd = a64 * q.cost;                              // F64 * PY (:162)
+    const float pcf = pcF32 ? capf * qf.cost : 0.0f;              // F32 * PY, or PY 0 * PY = 0.0
+    const float hcf = exP ? exf * qf.h : 0.0f;                    // :166
+    const float lpf = shP ? shf * qf.k : 0.0f;                    // :167
+    const double rev_v = B ? revd : (double)revf, hc_v = (double)hcf, lp_v = (double)lpf;
+    const double r64 = ((rev_v - pcd) - hc_v) - lp_v;             // pc is F64: float64 throughout (:170)
+    const float s32 = B ? (float)revd : revf;
+    const float r32 = ((s32 - pcf) - hcf) - lpf;                  // float32 from the first F32 operand on
+    const bool any32 = !B || pcF32 || exP || shP;
+    const double rew = pcF64 ? r64 : (any32 ? (double)r32 : revd);
+    if (parts) {
+        parts[0] = rev_v;
+        parts[1] = pcF64 ? pcd : (double)pcf;
+        parts[2] = hc_v;
+        parts[3] = lp_v;
+    }
+    if (su_out) {
+        *su_out = B ? dd : invd;
+        *ex_out = exP ? (double)exf : 0.0;
+        *sh_out = shP ? (double)shf : 0.0;
+    }
+    return rew;
+}
+
 // ---- reset ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nv_reset_kernel(const __grid_constant__ NvDev P, int64_t N, int64_t npad,
                                                        void* state, int reseed, uint64_t seed, int64_t env_offset,
@@ -293,7 +352,12 @@ __global__ void __launch_bounds__(ORGYM_TILE, NV_STEP_MINB) nv_step_kernel(const
             float pipe0 = P.L > 0 ? row[5] : 0.0f;
             float oq;
             double parts[4];
-            double r = nv_period(P, q, A.actions[e], d, pipe0, psum, &oq, parts, nullptr, nullptr, nullptr);
+            double r;
+            if (P.L > 0) {
+                const NvPar32 qf = {(float)q.price, (float)q.cost, (float)q.h, (float)q.k};
+                r = nv_period_lt(P, q, qf, A.actions[e], d, pipe0, psum, &oq, parts, nullptr, nullptr, nullptr);
+            } else
+                r = nv_period(P, q, A.actions[e], d, pipe0, psum, &oq, parts, nullptr, nullptr, nullptr);
             int sc1 = sc + 1;
             bool trunc = sc1 >= P.T;  // :190
             bool reset_now = trunc && A.autoreset == ORGYM_AUTORESET_SAME_STEP;
@@ -442,6 +506,7 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kern
     } else
         q = nv_draw_params(P, key, A.episode);
     const float fh = (float)q.h, fk = (float)q.k, fmu = (float)q.mu, hi = (float)P.max_q;
+    const NvPar32 qf = {(float)q.price, (float)q.cost, fh, fk};
     // per-episode constants of the drivers (they only read the float32 observation entries h, k, mu)
     double level = 0.0;
     bool fallback = false;
@@ -506,7 +571,11 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kern
         }
         float oq;
         double su, ex, sh;
-        double r = nv_period(P, q, act, d, pipe0, psum, &oq, nullptr, &su, &ex, &sh);
+        double r;
+        if (LT > 0 || L > 0)
+            r = nv_period_lt(P, q, qf, act, d, pipe0, psum, &oq, nullptr, &su, &ex, &sh);
+        else
+            r = nv_period(P, q, act, d, pipe0, psum, &oq, nullptr, &su, &ex, &sh);
         ret += r;
         s_sales += su; s_dem += (double)d; s_lost += sh; s_ex += ex;
         if (valid && A.reward_traj) A.reward_traj[e * P.T + t] = r;

@@ -10,7 +10,46 @@ including the median, by bisection on the order statistic -- is exact over all r
 `summary` (8 sums reduced inside the rollout, `sharding.describe_summary`) is the cheap alternative when only means and
 the standard deviation are needed.
 """
+import ctypes as C
 import math
+
+REPORT_LEN = 16
+REPORT_FIELDS = ("SuccessfulEpisodes", "AvgReward", "MedianReward", "StdReward", "MinReward", "MaxReward",
+                 "AvgServiceLevel", "AvgStockoutQty", "AvgEndInv")
+_STATS_KIND = {"torch.int64": 0, "torch.int32": 1, "torch.float64": 2}
+
+
+def report_to_dict(rep):
+    """float64[REPORT_LEN] (device or host) -> the reference's summary columns as Python numbers."""
+    v = [float(x) for x in rep.reshape(-1)[:9].tolist()]
+    d = dict(zip(REPORT_FIELDS, v))
+    d["SuccessfulEpisodes"] = int(d["SuccessfulEpisodes"])
+    return d
+
+
+def evaluation_report_device(out, periods, *, report=None, scratch=None, stream=None):
+    """The summary row for ONE rank's batch of episodes, computed by the library's report kernels
+    (csrc/report.cu: radix-select median, two-pass std, fixed-order sums) without leaving the device and without a host
+    synchronisation.  `out` is the dict of `env.rollout(...)`; returns (report float64[REPORT_LEN] device tensor,
+    scratch) -- pass both back in to reuse the buffers.  `report_to_dict` turns it into the reference's columns."""
+    import torch
+    from . import _capi
+    ret = out["ep_return"]
+    st = out.get("stats", out.get("stats32"))
+    n = ret.numel()
+    dev = ret.device
+    lib = _capi.lib()
+    need = int(lib.orgym_report_scratch_bytes(n))
+    if scratch is None or scratch.numel() * 8 < need or scratch.device != dev:
+        scratch = torch.empty((need + 7) // 8, dtype=torch.int64, device=dev)
+    if report is None:
+        report = torch.zeros(REPORT_LEN, dtype=torch.float64, device=dev)
+    kind = _STATS_KIND[str(st.dtype)] if st is not None else 0
+    s = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+    _capi.check(lib.orgym_evaluation_report(dev.index, C.c_void_p(ret.data_ptr()),
+                                            C.c_void_p(st.data_ptr() if st is not None else None), kind, n, int(periods),
+                                            C.c_void_p(scratch.data_ptr()), C.c_void_p(report.data_ptr()), C.c_void_p(s)))
+    return report, scratch
 
 
 def _dist(group):

@@ -232,6 +232,16 @@ class NetInvMgmtParams:
             dp = data["dist_param"]
             kind = data.get("dist")
             keys = set(dp)
+            if kind is None and data["demand_dist_func"] is not _np_poisson_marker:
+                # an arbitrary Python callable cannot run on the GPU: the law is inferred from the parameter names, which
+                # is only a guess (a negative-binomial sampler also takes n and p) -- say so instead of guessing silently
+                guess = ("poisson" if keys and keys <= {"lam", "mu"} else "binomial" if keys == {"n", "p"} else
+                         "randint" if keys == {"low", "high"} else "geometric" if keys == {"p"} else None)
+                if guess is not None:
+                    import warnings
+                    warnings.warn(f"Edge {edge}: demand_dist_func is a Python callable; assuming a {guess} distribution "
+                                  f"from dist_param keys {sorted(keys)} (set edge attribute dist='{guess}' to confirm, or "
+                                  "another supported name to override)", stacklevel=3)
             if kind == "poisson" or (kind is None and keys <= {"lam", "mu"} and keys):
                 return _capi.make_dist(_capi.DIST_POISSON, dp.get("lam", dp.get("mu")))
             if kind == "binomial" or (kind is None and keys == {"n", "p"}):
@@ -388,21 +398,32 @@ class NetInvMgmtMasterEnv(BatchedEnv):
         self._has_reset = False
         self._scratch = None
 
-    def reset(self, *, seed=None, options: Optional[Dict] = None):
-        """reset (network_management.py:301-332)."""
+    def _out_tensor(self, t, shape, dtype, what):
+        """A caller-provided output buffer (e.g. slot t of a trajectory tensor): must be a contiguous CUDA tensor of
+        the right shape / dtype on this env's device -- the kernels write into it directly (zero-copy)."""
+        torch = _torch()
+        if not (isinstance(t, torch.Tensor) and t.device == self.device and t.dtype == dtype and
+                tuple(t.shape) == tuple(shape) and t.is_contiguous()):
+            raise ValueError(f"{what} must be a contiguous {dtype} tensor of shape {tuple(shape)} on {self.device}")
+        return t
+
+    def reset(self, *, seed=None, options: Optional[Dict] = None, obs_out=None):
+        """reset (network_management.py:301-332).  obs_out: optional float32 [N, obs_dim] tensor that receives the
+        first observation instead of the env's own buffer."""
         reseed, base = self._resolve_seed(seed)
         mask = None
         if options and options.get("reset_mask") is not None:
             mask = self._to_dev(options["reset_mask"], _torch().uint8, (self.num_envs,))
+        obs = self._obs if obs_out is None else self._out_tensor(obs_out, self._obs.shape, self._obs.dtype, "obs_out")
         _capi.check(_capi.lib().orgym_netinv_reset(self._h, self._ptr(self._state), reseed, C.c_uint64(base),
-                                                   self.env_offset, self._ptr(mask), self._ptr(self._obs),
+                                                   self.env_offset, self._ptr(mask), self._ptr(obs),
                                                    self._stream()))
         self._has_reset = True
         if self.record_history:
             if mask is not None:
                 raise NotImplementedError("record_history keeps all instances in lock-step: reset without a mask")
             self._alloc_history()
-        return self._obs, {}
+        return obs, {}
 
     # -- full-history buffers: the DataFrames the reference keeps (:315-321) as [N, T(+1), columns] tensors; columns in
     # main_nodes / reorder_links / retail_links order, S = reorder links then retail links -----------------------------
@@ -428,25 +449,30 @@ class NetInvMgmtMasterEnv(BatchedEnv):
         self.D[:, t], self.P[:, t] = info["demand"], info["profit_node"]
         self._t_host = t + 1
 
-    def step(self, actions, demand=None):
+    def step(self, actions, demand=None, *, obs_out=None, reward_out=None):
         """step (network_management.py:436-635): actions float32 [N, len(reorder_links)] in sorted link order;
-        optional replayed demand float64 [N, len(retail_links)] in retail_links order."""
+        optional replayed demand float64 [N, len(retail_links)] in retail_links order.  obs_out / reward_out: optional
+        float32 [N, obs_dim] / float64 [N] tensors the kernels write into instead of the env's own buffers (e.g. slot
+        t of a rollout-collection buffer: no copy between the env and the learner's storage)."""
         torch = _torch()
         if not self._has_reset:
             raise RuntimeError("call reset() before step()")
         E, M = len(self.reorder_links), len(self.retail_links)
         a = self._to_dev(actions, torch.float32, (self.num_envs, E))
         d = self._to_dev(demand, torch.float64, (self.num_envs, M)) if demand is not None else None
+        obs = self._obs if obs_out is None else self._out_tensor(obs_out, self._obs.shape, self._obs.dtype, "obs_out")
+        rew = self._reward if reward_out is None else self._out_tensor(reward_out, self._reward.shape, self._reward.dtype,
+                                                                       "reward_out")
         _capi.check(_capi.lib().orgym_netinv_step(
             self._h, self._ptr(self._state), self._ptr(a), self._ptr(d), _AUTORESET[self.autoreset_mode],
-            self._ptr(self._obs), self._ptr(self._reward), self._ptr(self._terminated), self._ptr(self._truncated),
+            self._ptr(obs), self._ptr(rew), self._ptr(self._terminated), self._ptr(self._truncated),
             C.byref(self._info), self._stream()))
         info = dict(self._info_t)
         if self.autoreset_mode == "same_step":
             info["final_obs"] = self._final_obs
         if self.record_history:
             self._record(info)
-        return self._obs, self._reward, self._term_b, self._trunc_b, info
+        return obs, rew, self._term_b, self._trunc_b, info
 
     def export_state(self):
         """(X f64[N,J], Y f64[N,E], U f64[N,M], period i32[N]) in main_nodes / reorder_links / retail_links order."""

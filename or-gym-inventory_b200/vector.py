@@ -131,29 +131,55 @@ class BatchedEnv(_VectorEnvBase):
         if bits & _capi.ERR_INT32_RANGE:
             raise OverflowError("a state value left the int32 range; construct the env with wide_state=True")
 
-    def evaluate(self, policy, episodes=1, *, seed=None, first_episode=0, want=("ep_return", "stats", "summary"),
-                 **policy_kwargs):
-        """The reference's `evaluate_agent` loop (e.g. benchmark_InvManagementLostSalesEnv.py:239-302) for the whole batch:
-        yields, per episode index, a dict of HOST (pinned) numpy-backed tensors with the per-instance results.
-        Rollout k+1 runs on the GPU while the results of rollout k are copied to the host on a second stream
-        (two device buffer sets + two pinned host buffer sets); a yielded dict stays valid until two more
-        episodes have been yielded."""
+    def _episode_periods(self):
+        P = self.params
+        return int(getattr(P, "num_periods", getattr(P, "step_limit", 1)))
+
+    def evaluate(self, policy, episodes=1, *, seed=None, first_episode=0, want=("report",), **policy_kwargs):
+        """The reference's `evaluate_agent` + `process_and_report_results` loop (e.g.
+        benchmark_InvManagementLostSalesEnv.py:239-302, :493-504) for the whole batch: one fused rollout per episode
+        index, yielding a dict of HOST (pinned) tensors per index.
+
+        want=("report",) (default): the reference's summary row -- mean / median / std / min / max of the episode
+          returns, mean service level, stock-out quantity and ending inventory -- computed on the device right after
+          the rollout (csrc/report.cu); only those REPORT_LEN numbers cross PCIe.  `metrics.report_to_dict(res["report"])`
+          names them.  The per-episode tensors stay on the device (`self.last_rollout`).
+        want=("ep_return", "stats", "summary", ...): per-instance results copied to the host (PCIe-bound for large
+          batches: 8-40 B per episode).
+
+        Rollout k+1 runs on the GPU while the results of rollout k are copied on a second stream; three device and
+        three pinned host buffer sets rotate, so a yielded dict stays valid while the NEXT one is being consumed and
+        is overwritten only after two more have been yielded."""
         torch = _torch()
         main = torch.cuda.current_stream(self.device)
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(self.device)
             self._host_sets = {}
-        copy_done = [None, None]
+            self._report_bufs = {}
+        NSET = 3
+        copy_done = [None] * NSET
         pending = None
+        do_report = "report" in want
+        rwant = tuple(w for w in want if w != "report")
+        if do_report:
+            from .metrics import evaluation_report_device
+            stats_name = "stats32" if self._family == "invmgmt" else "stats"
+            rwant = tuple(dict.fromkeys(("ep_return", stats_name) + rwant))
         for k in range(int(episodes)):
-            b = k & 1
+            b = k % NSET
             if copy_done[b] is not None:
                 main.wait_event(copy_done[b])          # device buffers of set b are free again
-            out = self.rollout(policy, seed=seed if k == 0 else None, episode=first_episode + k, want=want,
+            out = self.rollout(policy, seed=seed if k == 0 else None, episode=first_episode + k, want=rwant,
                                buffer_set=b, **policy_kwargs)
+            self.last_rollout = out
+            if do_report:
+                rb = self._report_bufs.setdefault(b, [None, None])
+                rb[0], rb[1] = evaluation_report_device(out, self._episode_periods(), report=rb[0], scratch=rb[1])
+                out = {name: t for name, t in out.items() if name in want}
+                out["report"] = rb[0]
             ready = torch.cuda.Event()
             ready.record(main)
-            host = self._host_sets.setdefault(b, {})
+            host = self._host_sets.setdefault((b, tuple(sorted(out))), {})
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(ready)
                 for name, t in out.items():

@@ -398,3 +398,92 @@ def test_evaluation_report_reproduces_the_reference_summary_row():
     # order statistic by bisection == sort
     assert pkg.kth_smallest(out["ep_return"], 1234) == np.sort(ret)[1234]
     env.close()
+
+
+def _report_reference(ret, st, periods):
+    """pandas restatement of process_and_report_results (benchmark_InvManagementBacklogEnv.py:493-504)."""
+    import pandas as pd
+    st = st.astype(np.float64)
+    sl = np.where(st[:, 1] > 1e-6, st[:, 0] / np.maximum(1e-6, st[:, 1]), 1.0)
+    df = pd.DataFrame(dict(TotalReward=ret, AvgServiceLevel=sl, TotalStockoutQty=st[:, 2], AvgEndingInv=st[:, 3] / periods))
+    return dict(SuccessfulEpisodes=len(ret), AvgReward=df.TotalReward.mean(), MedianReward=df.TotalReward.median(),
+                StdReward=df.TotalReward.std(), MinReward=df.TotalReward.min(), MaxReward=df.TotalReward.max(),
+                AvgServiceLevel=df.AvgServiceLevel.mean(), AvgStockoutQty=df.TotalStockoutQty.mean(),
+                AvgEndInv=df.AvgEndingInv.mean())
+
+
+@pytest.mark.parametrize("case", ["rollout_odd", "rollout_even", "mixed_sign", "constant", "two_values", "n1", "n2", "n3",
+                                  "ties", "wide_range", "float_stats", "big"])
+def test_device_report_kernels_match_pandas(case):
+    """csrc/report.cu (radix-select median, two-pass std, min / max, service-level means) against pandas on rollout
+    outputs and on adversarial synthetic inputs: mixed signs and many binades (first-digit histogram path), all-equal
+    returns, central order statistics in different histogram bins, tiny batches, heavy ties, every stats dtype."""
+    torch = _torch()
+    rng = np.random.default_rng(11)
+    T = 30
+    if case.startswith("rollout"):
+        N = 20001 if case == "rollout_odd" else 65536
+        env = pkg.InvManagementBacklogEnv(num_envs=N, device="cuda:0")
+        out = env.rollout("base_stock", seed=4000, safety_factor=1.0, want=("ep_return", "stats32"))
+        ret, st = out["ep_return"], out["stats32"]
+    else:
+        n = dict(mixed_sign=50001, constant=4097, two_values=2, n1=1, n2=2, n3=3, ties=30000, wide_range=77777,
+                 float_stats=12345, big=3_000_001)[case]
+        if case == "mixed_sign":
+            r = rng.normal(0.0, 500.0, n)
+        elif case == "constant":
+            r = np.full(n, 1234.5)
+        elif case == "two_values":
+            r = np.array([1.0, 1e10])
+        elif case == "ties":
+            r = rng.integers(0, 7, n).astype(np.float64) * 0.25 - 0.5
+        elif case == "wide_range":
+            r = np.exp(rng.uniform(-30, 30, n)) * rng.choice([-1.0, 1.0], n)
+        else:
+            r = rng.normal(3900.0, 300.0, n)
+        s = rng.integers(0, 900, size=(n, 4))
+        s[rng.random(n) < 0.01, 1] = 0                              # episodes without demand: service level 1.0
+        ret = torch.from_numpy(r).cuda()
+        if case == "float_stats":
+            st = torch.from_numpy(s.astype(np.float64)).cuda()
+        elif case in ("ties", "big"):
+            st = torch.from_numpy(s.astype(np.int32)).cuda()
+        else:
+            st = torch.from_numpy(s.astype(np.int64)).cuda()
+    rep, scratch = pkg.evaluation_report_device({"ep_return": ret, "stats": st}, T)
+    got = pkg.report_to_dict(rep)
+    rep2, _ = pkg.evaluation_report_device({"ep_return": ret, "stats": st}, T, report=torch.zeros_like(rep), scratch=scratch)
+    assert torch.equal(rep.view(torch.int64), rep2.view(torch.int64))   # bitwise reproducible, buffers reusable
+    want = _report_reference(ret.cpu().numpy(), st.cpu().numpy(), T)
+    assert got["SuccessfulEpisodes"] == want["SuccessfulEpisodes"]
+    for k in ("MedianReward", "MinReward", "MaxReward"):
+        assert got[k] == want[k], (k, got[k], want[k])
+    for k in ("AvgReward", "AvgServiceLevel", "AvgStockoutQty", "AvgEndInv"):
+        assert np.isclose(got[k], want[k], rtol=1e-11, atol=1e-9), (k, got[k], want[k])
+    if want["SuccessfulEpisodes"] > 1:
+        assert np.isclose(got["StdReward"], want["StdReward"], rtol=1e-9, atol=1e-12), (got["StdReward"], want["StdReward"])
+    else:
+        assert np.isnan(got["StdReward"])
+
+
+def test_evaluate_default_product_is_the_device_report():
+    """env.evaluate() default: per episode index the reference's summary row, computed on the device; only 16 numbers
+    cross PCIe.  Same numbers as the torch / pandas path on the per-episode tensors; dicts stay valid while the next
+    one is being consumed (three buffer sets)."""
+    torch = _torch()
+    N = 10000
+    env = pkg.InvManagementLostSalesEnv(num_envs=N, device="cuda:0")
+    held = []
+    for k, res in enumerate(env.evaluate("base_stock", episodes=5, seed=5000, safety_factor=1.0)):
+        assert set(res) == {"report"} and not res["report"].is_cuda
+        held.append((res, res["report"].clone()))
+        if k >= 1:                                   # the previous result has not been overwritten yet
+            assert torch.equal(held[k - 1][0]["report"], held[k - 1][1])
+        o = env.rollout("base_stock", seed=5000, episode=k, safety_factor=1.0, want=("ep_return", "stats"))
+        want = pkg.evaluation_report(o, env.num_periods)
+        got = pkg.report_to_dict(res["report"])
+        assert got["MedianReward"] == want["MedianReward"] and got["MinReward"] == want["MinReward"]
+        assert np.isclose(got["AvgReward"], want["AvgReward"], rtol=1e-12)
+        assert np.isclose(got["StdReward"], want["StdReward"], rtol=1e-10)
+        assert np.isclose(got["AvgServiceLevel"], want["AvgServiceLevel"], rtol=1e-12)
+    env.close()

@@ -14,14 +14,18 @@ def _torch():
     return torch
 
 
-@pytest.fixture(params=["specialised", "stream", "generic"])
+@pytest.fixture(params=["specialised", "stream_aot", "stream_jit", "stream_jit_fused_obs", "generic"])
 def kernel_mode(request, monkeypatch):
-    """Run the parity tests through all network kernels: the NVRTC-specialised register-resident one, the
-    NVRTC-specialised streaming STEP kernel (meant for large graphs, forced here), and the generic constant-bank
-    interpreter."""
-    monkeypatch.setenv("ORGYM_NET_JIT", "0" if request.param == "generic" else "2")
-    monkeypatch.setenv("ORGYM_NET_JIT_STREAM", "1" if request.param == "stream" else "0")
-    return request.param
+    """Run the parity tests through all network kernels: the NVRTC-specialised register-resident one; the streaming
+    STEP path meant for large graphs, forced here, in its three forms -- table-driven ahead-of-time kernel +
+    observation kernel (the default), generated streaming kernel + observation kernel, generated kernel with its own
+    fused observation pass --; and the generic constant-bank interpreter."""
+    m = request.param
+    monkeypatch.setenv("ORGYM_NET_JIT", "0" if m == "generic" else "2")
+    monkeypatch.setenv("ORGYM_NET_JIT_STREAM", "1" if m.startswith("stream") else "0")
+    monkeypatch.setenv("ORGYM_NET_STREAM_AOT", "1" if m == "stream_aot" else "0")
+    monkeypatch.setenv("ORGYM_NET_OBS_TMA", "0" if m == "stream_jit_fused_obs" else "1")
+    return m
 
 
 def _mk(meta, n, **kw):
@@ -210,6 +214,40 @@ def test_synthetic_64_node_network_vs_oracle(spec):
         assert np.array_equal(o["reward"], rew_h[e])
         assert np.array_equal(o["obs"][-1], obs[e].cpu().numpy())
     env.close()
+
+
+def test_masked_reset_puts_instances_of_one_tile_in_different_periods(kernel_mode):
+    """After reset(options={'reset_mask': ...}) the instances of a 128-instance state tile are in different periods; the
+    observation window of every instance must still be rotated by ITS period (the TMA-staged observation kernel takes
+    its per-instance path for such tiles).  Checked against a second env that is stepped from a fresh reset."""
+    torch = _torch()
+    N, E = 300, 11
+    rng = np.random.default_rng(3)
+    acts = torch.from_numpy((rng.uniform(0, 0.1, size=(12, N, E)) * 1700).astype(np.float32)).cuda()
+    dem = torch.from_numpy(rng.poisson(20, size=(12, N, 1)).astype(np.float64)).cuda()
+    a = pkg.NetInvMgmtBacklogEnv(num_envs=N, device="cuda:0", autoreset_mode="disabled")
+    b = pkg.NetInvMgmtBacklogEnv(num_envs=N, device="cuda:0", autoreset_mode="disabled")
+    a.reset(seed=5)
+    for t in range(5):
+        a.step(acts[t], demand=dem[t])
+    mask = torch.zeros(N, dtype=torch.bool, device="cuda")
+    mask[::3] = True
+    a.reset(options={"reset_mask": mask})
+    b.reset(seed=5)
+    for t in range(5, 12):                       # masked instances of `a` restart at period 0, the others continue
+        oa, ra, *_ = a.step(acts[t], demand=dem[t])
+        ob, rb, *_ = b.step(acts[t], demand=dem[t])
+        assert torch.equal(oa[mask], ob[mask]) and torch.equal(ra[mask], rb[mask])
+    per = a.export_state()[3]
+    assert (per[mask] == 7).all() and (per[~mask] == 12).all()
+    # the instances that were not reset continue their own episode: compare with an uninterrupted run
+    c = pkg.NetInvMgmtBacklogEnv(num_envs=N, device="cuda:0", autoreset_mode="disabled")
+    c.reset(seed=5)
+    for t in range(12):
+        oc, rc, *_ = c.step(acts[t], demand=dem[t])
+    assert torch.equal(oa[~mask], oc[~mask]) and torch.equal(ra[~mask], rc[~mask])
+    for e in (a, b, c):
+        e.close()
 
 
 def test_autoreset_next_step(kernel_mode):

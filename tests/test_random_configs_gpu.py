@@ -133,13 +133,14 @@ def _random_graph(rng):
     return g
 
 
-@pytest.mark.parametrize("mode", ["specialised", "stream", "generic"])
+@pytest.mark.parametrize("mode", ["specialised", "stream", "stream_jit", "generic"])
 @pytest.mark.parametrize("case", range(6 * STRESS))
 def test_netinv_random_graph(case, mode, monkeypatch):
     from oracle import oracle
     torch = _torch()
     monkeypatch.setenv("ORGYM_NET_JIT", "0" if mode == "generic" else "2")
-    monkeypatch.setenv("ORGYM_NET_JIT_STREAM", "1" if mode == "stream" else "0")
+    monkeypatch.setenv("ORGYM_NET_JIT_STREAM", "1" if mode.startswith("stream") else "0")
+    monkeypatch.setenv("ORGYM_NET_STREAM_AOT", "0" if mode == "stream_jit" else "1")
     rng = np.random.default_rng(3000 + case)
     g = _random_graph(rng)
     T = int(rng.integers(4, 26))
