@@ -330,6 +330,8 @@ class MlpEpisode:
         torch.manual_seed(0)
         self.mlp = torch.nn.Sequential(torch.nn.Linear(env.obs_dim, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64),
                                        torch.nn.Tanh(), torch.nn.Linear(64, E), torch.nn.Sigmoid()).to(dev)
+        with torch.no_grad():                 # observations are O(1e3): the input scaling lives in the first layer
+            self.mlp[0].weight.mul_(1e-3)
         self.high = torch.from_numpy(env.single_action_space.high).to(dev) * 0.05
         self.obs = torch.zeros((T + 1, N, env.obs_dim), dtype=torch.float32, device=dev)
         self.act = torch.zeros((T, N, E), dtype=torch.float32, device=dev)
@@ -365,7 +367,7 @@ class MlpEpisode:
         env.reset(obs_out=self.obs[0])        # next episode of the same keys (episode counter += 1 on the device)
         with torch.no_grad():
             for t in range(T):
-                torch.mul(self.mlp(self.obs[t] * 1e-3), self.high, out=self.act[t])
+                torch.mul(self.mlp(self.obs[t]), self.high, out=self.act[t])
                 env.step(self.act[t], obs_out=self.obs[t + 1], reward_out=self.rew[t])
             ret = self.rew.sum(dim=0)
             self.summary[0:1].fill_(float(self.N))

@@ -29,7 +29,11 @@ out = env.rollout("base_stock", seed=4000, safety_factor=1.0, want=("ep_return",
 print("fused rollout, base-stock:", og.evaluation_report(out, env.num_periods))
 print("specialised kernel in use:", env.rollout_specialised)
 
-# 3. many episodes, results streamed to pinned host memory while the next rollout runs
+# 3. many episodes: per batch the reference's summary row is computed on the device (csrc/report.cu) and only those 16
+#    numbers are copied to pinned host memory, while the next rollout already runs
 for k, res in enumerate(env.evaluate("base_stock", episodes=5, seed=4000, safety_factor=1.0)):
+    print("episode batch", k, og.report_to_dict(res["report"]))
+#    per-instance results instead (PCIe-bound for large batches): want=("ep_return", "stats", "summary")
+for k, res in enumerate(env.evaluate("base_stock", episodes=2, seed=4000, safety_factor=1.0, want=("ep_return",))):
     print("episode batch", k, "mean return", float(res["ep_return"].mean()))
 env.close()

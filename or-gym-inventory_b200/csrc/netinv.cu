@@ -698,6 +698,9 @@ __global__ void __launch_bounds__(NET_OBS_THREADS) net_obs_kernel(const __grid_c
     __syncthreads();
     const double* src = (const double*)tile + el0 + lane;  // + row * 128
     float* orow = out + (size_t)lane * W;
+    // all of this warp's columns are requested into L2 at once (one instruction each, no register, no scoreboard slot):
+    // the batched loads below then wait for L2, not for HBM, and the CTA's 145 KB are in flight from the first cycle
+    for (int c = warp; c < W; c += NW) prefetch_l2(src + (size_t)colrow[c] * NET_TILE);
     for (int c0 = warp; c0 < W; c0 += NW * NET_OBS_BATCH) {
         double v[NET_OBS_BATCH];
 #pragma unroll
@@ -897,11 +900,12 @@ extern "C" int orgym_netinv_create(const orgym_netinv_config_t* c, int64_t num_e
             // 10-15 s, once: cubins are cached on disk); ORGYM_NET_JIT=0 never, =1 always, =2 always and fail loudly
             const char* jv = getenv("ORGYM_NET_JIT");
             const bool want_jit = jv ? jv[0] != '0' : (P.E <= 128);
-            // large graphs step through the table-driven streaming kernel + net_obs_kernel (no NVRTC needed for STEP);
-            // ORGYM_NET_STREAM_AOT=0 keeps the generated streaming kernel of netinv_jit.cu, ORGYM_NET_JIT=0 the generic one
+            // large graphs: ORGYM_NET_STREAM_AOT=1 steps through the table-driven streaming kernel (no NVRTC needed for
+            // STEP; measured 0.44 ms on the 64-node graph against 0.29 ms for the generated kernel of netinv_jit.cu, which
+            // therefore stays the default); ORGYM_NET_JIT=0 selects the generic kernel
             {
                 const char* av = getenv("ORGYM_NET_STREAM_AOT");
-                H->stream_aot = net_jit_uses_stream(P) && !(av && av[0] == '0') && !(jv && jv[0] == '0') &&
+                H->stream_aot = net_jit_uses_stream(P) && (av && av[0] == '1') && !(jv && jv[0] == '0') &&
                                 net_obs_smem(P) <= 200 * 1024;
             }
             if (want_jit) {

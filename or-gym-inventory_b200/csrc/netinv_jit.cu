@@ -330,11 +330,13 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     if (const char* mb = getenv("ORGYM_NET_JIT_MINBLOCKS_ROLLOUT")) mb_roll = atoi(mb) > 0 ? atoi(mb) : 1;
     const int stream = net_jit_uses_stream(P);  // large graphs: state stays in HBM, coalesced 32-column tiles
     const char* aotv = getenv("ORGYM_NET_STREAM_AOT");
-    if (stream && !(aotv && aotv[0] == '0') && net_obs_smem(P) <= 200 * 1024) {
+    if (stream && (aotv && aotv[0] == '1') && net_obs_smem(P) <= 200 * 1024) {
         // STEP runs netinv.cu's ahead-of-time streaming kernel: only the fused rollout is generated for this topology
         o("extern \"C\" __global__ void net_jit_step(const NetSimArgs A, const double* __restrict__ disc, const AliasDev* __restrict__ dem) {}");
     } else if (stream) {
-        int mb = nthr >= 512 ? 1 : (nthr >= 256 ? 2 : 4);  // 128 registers per thread at any CTA size
+        // 64 registers per thread: without the observation pass the kernel spills little, and measured on the 64-node
+        // graph 32 resident warps per SM beat 16 (0.470 vs 0.486 ms for the step pair; (256, 4) is equivalent)
+        int mb = nthr >= 512 ? 2 : (nthr >= 256 ? 4 : 8);
         if (const char* mbv = getenv("ORGYM_NET_JIT_MINBLOCKS_STEP")) mb = atoi(mbv) > 0 ? atoi(mbv) : mb;
         emit_step_stream(o, P, mb);
     }

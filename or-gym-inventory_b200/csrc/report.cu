@@ -178,14 +178,23 @@ __global__ void __launch_bounds__(RTHR) report_pass(int pass, const double* __re
             const bool m0 = pre == p0, m1 = !same && pre == p1;
             if (m0) atomicAdd(&sh[0][(unsigned int)(u >> shift) & mask], 1u);
             if (m1) atomicAdd(&sh[1][(unsigned int)(u >> shift) & mask], 1u);
-            if (APPEND) {
-                if (m0) {
-                    const unsigned long long at = atomicAdd(&S->list_n[0], 1ULL);
-                    if ((long long)at < cap) list[at] = u;
+            if (APPEND) {  // warp-aggregated append: one atomic per warp and list
+                const unsigned act = __activemask();
+                const unsigned b0 = __ballot_sync(act, m0), b1 = __ballot_sync(act, m1);
+                const int lane = threadIdx.x & 31;
+                if (b0) {
+                    unsigned long long base = 0ULL;
+                    if (lane == __ffs(b0) - 1) base = atomicAdd(&S->list_n[0], (unsigned long long)__popc(b0));
+                    base = __shfl_sync(act, base, __ffs(b0) - 1);
+                    const unsigned long long at = base + __popc(b0 & ((1u << lane) - 1u));
+                    if (m0 && (long long)at < cap) list[at] = u;
                 }
-                if (m1) {
-                    const unsigned long long at = atomicAdd(&S->list_n[1], 1ULL);
-                    if ((long long)at < cap) list[cap + at] = u;
+                if (b1) {
+                    unsigned long long base = 0ULL;
+                    if (lane == __ffs(b1) - 1) base = atomicAdd(&S->list_n[1], (unsigned long long)__popc(b1));
+                    base = __shfl_sync(act, base, __ffs(b1) - 1);
+                    const unsigned long long at = base + __popc(b1 & ((1u << lane) - 1u));
+                    if (m1 && (long long)at < cap) list[cap + at] = u;
                 }
             }
           }
@@ -224,11 +233,21 @@ __global__ void __launch_bounds__(RTHR) report_pick(int pass, int sub, long long
     __shared__ int s_digit[2];
     __shared__ unsigned long long s_below[2];
     const int tid = threadIdx.x;
-    if ((pass == 0 && sub == 0) || pass == 1) {  // partial rows -> sums, in row order
+    if ((pass == 0 && sub == 0) || pass == 1) {
+        // partial rows -> sums in a fixed order: 64 threads per column add a strided subset of the rows, then the 64
+        // partial results are added in thread order (bitwise reproducible for a given grid size)
+        __shared__ double part[4][64];
         const int ncol = pass == 0 ? 4 : 1;
+        const int col = tid >> 6, sub64 = tid & 63;
+        if (col < ncol) {
+            double x = 0.0;
+            for (int r = sub64; r < npart; r += 64) x += partials[(size_t)r * 8 + col];
+            part[col][sub64] = x;
+        }
+        __syncthreads();
         if (tid < ncol) {
             double x = 0.0;
-            for (int r = 0; r < npart; r++) x += partials[(size_t)r * 8 + tid];
+            for (int q = 0; q < 64; q++) x += part[tid][q];
             sums[tid] = x;
         }
         __syncthreads();
