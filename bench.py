@@ -289,7 +289,8 @@ class Rollout:
             self.env = pkg.NetInvMgmtBacklogEnv(num_envs=N, device=dev, env_offset=offset)
             self.policy, self.kw = "constant", dict(order_fraction=0.1)
             self.dtype = "f64"
-        self.launches_per_call = 2      # rollout kernel + the fixed-order reduction of the block partial sums
+        # rollout kernel + the fixed-order reduction of the block partial sums (+ the newsvendor's order-level kernel)
+        self.launches_per_call = 3 if W["family"] == "newsvendor" else 2
         self.env_steps_per_call = N * self.T
 
     def call(self, ep):
@@ -302,7 +303,7 @@ class Rollout:
                 return ("inv_jit_rollout_rnd" if self.policy == "random" else "inv_jit_rollout_bs") + " (specialised at run time, NVRTC)"
             return "inv_rollout_kernel<3,true,%s>" % ("long long" if self.wname == "invmgmt_wide" else "int")
         if fam == "newsvendor":
-            return "nv_rollout_kernel<5>"
+            return "nv_rollout_kernel<5> (+ nv_level_kernel: per-episode Poisson quantile)"
         return "net_jit_rollout" if self.env.specialised else "net_sim_kernel<128> (generic)"
 
     def count_key(self):

@@ -68,6 +68,16 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
     const bool episode_sum = iprofit && undiscounted && inv_jit_profit_is_exact(S, T);
     const char* W4[4] = {"w.x", "w.y", "w.z", "w.w"};
     const char* A4[4] = {"a4.x", "a4.y", "a4.z", "a4.w"};
+    // (random policy) periods re-rolled into a loop over blocks of UNR periods -- see below; the per-period discount
+    // factors then come from a constant-memory table (uniform loads)
+    int UNR = bs ? 0 : env_int("ORGYM_INV_JIT_RND_UNROLL", 8, 0, 32);
+    if (UNR % 4 != 0 || T < 2 * UNR) UNR = 0;
+    if (UNR > 0 && !(iprofit && episode_sum)) {
+        o("__constant__ double c_disc[%d] = {", T);
+        for (int t = 0; t < T; t++)
+            o("    %s,", lit(iprofit ? std::ldexp(S.disc[(size_t)t], qexp) : S.disc[(size_t)t]).c_str());
+        o("};");
+    }
     o("extern \"C\" __global__ void __launch_bounds__(NTHR, %d) %s(const InvJitArgs A) {", min_blocks, name);
     // alias table, one 32-bit word per bucket: (ceil(threshold / K) << log2k) | alias.  The acceptance test of
     // alias_draw, frac < threshold with frac = w << log2k (low log2k bits zero), is equivalent to
@@ -99,8 +109,30 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
     o("  double ret = 0.0; int s_sales = 0, s_dem = 0, s_stock = 0, s_inv = 0;");
     if (episode_sum) o("  long long acc = 0;");
     o("  uint4 w = make_uint4(0u, 0u, 0u, 0u);");
-    for (int t = 0; t < T; t++) {
-        o("  {  // ---- period %d", t);
+    // Random policy: nothing folds (every stage sees random orders), and 30 straight-line periods are ~3000 instructions
+    // that every warp fetches exactly once -- ncu showed `no_instruction` as that kernel's largest stall.  Its periods are
+    // therefore emitted as a LOOP over blocks of UNR periods (UNR a multiple of 4, so the Philox word of a period stays a
+    // compile-time choice) with the lead-time rings shifted by register moves instead of being indexed by t mod L, plus a
+    // straight-line tail: a few hundred instructions that stay in the instruction cache.  Same arithmetic, same order.
+    const bool shift = UNR > 0;                      // ring slot 0 = arriving now; shifted at the end of the period
+    const int Tloop = UNR > 0 ? T - T % UNR : 0;
+    // emits period t; inside the loop t = tb + u is symbolic and only u is known here
+    auto emit_period = [&](int t, int u, bool in_loop) {
+        char tx[32], bx[32], dx[48];
+        if (in_loop) {
+            snprintf(tx, sizeof(tx), "(unsigned)(tb + %d)", u);
+            snprintf(bx, sizeof(bx), "(unsigned)((tb >> 2) + %d)", u >> 2);
+            snprintf(dx, sizeof(dx), "c_disc[tb + %d]", u);
+        } else {
+            snprintf(tx, sizeof(tx), "%uu", (unsigned)t);
+            snprintf(bx, sizeof(bx), "%uu", (unsigned)(t >> 2));
+            snprintf(dx, sizeof(dx), "%s", lit(iprofit ? std::ldexp(S.disc[(size_t)t], qexp) : S.disc[(size_t)t]).c_str());
+        }
+        const int w4 = (in_loop ? u : t) & 3;
+        if (in_loop)
+            o("  {  // ---- period tb + %d", u);
+        else
+            o("  {  // ---- period %d", t);
         // policy
         if (bs) {
             for (int i = 0; i < n; i++) {
@@ -110,14 +142,14 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
         } else {
             o("    uint4 a4;");
             for (int i = 0; i < n; i++) {
-                if ((i & 3) == 0) o("    a4 = philox_block(key, %uu, ep, STREAM_ACTION, %uu);", (unsigned)t, (unsigned)(i >> 2));
+                if ((i & 3) == 0) o("    a4 = philox_block(key, %s, ep, STREAM_ACTION, %uu);", tx, (unsigned)(i >> 2));
                 o("    const int q_%d = (int)mulhi32(%s, %lluu);", i, A4[i & 3], (unsigned long long)(S.c[i] + 1));
             }
         }
         // demand
         if (S.log2k > 0) {
-            if ((t & 3) == 0) o("    w = philox_block(key, %uu, ep, STREAM_DEMAND, 0u);", (unsigned)(t >> 2));
-            o("    int dl; { const unsigned int wv = %s, pe = tab[wv >> %d];", W4[t & 3], 32 - S.log2k);
+            if (w4 == 0) o("    w = philox_block(key, %s, ep, STREAM_DEMAND, 0u);", bx);
+            o("    int dl; { const unsigned int wv = %s, pe = tab[wv >> %d];", W4[w4], 32 - S.log2k);
             o("      dl = %d + (int)((((wv << %d) | %uu) < pe) ? (wv >> %d) : (pe & %uu)); }", S.base, S.log2k, (unsigned)(K - 1),
               32 - S.log2k, (unsigned)(K - 1));
         } else {
@@ -136,7 +168,7 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
             if (S.L[i] == 0)
                 o("    int Ic_%d = I_%d + r_%d;", i, i, i);
             else
-                o("    int Ic_%d = I_%d + rr%d_%d;", i, i, i, t % S.L[i]);
+                o("    int Ic_%d = I_%d + rr%d_%d;", i, i, i, shift ? 0 : t % S.L[i]);
         }
         if (S.base >= 0)
             o("    const int d = dl;");  // the alias table's support starts at base >= 0: max(0, .) is the identity
@@ -203,8 +235,7 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
                 o("    acc = pa;");
             else  // |pa| < 2^51 (the proof leaves one bit of head-room): exact int64 -> float64 through the 2^52 + 2^51
                   // offset (two integer adds and one DADD instead of an I2F.F64.S64 on the quarter-rate pipe)
-                o("    ret += %s * (__longlong_as_double(pa + 0x4338000000000000LL) - 0x1.8p52);",
-                  lit(std::ldexp(S.disc[(size_t)t], qexp)).c_str());
+                o("    ret += %s * (__longlong_as_double(pa + 0x4338000000000000LL) - 0x1.8p52);", dx);
         } else if (exact) {
             // every operation is exact (inv_jit_profit_is_exact): one fused chain, (up - uc) folded into one coefficient
             o("    double pr = 0.0;");
@@ -216,7 +247,7 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
                 else
                     o("    pr = fma(%s, (double)r_%d, pr);", lit(S.up[j] - S.uc[j]).c_str(), j - 1);
             }
-            o("    ret += %s * pr;", lit(S.disc[(size_t)t]).c_str());
+            o("    ret += %s * pr;", dx);
         } else {
             for (int j = 0; j <= n; j++) {
                 if (j == 0)
@@ -233,7 +264,7 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
             }
             o("    double pr = 0.0;");
             for (int j = 0; j <= n; j++) o("    pr = pr + tm_%d;", j);
-            o("    ret += %s * pr;", lit(S.disc[(size_t)t]).c_str());
+            o("    ret += %s * pr;", dx);
         }
         // statistics and state
         o("    s_sales += s0; s_dem += d; s_stock += U_0;");
@@ -243,11 +274,24 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
         // rings: slot t mod L_i held R[t - L_i] / the request of period t - L_i
         for (int i = 0; i < n; i++) {
             if (S.L[i] == 0) continue;
+            if (shift) {  // slot 0 has arrived: everything moves one period closer, the new order enters at the back
+                for (int q = 0; q + 1 < S.L[i]; q++) o("    rr%d_%d = rr%d_%d;", i, q, i, q + 1);
+                o("    rr%d_%d = r_%d;", i, S.L[i] - 1, i);
+                continue;
+            }
             const int s = t % S.L[i];
             if (bs) o("    ps_%d = ps_%d + q_%d - ar%d_%d; ar%d_%d = q_%d;", i, i, i, i, s, i, s, i);
             o("    rr%d_%d = r_%d;", i, s, i);
         }
         o("  }");
+    };
+    if (UNR > 0) {
+        o("  for (int tb = 0; tb < %d; tb += %d) {", Tloop, UNR);
+        for (int u = 0; u < UNR; u++) emit_period(0, u, true);
+        o("  }");
+        for (int t = Tloop; t < T; t++) emit_period(t, 0, false);
+    } else {
+        for (int t = 0; t < T; t++) emit_period(t, 0, false);
     }
     if (episode_sum) o("  ret = (double)acc * %s;", lit(std::ldexp(1.0, qexp)).c_str());
     // outputs: identical to the ahead-of-time kernel

@@ -334,8 +334,9 @@ std::string net_jit_source(const NetDev& P, int nthr) {
         // STEP runs netinv.cu's ahead-of-time streaming kernel: only the fused rollout is generated for this topology
         o("extern \"C\" __global__ void net_jit_step(const NetSimArgs A, const double* __restrict__ disc, const AliasDev* __restrict__ dem) {}");
     } else if (stream) {
-        // 64 registers per thread: without the observation pass the kernel spills little, and measured on the 64-node
-        // graph 32 resident warps per SM beat 16 (0.470 vs 0.486 ms for the step pair; (256, 4) is equivalent)
+        // 64 registers per thread: a launch of 2^17 instances is 28 warps per SM, so with 8 CTAs per SM the whole batch
+        // is resident in one wave (measured on the 64-node graph: 0.470 vs 0.486 ms for the step pair at 128 registers;
+        // (256, 4) and (64, 16) are equivalent)
         int mb = nthr >= 512 ? 2 : (nthr >= 256 ? 4 : 8);
         if (const char* mbv = getenv("ORGYM_NET_JIT_MINBLOCKS_STEP")) mb = atoi(mbv) > 0 ? atoi(mbv) : mb;
         emit_step_stream(o, P, mb);
@@ -406,9 +407,11 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
     // Software prefetch into L2 (ORGYM_NET_JIT_PREFETCH: 0 = off, 1 = every row this instance will read, issued before
     // pass A, d >= 2 = the rows of node group g + d - 1 issued before group g): the kernel is bound by the latency of
     // dependent global loads at 16 warps per SM; a prefetch costs one instruction and no register or scoreboard slot.
-    const int PF = env_int("ORGYM_NET_JIT_PREFETCH", 1, 0, 8);
-    int GROUP = 4;
-    if (const char* gv = getenv("ORGYM_NET_JIT_GROUP")) GROUP = atoi(gv) > 0 ? atoi(gv) : 4;
+    const int PF = env_int("ORGYM_NET_JIT_PREFETCH", 0, 0, 8);  // measured: no gain (0.435 / 0.428 vs 0.419 ms), off by default
+    // nodes per load group in pass B: with the 64-register budget below, one node per group measured fastest on the
+    // 64-node graph (0.419 ms for the step pair; 2: 0.433, 3: 0.449, 4: 0.470) -- fewer live values, fewer spills
+    int GROUP = 1;
+    if (const char* gv = getenv("ORGYM_NET_JIT_GROUP")) GROUP = atoi(gv) > 0 ? atoi(gv) : 1;
     auto emit_prefetch_node = [&](int j, const char* ind) {  // rows pass B reads for node j that pass A does not produce
         for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
             const int i = P.pred_idx[z], L = P.L[i];

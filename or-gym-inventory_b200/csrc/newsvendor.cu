@@ -434,10 +434,22 @@ __device__ __forceinline__ double poisson_ppf_dev(double q, double mu, const dou
     double term = exp(-mu + lo * log(mu) - lgamma(lo + 1.0)), cdf = 0.0;  // term = pmf(k), cdf = P(X < k)
     int k = (int)lo;
     const int kmu = mu < 1e9 ? (int)mu : 1000000000;  // for integer k: k > mu <=> k > floor(mu)
+    // Every lane walks the reciprocal table at its own k, so a warp load is a gather: with four 8-byte loads per block at
+    // an arbitrary offset it touched ~20 sectors per load and the L1 data stage bounded the search (ncu, round 2).
+    // Up to three single steps first bring k + 1 to a multiple of 4; the block's four reciprocals are then one aligned
+    // 32-byte piece -- two 16-byte loads, one sector per lane.  Term-by-term the arithmetic is unchanged.
+    while (((k + 1) & 3) != 0 && k + 1 <= ORGYM_RCP_N) {
+        const double c = cdf + term;
+        if (c >= q) return (double)k;
+        term *= mu * rcp[k + 1];
+        ++k;
+        if (term == 0.0 && k > kmu) return (double)k;
+        cdf = c;
+    }
     while (k + 4 <= ORGYM_RCP_N) {
-        const double* pr = rcp + k;
-        const double t0 = term, t1 = t0 * (mu * pr[1]), t2 = t1 * (mu * pr[2]), t3 = t2 * (mu * pr[3]),
-                     t4 = t3 * (mu * pr[4]);
+        const double2 ra = *reinterpret_cast<const double2*>(rcp + k + 1), rb = *reinterpret_cast<const double2*>(rcp + k + 3);
+        const double t0 = term, t1 = t0 * (mu * ra.x), t2 = t1 * (mu * ra.y), t3 = t2 * (mu * rb.x),
+                     t4 = t3 * (mu * rb.y);
         const double c0 = cdf + t0, c1 = c0 + t1, c2 = c1 + t2, c3 = c2 + t3;
         if (c3 >= q) return (double)(k + (c0 >= q ? 0 : (c1 >= q ? 1 : (c2 >= q ? 2 : 3))));
         if (t4 == 0.0) {  // underflow beyond the mean: q is within rounding of 1
@@ -472,6 +484,7 @@ struct NvRolloutArgs {
     const int64_t* demand;
     int64_t d_se, d_st;
     const double* fixed;
+    const double* level_in;  // classic / (s,S): the episode's order-up-to level, computed by nv_level_kernel (else null)
     double* ep_return;
     double* stats;
     double* reward_traj;
@@ -481,6 +494,32 @@ struct NvRolloutArgs {
 };
 
 #define NV_ROLL_THREADS 128
+
+// per-episode order-up-to level of the classic-newsvendor and (s,S) drivers: they only read the float32 observation
+// entries h, k, mu (benchmark_newsvendor.py:113-161, benchmark_newsvendor_sb3_rllib.py:363-371)
+__device__ __forceinline__ bool nv_classic_fallback(float fh, float fk) {
+    const float hk = fh + fk;
+    return hk <= 1e-6f || fk < 0.0f || fh < 0.0f;
+}
+__device__ __forceinline__ double nv_policy_level(const NvDev& P, int policy, double param0, int L, float fh, float fk, float fmu) {
+    double level = 0.0;
+    if (policy == ORGYM_NV_POLICY_CLASSIC) {
+        if (!nv_classic_fallback(fh, fk)) {
+            const float cr = fk / (fh + fk);
+            const float eff = (fmu * (float)(L + 1)) * (float)param0;
+            level = poisson_ppf_dev((double)cr, eff > 1e-6f ? (double)eff : 1e-6, P.rcp);
+        }
+    } else {
+        if (fh + fk > 1e-6f) {
+            float cr = fk / (fh + fk);
+            cr = cr < 0.001f ? 0.001f : (cr > 0.999f ? 0.999f : cr);
+            const float eff = fmu * (float)(L + 1);
+            level = poisson_ppf_dev((double)cr, eff > 1e-6f ? (double)eff : 1e-6, P.rcp);
+        }
+        level = level > 0.0 ? level : 0.0;
+    }
+    return level;
+}
 
 __device__ __forceinline__ float clipf(float q, float hi) { return q < 0.0f ? 0.0f : (q > hi ? hi : q); }
 
@@ -511,22 +550,10 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kern
     double level = 0.0;
     bool fallback = false;
     if (A.policy == ORGYM_NV_POLICY_CLASSIC) {  // benchmark_newsvendor.py:113-161 (k_vs_h)
-        float hk = fh + fk;
-        fallback = hk <= 1e-6f || fk < 0.0f || fh < 0.0f;
-        if (!fallback) {
-            float cr = fk / hk;
-            float eff = (fmu * (float)(L + 1)) * (float)A.param0;
-            level = poisson_ppf_dev((double)cr, eff > 1e-6f ? (double)eff : 1e-6, P.rcp);
-        }
-    } else if (A.policy == ORGYM_NV_POLICY_SS) {  // benchmark_newsvendor_sb3_rllib.py:363-371
-        if (fh + fk > 1e-6f) {
-            float cr = fk / (fh + fk);
-            cr = cr < 0.001f ? 0.001f : (cr > 0.999f ? 0.999f : cr);
-            float eff = fmu * (float)(L + 1);
-            level = poisson_ppf_dev((double)cr, eff > 1e-6f ? (double)eff : 1e-6, P.rcp);
-        }
-        level = level > 0.0 ? level : 0.0;
-    }
+        fallback = nv_classic_fallback(fh, fk);
+        level = A.level_in ? (valid ? A.level_in[e] : 0.0) : nv_policy_level(P, A.policy, A.param0, L, fh, fk, fmu);
+    } else if (A.policy == ORGYM_NV_POLICY_SS)  // benchmark_newsvendor_sb3_rllib.py:363-371
+        level = A.level_in ? (valid ? A.level_in[e] : 0.0) : nv_policy_level(P, A.policy, A.param0, L, fh, fk, fmu);
     const PoisSplit ps = poisson_split(P.pt, q.mu);  // per-episode constants of the demand sampler
     uint4 dw = make_uint4(0, 0, 0, 0);
     __shared__ double pcdf[ORGYM_PT_CDF * NV_ROLL_THREADS];  // cdf of the Poisson(r) remainder, [k][thread]
@@ -651,6 +678,32 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kern
     }
 }
 
+
+// The Poisson quantile behind that level is a serial float64 recurrence of a few hundred terms per episode.  Inside the
+// rollout kernel (96 registers, 5 warps per scheduler) its latency is exposed: 19 % of the instructions but ~40 % of the
+// time of a classic-policy rollout.  As a kernel of its own -- one thread per episode, nothing else live -- it runs at
+// several times the occupancy and hides that latency; the level travels to the rollout kernel through the episode's
+// slot of the ep_return output array (written here, read at the start of the rollout, overwritten with the return at
+// its end), so no extra memory is needed.  Same arithmetic, same value.
+struct NvLevelArgs {
+    int64_t N, env_offset;
+    uint64_t seed;
+    uint32_t episode;
+    int policy;
+    double param0;
+    const double* fixed;
+    double* level_out;
+};
+__global__ void __launch_bounds__(256, 4) nv_level_kernel(const __grid_constant__ NvDev P, const __grid_constant__ NvLevelArgs A) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= A.N) return;
+    NvParams q;
+    if (A.fixed) {
+        q.h = A.fixed[e * 5 + 2]; q.k = A.fixed[e * 5 + 3]; q.mu = A.fixed[e * 5 + 4];
+    } else
+        q = nv_draw_params(P, A.seed + (uint64_t)(A.env_offset + e), A.episode);
+    A.level_out[e] = nv_policy_level(P, A.policy, A.param0, P.L, (float)q.h, (float)q.k, (float)q.mu);
+}
 
 // ------------------------------------------------------------------------------------------------
 // host side of the C ABI
@@ -818,6 +871,14 @@ extern "C" int orgym_newsvendor_rollout(orgym_handle_t h, uint64_t seed, int64_t
     A.action_traj = out->action_traj_dev;
     A.final_obs = out->final_obs_dev;
     A.partials = out->summary_dev ? H->partials : nullptr;
+    if ((in->policy == ORGYM_NV_POLICY_CLASSIC || in->policy == ORGYM_NV_POLICY_SS) && A.ep_return) {
+        NvLevelArgs LA;
+        memset(&LA, 0, sizeof(LA));
+        LA.N = A.N; LA.env_offset = env_offset; LA.seed = seed; LA.episode = episode; LA.policy = in->policy;
+        LA.param0 = in->param[0]; LA.fixed = in->fixed_params_dev; LA.level_out = A.ep_return;
+        nv_level_kernel<<<(unsigned)((A.N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(H->dev, LA);
+        A.level_in = A.ep_return;
+    }
     size_t smem = (size_t)H->dev.L * NV_ROLL_THREADS * 4 + 16;
     int nblocks = (int)((A.N + NV_ROLL_THREADS - 1) / NV_ROLL_THREADS);
 #define NV_ROLL_CASE(LTV)                                                                          \

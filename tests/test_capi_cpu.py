@@ -109,7 +109,14 @@ def test_serial_rollout_specialiser_compiles_without_gpu(lib, kind):
         assert rc == 0, lib.orgym_last_error()
         src = buf.value.decode()
         assert len(src) == need.value and name in src
-        assert src.count("// ---- period") == P.num_periods
+        if name.endswith("_bs"):       # straight-line periods (the compiler folds the demand-independent stages)
+            assert src.count("// ---- period") == P.num_periods
+        else:                          # random policy: a loop over blocks of 8 periods + a straight-line tail
+            unr = 8 if P.num_periods >= 16 else 0
+            if unr:
+                assert "for (int tb = 0;" in src and src.count("// ---- period") == unr + P.num_periods % unr
+            else:
+                assert src.count("// ---- period") == P.num_periods
 
 
 def test_serial_rollout_specialiser_reports_unsupported_configs(lib):

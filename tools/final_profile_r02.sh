@@ -21,7 +21,7 @@ cap inv_lost    inv_lost    'inv_jit_rollout_bs'  1 1
 cap inv_backlog inv_backlog 'inv_jit_rollout_bs'  1 1
 cap inv_random  inv_random  'inv_jit_rollout_rnd' 1 1
 cap inv_step    inv_step    'inv_step_kernel'     13 1
-cap nv          nv          'nv_rollout_kernel'   1 1
+cap nv          nv          'nv_level_kernel|nv_rollout_kernel' 2 2
 cap nv_step     nv_step     'nv_step_kernel'      7 1
 cap net         net         'net_jit_rollout'     1 1
 cap net_step    net_step    'net_jit_step'        11 1

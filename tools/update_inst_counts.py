@@ -19,25 +19,34 @@ def main():
     raw = list(csv.reader(io.StringIO(out)))
     hdr = raw[0]
     col = {h: i for i, h in enumerate(hdr)}
-    row = next(r for r in raw[2:] if re.search(pat, r[col["Kernel Name"]]))
+    # ORGYM_COUNT_SUM=n: one call of the API launches n kernels that belong together (e.g. the newsvendor's order-level
+    # kernel + rollout kernel): counts and durations of the first n matching launches are added up
+    nsum = int(os.environ.get("ORGYM_COUNT_SUM", "1"))
+    rows = [r for r in raw[2:] if re.search(pat, r[col["Kernel Name"]])][:nsum]
+    row = rows[0]
     units = raw[1]
 
-    def val(name):
-        v = float(row[col[name]].replace(",", ""))
+    def val1(r, name):
+        v = float(r[col[name]].replace(",", ""))
         u = units[col[name]].lower()
         scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(u, 1)
         return v * scale
+
+    def val(name):
+        return sum(val1(r, name) for r in rows)
     inst = val("smsp__inst_executed.sum")
     dram = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
     dur_us = val("gpu__time_duration.sum")
     du = units[col["gpu__time_duration.sum"]].lower()
     dur_us *= {"ns": 1e-3, "us": 1, "usecond": 1, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6, "nsecond": 1e-3}.get(du, 1)
-    issue = val("smsp__issue_active.avg.pct_of_peak_sustained_active")
-    dthr = val("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
+    issue = sum(val1(r, "smsp__issue_active.avg.pct_of_peak_sustained_active") * val1(r, "gpu__time_duration.sum") for r in rows) / \
+        sum(val1(r, "gpu__time_duration.sum") for r in rows)      # duration-weighted
+    dthr = val1(row, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
     path = os.path.join(ROOT, "profiles", "inst_counts.json")
     J = json.load(open(path))
     e = {"dram_bytes_per_env_step": dram / steps}
-    src = (f"{summary}: {row[col['Kernel Name']][:60]}, {steps:.0f} env-steps per launch: smsp__inst_executed.sum {inst:.0f} "
+    names = " + ".join(r[col['Kernel Name']][:40] for r in rows)
+    src = (f"{summary}: {names}, {steps:.0f} env-steps per launch: smsp__inst_executed.sum {inst:.0f} "
            f"({inst * 32 / steps:.1f} per warp-step), issue-slot utilisation {issue:.1f} %, dram read+write {dram / 1e9:.3f} GB, "
            f"{dthr:.1f} % DRAM throughput, {dur_us:.1f} us under ncu")
     if not key.endswith("_step"):
