@@ -70,8 +70,17 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
     const char* A4[4] = {"a4.x", "a4.y", "a4.z", "a4.w"};
     // (random policy) periods re-rolled into a loop over blocks of UNR periods -- see below; the per-period discount
     // factors then come from a constant-memory table (uniform loads)
-    int UNR = bs ? 0 : env_int("ORGYM_INV_JIT_RND_UNROLL", 8, 0, 32);
-    if (UNR % 4 != 0 || T < 2 * UNR) UNR = 0;
+    // Block length 8 (4 for short horizons; ORGYM_INV_JIT_RND_UNROLL overrides, 0 = straight-line).  A ring whose lead time
+    // divides the block length keeps compile-time slot indices ((tb + u) mod L = u mod L), the others are shifted by L - 1
+    // register moves per period; a block length that is not a multiple of 4 picks the period's Philox word at run time.
+    // Measured on the default configuration (lead times 3, 5, 10; 2^24 x 30): straight-line 2.78-3.0 ms, blocks of 4
+    // 2.57, 8 2.55, 12 2.56, 10 (two rings static, run-time word) 2.78, 15 3.01 -- the block has to stay small.
+    int UNR = 0;
+    if (!bs) {
+        UNR = T >= 16 ? 8 : (T >= 8 ? 4 : 0);
+        const int forced = env_int("ORGYM_INV_JIT_RND_UNROLL", -1, 0, 32);
+        if (forced >= 0) UNR = (forced > 0 && T >= 2 * forced) ? forced : 0;
+    }
     if (UNR > 0 && !(iprofit && episode_sum)) {
         o("__constant__ double c_disc[%d] = {", T);
         for (int t = 0; t < T; t++)
@@ -114,8 +123,11 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
     // therefore emitted as a LOOP over blocks of UNR periods (UNR a multiple of 4, so the Philox word of a period stays a
     // compile-time choice) with the lead-time rings shifted by register moves instead of being indexed by t mod L, plus a
     // straight-line tail: a few hundred instructions that stay in the instruction cache.  Same arithmetic, same order.
-    const bool shift = UNR > 0;                      // ring slot 0 = arriving now; shifted at the end of the period
+    // per ring: shifted (slot 0 = arriving now, moved at the end of the period) or indexed by (period mod L)
+    bool shift[ORGYM_INV_MAX_STAGES];
+    for (int i = 0; i < n; i++) shift[i] = UNR > 0 && S.L[i] > 0 && UNR % S.L[i] != 0;
     const int Tloop = UNR > 0 ? T - T % UNR : 0;
+    const bool dyn_word = UNR > 0 && UNR % 4 != 0;   // the demand word of a period inside the loop is picked at run time
     // emits period t; inside the loop t = tb + u is symbolic and only u is known here
     auto emit_period = [&](int t, int u, bool in_loop) {
         char tx[32], bx[32], dx[48];
@@ -129,6 +141,7 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
             snprintf(dx, sizeof(dx), "%s", lit(iprofit ? std::ldexp(S.disc[(size_t)t], qexp) : S.disc[(size_t)t]).c_str());
         }
         const int w4 = (in_loop ? u : t) & 3;
+        const int tq = in_loop ? u : t;               // ring slots of the non-shifted rings: (tb + u) mod L = u mod L
         if (in_loop)
             o("  {  // ---- period tb + %d", u);
         else
@@ -148,8 +161,13 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
         }
         // demand
         if (S.log2k > 0) {
-            if (w4 == 0) o("    w = philox_block(key, %s, ep, STREAM_DEMAND, 0u);", bx);
-            o("    int dl; { const unsigned int wv = %s, pe = tab[wv >> %d];", W4[w4], 32 - S.log2k);
+            if (in_loop && dyn_word) {
+                o("    if (((tb + %d) & 3) == 0) w = philox_block(key, (unsigned)((tb + %d) >> 2), ep, STREAM_DEMAND, 0u);", u, u);
+                o("    int dl; { const unsigned int wv = pick_word(w, (tb + %d) & 3), pe = tab[wv >> %d];", u, 32 - S.log2k);
+            } else {
+                if (w4 == 0) o("    w = philox_block(key, %s, ep, STREAM_DEMAND, 0u);", bx);
+                o("    int dl; { const unsigned int wv = %s, pe = tab[wv >> %d];", W4[w4], 32 - S.log2k);
+            }
             o("      dl = %d + (int)((((wv << %d) | %uu) < pe) ? (wv >> %d) : (pe & %uu)); }", S.base, S.log2k, (unsigned)(K - 1),
               32 - S.log2k, (unsigned)(K - 1));
         } else {
@@ -168,7 +186,7 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
             if (S.L[i] == 0)
                 o("    int Ic_%d = I_%d + r_%d;", i, i, i);
             else
-                o("    int Ic_%d = I_%d + rr%d_%d;", i, i, i, shift ? 0 : t % S.L[i]);
+                o("    int Ic_%d = I_%d + rr%d_%d;", i, i, i, shift[i] ? 0 : tq % S.L[i]);
         }
         if (S.base >= 0)
             o("    const int d = dl;");  // the alias table's support starts at base >= 0: max(0, .) is the identity
@@ -274,12 +292,12 @@ void emit_kernel(Src& o, const InvJitSpec& S, const char* name, int policy, int 
         // rings: slot t mod L_i held R[t - L_i] / the request of period t - L_i
         for (int i = 0; i < n; i++) {
             if (S.L[i] == 0) continue;
-            if (shift) {  // slot 0 has arrived: everything moves one period closer, the new order enters at the back
+            if (shift[i]) {  // slot 0 has arrived: everything moves one period closer, the new order enters at the back
                 for (int q = 0; q + 1 < S.L[i]; q++) o("    rr%d_%d = rr%d_%d;", i, q, i, q + 1);
                 o("    rr%d_%d = r_%d;", i, S.L[i] - 1, i);
                 continue;
             }
-            const int s = t % S.L[i];
+            const int s = tq % S.L[i];
             if (bs) o("    ps_%d = ps_%d + q_%d - ar%d_%d; ar%d_%d = q_%d;", i, i, i, i, s, i, s, i);
             o("    rr%d_%d = r_%d;", i, s, i);
         }

@@ -50,13 +50,13 @@ __device__ __forceinline__ void net_write_obs(const NetDev& P, const double* sU,
     }
 }
 
-__global__ void __launch_bounds__(NET_TILE) net_reset_kernel(const __grid_constant__ NetDev P, int64_t N, void* state,
-                                                             int reseed, uint64_t seed, int64_t env_offset,
+__global__ void __launch_bounds__(128) net_reset_kernel(const __grid_constant__ NetDev P, int64_t N, void* state,
+                                                        int reseed, uint64_t seed, int64_t env_offset,
                                                         const uint8_t* __restrict__ mask, float* __restrict__ obs) {
     const int64_t e0 = (int64_t)blockIdx.x * 128, e = e0 + threadIdx.x;
     if (e < N && (!mask || mask[e])) {
-        NetState st((char*)state + (int64_t)blockIdx.x * net_tile_bytes(P), P);  // one CTA per state tile
-        const int el = threadIdx.x;
+        NetState st((char*)state + (e / NET_TILE) * net_tile_bytes(P), P);
+        const int el = (int)(e % NET_TILE);
         for (int j = 0; j < P.J; j++) st.X[j * NET_TILE + el] = P.I0[j];  // :326
         for (int i = 0; i < P.E; i++) st.Y[i * NET_TILE + el] = 0.0;
         for (int r = 0; r < P.M; r++) st.U[r * NET_TILE + el] = 0.0;
@@ -963,7 +963,7 @@ extern "C" int orgym_netinv_reset(orgym_handle_t h, void* state_dev, int reseed,
     ORGYM_REQUIRE(state_dev && obs_dev, "state_dev and obs_dev are required");
     DeviceGuard g(H->base.device);
     int64_t N = H->base.num_envs;
-    net_reset_kernel<<<(unsigned)((N + NET_TILE - 1) / NET_TILE), NET_TILE, 0, (cudaStream_t)stream>>>(H->dev, N, state_dev, reseed,
+    net_reset_kernel<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(H->dev, N, state_dev, reseed,
                                                                                   seed, env_offset, mask_dev, obs_dev);
     ORGYM_CUDA(cudaGetLastError());
     return ORGYM_OK;

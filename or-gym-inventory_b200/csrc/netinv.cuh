@@ -49,7 +49,9 @@ struct NetHandle {
 // between slots is a compile-time constant (every access of the specialised kernels becomes base + immediate, no
 // 64-bit index arithmetic) and the ~1700 slots of a 64-node graph that one CTA touches per period lie in one
 // contiguous 1.7 MB region instead of being spread over as many distinct 1 MB-apart rows (TLB reach, DRAM pages).
+#ifndef NET_TILE
 #define NET_TILE 128
+#endif
 struct NetState {
     uint64_t* key;
     double *X, *Y, *U, *ring;

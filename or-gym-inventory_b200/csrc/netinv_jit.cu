@@ -477,6 +477,13 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
     // instructions, so that a line of this long straight-line kernel is fetched into the instruction cache once per CTA
     // instead of once per warp (ncu: 7 of 18 stall cycles per issue were instruction fetch).
     const int SYNC = env_int("ORGYM_NET_JIT_SYNC", 0, 0, 1);
+    const int LDGSTS = env_int("ORGYM_NET_JIT_LDGSTS", 0, 0, 1);  // measured: 0.428 vs 0.418 ms without -- off by default
+    if (LDGSTS) {
+        // landing zone: [16 values][32 lanes] doubles inside this warp's rows of the action tile (4224 bytes per warp)
+        o("  __syncwarp();");
+        o("  double* const lz = (double*)(tile + wrow0 * 33) + ln;");
+        o("  const unsigned lz_s = (unsigned)__cvta_generic_to_shared(lz);");
+    }
     o("  double total = 0.0;");
     o("  if (do_step) {");
     std::vector<int> link_done(E, 0);
@@ -488,23 +495,65 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
         o("    {");
         if (PF >= 2)
             for (int j = j0 + GROUP * (PF - 1); j < std::min(J, j0 + GROUP * PF); j++) emit_prefetch_node(j, "      ");
-        for (int j = j0; j < j1; j++) {  // load phase
-            o("      double x%d = s_X[%d * NP + el];", j, j);
-            if (has_seg[j]) o("      const double c%d = sc_C[%d * NP + el];", j, j);
+        // load phase.  ORGYM_NET_JIT_LDGSTS=1: every value the group needs is fetched with an asynchronous
+        // global->shared copy (cp.async, SASS LDGSTS) into a per-lane landing zone -- the warp's own 4 KB of the action tile,
+        // free after pass A -- and read back once the group has landed.  Loads in flight then cost no registers: at the 64
+        // registers that keep the whole batch resident in one wave the compiler had been serialising a node's dozen loads
+        // into ~4 dependent round trips (ncu: long_scoreboard 27 of 38 stall cycles per issue).
+        struct Ld { std::string decl, addr; };
+        std::vector<Ld> lds;
+        char nb[160], ab[160];
+        for (int j = j0; j < j1; j++) {
+            snprintf(nb, sizeof(nb), "double x%d", j);
+            snprintf(ab, sizeof(ab), "s_X + %d * NP + el", j);
+            lds.push_back({nb, ab});
+            if (has_seg[j]) {
+                snprintf(nb, sizeof(nb), "const double c%d", j);
+                snprintf(ab, sizeof(ab), "sc_C + %d * NP + el", j);
+                lds.push_back({nb, ab});
+            }
             for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
                 const int i = P.pred_idx[z], L = P.L[i];
-                o("      const double rt%d = sc_R[%d * NP + el]; const double y%d = s_Y[%d * NP + el];", i, i, i, i);
+                snprintf(nb, sizeof(nb), "const double rt%d", i);
+                snprintf(ab, sizeof(ab), "sc_R + %d * NP + el", i);
+                lds.push_back({nb, ab});
+                snprintf(nb, sizeof(nb), "const double y%d", i);
+                snprintf(ab, sizeof(ab), "s_Y + %d * NP + el", i);
+                lds.push_back({nb, ab});
                 if (L > 0) {
-                    o("      double* const slot%d = ring + (%d + t %% %d) * NP + el; const double ar%d = *slot%d;", i, P.roff[i], L,
-                      i, i);
+                    o("      double* const slot%d = ring + (%d + t %% %d) * NP + el;", i, P.roff[i], L);
+                    snprintf(nb, sizeof(nb), "const double ar%d", i);
+                    snprintf(ab, sizeof(ab), "slot%d", i);
+                    lds.push_back({nb, ab});
                 }
             }
             for (int r = 0; r < M; r++)
-                if (P.rt_node[r] == j) o("      const double u%d = s_U[%d * NP + el];", r, r);
+                if (P.rt_node[r] == j) {
+                    snprintf(nb, sizeof(nb), "const double u%d", r);
+                    snprintf(ab, sizeof(ab), "s_U + %d * NP + el", r);
+                    lds.push_back({nb, ab});
+                }
             for (int z = P.succ_ptr[j]; z < P.succ_ptr[j + 1]; z++) {
                 const int l = P.succ_idx[z];
-                if (l < E) o("      const double qs%d_%d = sc_R[%d * NP + el];", j, l, l);
+                if (l < E) {
+                    snprintf(nb, sizeof(nb), "const double qs%d_%d", j, l);
+                    snprintf(ab, sizeof(ab), "sc_R + %d * NP + el", l);
+                    lds.push_back({nb, ab});
+                }
             }
+        }
+        if (LDGSTS) {
+            for (size_t b0 = 0; b0 < lds.size(); b0 += 16) {  // the landing zone holds 16 values per lane
+                const size_t b1 = std::min(lds.size(), b0 + 16);
+                for (size_t k = b0; k < b1; k++)
+                    o("      asm volatile(\"cp.async.ca.shared.global [%%0], [%%1], 8;\" ::\"r\"(lz_s + %uu), \"l\"(%s) : \"memory\");",
+                      (unsigned)((k - b0) * 256), lds[k].addr.c_str());
+                o("      asm volatile(\"cp.async.commit_group;\" ::: \"memory\");");
+                o("      asm volatile(\"cp.async.wait_group 0;\" ::: \"memory\");");
+                for (size_t k = b0; k < b1; k++) o("      %s = lz[%u];", lds[k].decl.c_str(), (unsigned)((k - b0) * 32));
+            }
+        } else {
+            for (const Ld& l : lds) o("      %s = *(%s);", l.decl.c_str(), l.addr.c_str());
         }
         for (int j = j0; j < j1; j++) {  // compute + store phase
             o("      { double arr = 0.0, PC = 0.0, HCp = 0.0;");

@@ -111,12 +111,13 @@ def test_serial_rollout_specialiser_compiles_without_gpu(lib, kind):
         assert len(src) == need.value and name in src
         if name.endswith("_bs"):       # straight-line periods (the compiler folds the demand-independent stages)
             assert src.count("// ---- period") == P.num_periods
-        else:                          # random policy: a loop over blocks of 8 periods + a straight-line tail
-            unr = 8 if P.num_periods >= 16 else 0
-            if unr:
-                assert "for (int tb = 0;" in src and src.count("// ---- period") == unr + P.num_periods % unr
-            else:
-                assert src.count("// ---- period") == P.num_periods
+        else:                          # random policy: a loop over blocks of periods + a straight-line tail
+            import re as _re
+            m = _re.search(r"for \(int tb = 0; tb < (\d+); tb \+= (\d+)\)", src)
+            assert m, "the random-policy kernel should loop over blocks of periods"
+            tloop, unr = int(m.group(1)), int(m.group(2))
+            assert tloop == P.num_periods - P.num_periods % unr and unr == (8 if P.num_periods >= 16 else 4)
+            assert src.count("// ---- period") == unr + P.num_periods - tloop
 
 
 def test_serial_rollout_specialiser_reports_unsupported_configs(lib):

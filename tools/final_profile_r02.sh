@@ -20,6 +20,7 @@ cap() {  # name, prof_r02 mode, kernel regex, skip, count
 cap inv_lost    inv_lost    'inv_jit_rollout_bs'  1 1
 cap inv_backlog inv_backlog 'inv_jit_rollout_bs'  1 1
 cap inv_random  inv_random  'inv_jit_rollout_rnd' 1 1
+cap inv_wide    inv_wide    'inv_rollout_kernel'  1 1
 cap inv_step    inv_step    'inv_step_kernel'     13 1
 cap nv          nv          'nv_level_kernel|nv_rollout_kernel' 2 2
 cap nv_step     nv_step     'nv_step_kernel'      7 1

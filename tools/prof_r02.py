@@ -1,5 +1,5 @@
 """small launch sequences for the round-2 ncu captures (one target per invocation):
-    python tools/prof_r02.py inv_lost | inv_backlog | inv_random | inv_step | nv | nv_step | net | net_step | net64"""
+    python tools/prof_r02.py inv_lost | inv_backlog | inv_random | inv_wide | inv_step | nv | nv_step | net | net_step | net64"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,7 +8,7 @@ which = sys.argv[1]
 if which.startswith("inv"):
     N = 1 << 24
     cls = pkg.InvManagementBacklogEnv if which == "inv_backlog" else pkg.InvManagementLostSalesEnv
-    env = cls(num_envs=N, device="cuda:0")
+    env = cls(num_envs=N, device="cuda:0", wide_state=(which == "inv_wide"))
     if which == "inv_step":
         a = torch.randint(0, 100, (N, 3), dtype=torch.int64, device="cuda")
         env.reset(seed=1)
