@@ -172,16 +172,18 @@ class BatchedEnv(_VectorEnvBase):
             out = self.rollout(policy, seed=seed if k == 0 else None, episode=first_episode + k, want=rwant,
                                buffer_set=b, **policy_kwargs)
             self.last_rollout = out
-            if do_report:
-                rb = self._report_bufs.setdefault(b, [None, None])
-                rb[0], rb[1] = evaluation_report_device(out, self._episode_periods(), report=rb[0], scratch=rb[1])
-                out = {name: t for name, t in out.items() if name in want}
-                out["report"] = rb[0]
             ready = torch.cuda.Event()
             ready.record(main)
-            host = self._host_sets.setdefault((b, tuple(sorted(out))), {})
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(ready)
+                if do_report:
+                    # the report kernels (HBM-bound) run on the second stream too: they overlap the next rollout
+                    # (issue-bound) instead of delaying it
+                    rb = self._report_bufs.setdefault(b, [None, None])
+                    rb[0], rb[1] = evaluation_report_device(out, self._episode_periods(), report=rb[0], scratch=rb[1])
+                    out = {name: t for name, t in out.items() if name in want}
+                    out["report"] = rb[0]
+                host = self._host_sets.setdefault((b, tuple(sorted(out))), {})
                 for name, t in out.items():
                     if name not in host:
                         host[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
