@@ -45,9 +45,12 @@ class SB3VecEnvAdapter:
         import torch
         if getattr(self, "_pin", None) is None:
             dev = obs.device
+            # observations are cast to obs_dtype ON THE DEVICE (FloatObsWrapper semantics): an int64 observation row of
+            # the serial env crosses PCIe as float32, half the bytes
+            self._obs_torch_dtype = getattr(torch, self.obs_dtype.name)
             self._pin = dict(act=torch.empty((self.num_envs,) + tuple(self.action_space.shape),
                                              dtype=getattr(torch, np.dtype(self.action_space.dtype).name)).pin_memory(),
-                             obs=torch.empty(obs.shape, dtype=obs.dtype).pin_memory(),
+                             obs=torch.empty(obs.shape, dtype=self._obs_torch_dtype).pin_memory(),
                              rew=torch.empty(rew.shape, dtype=rew.dtype).pin_memory(),
                              done=torch.empty(self.num_envs, dtype=torch.bool).pin_memory(),
                              trunc=torch.empty(self.num_envs, dtype=torch.bool).pin_memory())
@@ -67,13 +70,13 @@ class SB3VecEnvAdapter:
         else:
             obs, rew, term, trunc, info = env.step(self._actions)
         pin = self._buffers(obs, rew)
-        pin["obs"].copy_(obs, non_blocking=True)
+        pin["obs"].copy_(obs if obs.dtype == self._obs_torch_dtype else obs.to(self._obs_torch_dtype), non_blocking=True)
         pin["rew"].copy_(rew, non_blocking=True)
         pin["done"].copy_(term | trunc, non_blocking=True)
         pin["trunc"].copy_(trunc, non_blocking=True)
         torch.cuda.current_stream(obs.device).synchronize()
         dones = pin["done"].numpy().copy()
-        obs_h = pin["obs"].numpy().astype(self.obs_dtype, copy=True)
+        obs_h = pin["obs"].numpy().copy()
         # infos: one shared empty dict for the instances that go on (a list of N references, no Python loop over the
         # batch); only finished instances get a dict of their own (terminal observation, like DummyVecEnv).  Consumers
         # such as VecMonitor write into the infos of finished instances only.

@@ -279,3 +279,12 @@ def test_geometric_demand_with_a_long_tail_is_refused_not_truncated(lib):
     assert bounds(0.12) == 0 and bounds(0.011) == 0
     assert bounds(0.01) == _capi.E_UNSUPPORTED and b"geometric" in lib.orgym_last_error()
     assert bounds(0.001) == _capi.E_UNSUPPORTED
+
+
+def test_new_entry_points_reject_bad_handles_without_a_gpu(lib):
+    """specialise / scratch-size / report entry points: argument checking works on a box without a GPU."""
+    rin = _capi.InvRolloutIn()
+    assert lib.orgym_invmgmt_specialise(None, C.byref(rin)) == _capi.E_INVALID
+    assert lib.orgym_invmgmt_rollout_scratch_bytes(None) == -1
+    assert lib.orgym_report_scratch_bytes(1 << 24) > (1 << 20) and lib.orgym_report_scratch_bytes(-1) == -1
+    assert lib.orgym_evaluation_report(0, None, None, 0, 10, 30, None, None, None) == _capi.E_INVALID

@@ -487,3 +487,43 @@ def test_evaluate_default_product_is_the_device_report():
         assert np.isclose(got["StdReward"], want["StdReward"], rtol=1e-10)
         assert np.isclose(got["AvgServiceLevel"], want["AvgServiceLevel"], rtol=1e-12)
     env.close()
+
+
+def test_explicit_specialisation_and_strict_mode(monkeypatch):
+    """orgym_invmgmt_specialise builds the kernel for a policy ahead of time and says why when it cannot;
+    ORGYM_INV_JIT=2 turns a rollout that cannot get its specialised kernel into an error instead of a silent fall-back
+    to the 2-3x slower ahead-of-time kernel; ORGYM_INV_JIT=0 never specialises."""
+    from or_gym_inventory_b200._capi import OrgymError, E_UNSUPPORTED
+    env = pkg.InvManagementLostSalesEnv(num_envs=500, device="cuda:0")
+    assert env.specialise("base_stock", safety_factor=1.0) and env.rollout_specialised
+    assert env.specialise("random")
+    a = env.rollout("base_stock", seed=3, safety_factor=1.0, want=("ep_return",))["ep_return"].clone()
+    assert env.rollout_specialised
+    # a second safety factor is a second kernel variant (levels are literals); results differ, both specialised
+    b = env.rollout("base_stock", seed=3, safety_factor=1.5, want=("ep_return",))["ep_return"].clone()
+    assert env.rollout_specialised and not _torch().equal(a, b)
+    # non-integer levels cannot be specialised: the ahead-of-time kernel evaluates them in float64
+    with pytest.raises(OrgymError) as ei:
+        env.specialise("base_stock", safety_factor=1.013)
+    assert ei.value.code == E_UNSUPPORTED
+    env.rollout("base_stock", seed=3, safety_factor=1.013, want=("ep_return",))
+    assert not env.rollout_specialised
+    env.close()
+    # seven stages are outside the specialiser's range
+    big = dict(I0=[10] * 7, r=[9, 8, 7, 6, 5, 4, 3, 2], k=[0.1] * 8, h=[0.1] * 7, c=[10] * 7, L=[1] * 7)
+    env = pkg.InvManagementBacklogEnv(num_envs=100, device="cuda:0", **big)
+    with pytest.raises(OrgymError) as ei:
+        env.specialise("base_stock", safety_factor=1.0, mu=10)
+    assert ei.value.code == E_UNSUPPORTED and "specialiser" in str(ei.value)
+    ref = env.rollout("base_stock", seed=1, safety_factor=1.0, mu=10, want=("ep_return",))["ep_return"].clone()
+    assert not env.rollout_specialised
+    monkeypatch.setenv("ORGYM_INV_JIT", "2")
+    with pytest.raises(OrgymError):
+        env.rollout("base_stock", seed=1, safety_factor=1.0, mu=10, want=("ep_return",))
+    monkeypatch.setenv("ORGYM_INV_JIT", "0")
+    assert _torch().equal(env.rollout("base_stock", seed=1, safety_factor=1.0, mu=10, want=("ep_return",))["ep_return"], ref)
+    env.close()
+    env = pkg.InvManagementLostSalesEnv(num_envs=500, device="cuda:0")
+    c = env.rollout("base_stock", seed=3, safety_factor=1.0, want=("ep_return",))["ep_return"]
+    assert not env.rollout_specialised and _torch().equal(a, c)      # ahead-of-time kernel: the same numbers
+    env.close()
