@@ -152,9 +152,14 @@ __global__ void __launch_bounds__(RTHR) report_pass(int pass, const double* __re
                                                     long long cap, double* __restrict__ partials) {
     if (pass >= 3 && (FULL ? S->lists_ok != 0 : S->lists_ok == 0)) return;
     __shared__ unsigned int sh[2][NBIN];
+    constexpr unsigned int SBUF = APPEND ? 1024u : 1u;  // candidates buffered per CTA and list before they are published
+    __shared__ unsigned long long sbuf[2][SBUF];
+    __shared__ unsigned int scount[2];
+    __shared__ unsigned long long sbase[2];
     const int same = S->same;
     const int nsel = same ? 1 : 2;
     for (int i = threadIdx.x; i < 2 * NBIN; i += RTHR) (&sh[0][0])[i] = 0u;
+    if (threadIdx.x < 2) scount[threadIdx.x] = 0u;
     __syncthreads();
     const int shift = c_shift[pass], pshift = c_shift[pass - 1];
     const unsigned int mask = (1u << c_bits[pass]) - 1u;
@@ -178,23 +183,35 @@ __global__ void __launch_bounds__(RTHR) report_pass(int pass, const double* __re
             const bool m0 = pre == p0, m1 = !same && pre == p1;
             if (m0) atomicAdd(&sh[0][(unsigned int)(u >> shift) & mask], 1u);
             if (m1) atomicAdd(&sh[1][(unsigned int)(u >> shift) & mask], 1u);
-            if (APPEND) {  // warp-aggregated append: one atomic per warp and list
+            if (APPEND) {
+                // Candidates are collected per CTA in shared memory and published with ONE global atomic per CTA and list
+                // at the end (the first version appended with one global atomic per warp: ~110 000 atomics on one address,
+                // 65 of this pass's 100 microseconds).  A full CTA buffer falls back to direct, warp-aggregated appends.
+                bool d0 = false, d1 = false;
+                if (m0) {
+                    const unsigned int at = atomicAdd(&scount[0], 1u);
+                    if (at < SBUF) sbuf[0][at] = u; else d0 = true;
+                }
+                if (m1) {
+                    const unsigned int at = atomicAdd(&scount[1], 1u);
+                    if (at < SBUF) sbuf[1][at] = u; else d1 = true;
+                }
                 const unsigned act = __activemask();
-                const unsigned b0 = __ballot_sync(act, m0), b1 = __ballot_sync(act, m1);
+                const unsigned b0 = __ballot_sync(act, d0), b1 = __ballot_sync(act, d1);
                 const int lane = threadIdx.x & 31;
                 if (b0) {
                     unsigned long long base = 0ULL;
                     if (lane == __ffs(b0) - 1) base = atomicAdd(&S->list_n[0], (unsigned long long)__popc(b0));
                     base = __shfl_sync(act, base, __ffs(b0) - 1);
                     const unsigned long long at = base + __popc(b0 & ((1u << lane) - 1u));
-                    if (m0 && (long long)at < cap) list[at] = u;
+                    if (d0 && (long long)at < cap) list[at] = u;
                 }
                 if (b1) {
                     unsigned long long base = 0ULL;
                     if (lane == __ffs(b1) - 1) base = atomicAdd(&S->list_n[1], (unsigned long long)__popc(b1));
                     base = __shfl_sync(act, base, __ffs(b1) - 1);
                     const unsigned long long at = base + __popc(b1 & ((1u << lane) - 1u));
-                    if (m1 && (long long)at < cap) list[cap + at] = u;
+                    if (d1 && (long long)at < cap) list[cap + at] = u;
                 }
             }
           }
@@ -202,6 +219,19 @@ __global__ void __launch_bounds__(RTHR) report_pass(int pass, const double* __re
         if (VAR) {
             double v[1] = {var};
             block_sums<1>(v, partials + (size_t)blockIdx.x * 8);
+        }
+        if (APPEND) {  // publish the CTA's candidates: one global atomic per list
+            __syncthreads();
+            for (int s = 0; s < 2; s++) {
+                const unsigned int cnt = scount[s] < SBUF ? scount[s] : SBUF;
+                if (cnt == 0) continue;  // uniform: scount is shared
+                if (threadIdx.x == 0) sbase[s] = atomicAdd(&S->list_n[s], (unsigned long long)cnt);
+                __syncthreads();
+                for (unsigned int i = threadIdx.x; i < cnt; i += RTHR) {
+                    const unsigned long long at = sbase[s] + i;
+                    if ((long long)at < cap) list[(size_t)s * cap + at] = sbuf[s][i];
+                }
+            }
         }
     } else {
         for (int s = 0; s < nsel; s++) {
