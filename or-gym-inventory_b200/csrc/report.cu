@@ -434,13 +434,15 @@ extern "C" int orgym_evaluation_report(int device, const double* ep_return_dev, 
     ORGYM_CUDA(cudaMemsetAsync(L.kmm, 0xff, 8, s));
     ORGYM_CUDA(cudaMemsetAsync(L.kmm + 1, 0, 8, s));
     ORGYM_CUDA(cudaMemsetAsync(L.hist, 0, (size_t)2 * NBIN * 8, s));
+    // pass 0 holds UNR returns + UNR statistics rows per thread (77-80 registers -> 3 CTAs per SM): its grid is one wave of that
+    const int grid0 = grid < 444 ? grid : 444;
     if (stats_kind == 0)
-        report_pass0<0><<<grid, RTHR, 0, s>>>(ep_return_dev, stats_dev, n, L.partials, L.kmm);
+        report_pass0<0><<<grid0, RTHR, 0, s>>>(ep_return_dev, stats_dev, n, L.partials, L.kmm);
     else if (stats_kind == 1)
-        report_pass0<1><<<grid, RTHR, 0, s>>>(ep_return_dev, stats_dev, n, L.partials, L.kmm);
+        report_pass0<1><<<grid0, RTHR, 0, s>>>(ep_return_dev, stats_dev, n, L.partials, L.kmm);
     else
-        report_pass0<2><<<grid, RTHR, 0, s>>>(ep_return_dev, stats_dev, n, L.partials, L.kmm);
-    report_pick<<<1, RTHR, 0, s>>>(0, 0, n, periods, grid, L.partials, L.kmm, L.S, L.hist, L.cap, report_dev);
+        report_pass0<2><<<grid0, RTHR, 0, s>>>(ep_return_dev, stats_dev, n, L.partials, L.kmm);
+    report_pick<<<1, RTHR, 0, s>>>(0, 0, n, periods, grid0, L.partials, L.kmm, L.S, L.hist, L.cap, report_dev);
     report_pass0b<<<grid, RTHR, 0, s>>>(ep_return_dev, n, L.S, L.hist);
     report_pick<<<1, RTHR, 0, s>>>(0, 1, n, periods, grid, L.partials, L.kmm, L.S, L.hist, L.cap, report_dev);
     report_pass<true, false, true><<<grid, RTHR, 0, s>>>(1, ep_return_dev, n, L.S, L.hist, L.list, L.cap, L.partials);
