@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(128) net_reset_kernel(const __grid_constant__ 
         for (int i = 0; i < P.E; i++) st.Y[i * NET_TILE + el] = 0.0;
         for (int r = 0; r < P.M; r++) st.U[r * NET_TILE + el] = 0.0;
         for (int k = 0; k < P.sumL; k++) st.ring[k * NET_TILE + el] = 0.0;
+        if (P.ring32)
+            for (int k = 0; k < P.sumL; k++) st.ring32[k * NET_TILE + el] = 0.0f;
         st.period[el] = 0;
         if (reseed) {
             st.key[el] = seed + (uint64_t)(env_offset + e);
@@ -440,6 +442,8 @@ __global__ void __launch_bounds__(NET_STREAM_THREADS, 7) net_stream_step_kernel(
                 for (int i = 0; i < E; i++) st.Y[i * NP + el] = 0.0;
                 for (int r = 0; r < M; r++) st.U[r * NP + el] = 0.0;
                 for (int k = 0; k < P.sumL; k++) ring[k * NP + el] = 0.0;
+                if (st.ring32)
+                    for (int k = 0; k < P.sumL; k++) st.ring32[k * NP + el] = 0.0f;
                 st.period[el] = 0;
                 st.episode[el] = episode + 1;
                 A.reward[e] = 0.0; A.terminated[e] = 0; A.truncated[e] = 0;
@@ -535,7 +539,10 @@ __global__ void __launch_bounds__(NET_STREAM_THREADS, 7) net_stream_step_kernel(
                 if (L0 > 0) ar0 = *slot0;
                 if (L1 > 0 && two) ar1 = *slot1;
                 {
-                    if (L0 > 0) *slot0 = rt0;
+                    if (L0 > 0) {
+                        *slot0 = rt0;
+                        if (st.ring32) st.ring32[slot0 - ring] = (float)rt0;
+                    }
                     arr += ar0;
                     const double yn = (y0 - ar0) + rt0;
                     st.Y[i0 * NP + el] = yn;
@@ -543,7 +550,10 @@ __global__ void __launch_bounds__(NET_STREAM_THREADS, 7) net_stream_step_kernel(
                     HCp += P.g[i0] * (yn > 0.0 ? yn : 0.0);  // :591
                 }
                 if (two) {
-                    if (L1 > 0) *slot1 = rt1;
+                    if (L1 > 0) {
+                        *slot1 = rt1;
+                        if (st.ring32) st.ring32[slot1 - ring] = (float)rt1;
+                    }
                     arr += ar1;
                     const double yn = (y1 - ar1) + rt1;
                     st.Y[i1 * NP + el] = yn;
@@ -613,6 +623,7 @@ __global__ void __launch_bounds__(NET_STREAM_THREADS, 7) net_stream_step_kernel(
                 double* slot = ring + (size_t)(P.roff[i] + net_mod(t, L, P.Lmagic[i])) * NP + el;
                 ar = *slot;
                 *slot = rt;
+                if (st.ring32) st.ring32[slot - ring] = (float)rt;
             }
             st.Y[i * NP + el] = (st.Y[i * NP + el] - ar) + rt;
         }
@@ -628,6 +639,8 @@ __global__ void __launch_bounds__(NET_STREAM_THREADS, 7) net_stream_step_kernel(
             for (int i = 0; i < E; i++) st.Y[i * NP + el] = 0.0;
             for (int r = 0; r < M; r++) st.U[r * NP + el] = 0.0;
             for (int k = 0; k < P.sumL; k++) ring[k * NP + el] = 0.0;
+                if (st.ring32)
+                    for (int k = 0; k < P.sumL; k++) st.ring32[k * NP + el] = 0.0f;
             st.period[el] = 0;
             st.episode[el] = episode + 1;
         } else
@@ -639,8 +652,11 @@ __global__ void __launch_bounds__(NET_STREAM_THREADS, 7) net_stream_step_kernel(
 // The streaming STEP path for large graphs leaves the new state in HBM; this kernel turns it into row-major float32
 // observation rows.  One CTA owns NET_OBS_ROWS = 32 instances (a quarter of a 128-instance state tile).  A state tile is
 // slot-major ([slot][128 instances]), so the CTA's share of an observation COLUMN is 32 consecutive doubles: one
-// coalesced 256-byte warp load.  Every warp takes every 8th column, NET_OBS_BATCH loads in flight per thread, converts
-// and scatters into a shared-memory image of the 32 finished rows (lane = instance; the row pitch obs_dim is odd for
+// coalesced 256-byte warp load -- 128 bytes for the window columns, which come from the tile's float32 copy of the rings
+// (P.ring32).  The warps take the columns round-robin, NET_OBS_BATCH (float64) / NET_OBS_BATCH32 (float32) loads in flight
+// per thread -- the kernel is bound by the round trips of a CTA, not by bytes: halving the bytes read did not move it,
+// 22 instead of 12 loads per batch and 12 instead of 8 warps took it from 0.18 to 0.115 ms on the 64-node graph --,
+// convert and scatter into a shared-memory image of the 32 finished rows (lane = instance; the row pitch obs_dim is odd for
 // the large graphs -> conflict-free).  Those 32 rows are contiguous in the caller's [N][obs_dim] tensor, so they leave
 // with ONE bulk store through the TMA engine (cp.async.bulk.global.shared::cta): full 32-byte sectors whatever the
 // alignment of an individual row -- per-lane 4-byte stores of an odd-length row write every sector in two partial
@@ -650,8 +666,13 @@ __global__ void __launch_bounds__(NET_STREAM_THREADS, 7) net_stream_step_kernel(
 // Which slot feeds which column depends on the period only through t mod L_i of every link (ring rotation); a group of
 // instances that are not all in the same period (possible only after masked resets) takes the per-instance fallback.
 #define NET_OBS_ROWS 32    // instances per CTA
-#define NET_OBS_THREADS 256
+#ifndef NET_OBS_THREADS
+#define NET_OBS_THREADS 384
+#endif
 #define NET_OBS_BATCH 12   // independent column loads in flight per thread
+#ifndef NET_OBS_BATCH32
+#define NET_OBS_BATCH32 22  // ... for the float32 ring columns (one register each)
+#endif
 size_t net_obs_smem(const NetDev& P) {
     return 128 + (((size_t)P.obs_dim * 2 + 127) & ~(size_t)127) + (((size_t)NET_OBS_ROWS * P.obs_dim * 4 + 127) & ~(size_t)127);
 }
@@ -691,27 +712,45 @@ __global__ void __launch_bounds__(NET_OBS_THREADS) net_obs_kernel(const __grid_c
         int sl = net_mod(t0, L, P.Lmagic[i]);  // window element q (oldest first) lives in ring slot (t + q) % L
         uint16_t* dst = colrow + P.M + P.J + P.roff[i];
         for (int q = 0; q < L; q++) {
-            dst[q] = (uint16_t)(rowR + P.roff[i] + sl);
+            dst[q] = (uint16_t)((P.ring32 ? 0 : rowR) + P.roff[i] + sl);
             sl = sl + 1 == L ? 0 : sl + 1;
         }
     }
     __syncthreads();
     const double* src = (const double*)tile + el0 + lane;  // + row * 128
     float* orow = out + (size_t)lane * W;
+    // The window columns come from the float32 copy of the rings when the tile carries one (colrow then holds the ring
+    // slot, a 512-byte row of st.ring32): 4 instead of 8 bytes read per column and instance.
+    const int WD = st.ring32 ? P.M + P.J : W;  // columns [0, WD) are float64 rows, [WD, W) float32 rows
+    const float* src32 = st.ring32 + el0 + lane;
     // all of this warp's columns are requested into L2 at once (one instruction each, no register, no scoreboard slot):
-    // the batched loads below then wait for L2, not for HBM, and the CTA's 145 KB are in flight from the first cycle
-    for (int c = warp; c < W; c += NW) prefetch_l2(src + (size_t)colrow[c] * NET_TILE);
-    for (int c0 = warp; c0 < W; c0 += NW * NET_OBS_BATCH) {
+    // the batched loads below then wait for L2, not for HBM, and the CTA's share is in flight from the first cycle
+    for (int c = warp; c < WD; c += NW) prefetch_l2(src + (size_t)colrow[c] * NET_TILE);
+    for (int c = WD + warp; c < W; c += NW) prefetch_l2(src32 + (size_t)colrow[c] * NET_TILE);
+    for (int c0 = warp; c0 < WD; c0 += NW * NET_OBS_BATCH) {
         double v[NET_OBS_BATCH];
 #pragma unroll
         for (int j = 0; j < NET_OBS_BATCH; j++) {
             const int c = c0 + j * NW;
-            v[j] = c < W ? __ldcs(src + (size_t)colrow[c] * NET_TILE) : 0.0;
+            v[j] = c < WD ? __ldcs(src + (size_t)colrow[c] * NET_TILE) : 0.0;
         }
 #pragma unroll
         for (int j = 0; j < NET_OBS_BATCH; j++) {
             const int c = c0 + j * NW;
-            if (c < W) orow[c] = (float)v[j];
+            if (c < WD) orow[c] = (float)v[j];
+        }
+    }
+    for (int c0 = WD + warp; c0 < W; c0 += NW * NET_OBS_BATCH32) {  // one register per value: a deeper batch
+        float v[NET_OBS_BATCH32];
+#pragma unroll
+        for (int j = 0; j < NET_OBS_BATCH32; j++) {
+            const int c = c0 + j * NW;
+            v[j] = c < W ? __ldcs(src32 + (size_t)colrow[c] * NET_TILE) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < NET_OBS_BATCH32; j++) {
+            const int c = c0 + j * NW;
+            if (c < W) orow[c] = v[j];
         }
     }
     float* g = obs + e0 * W;
@@ -730,9 +769,16 @@ __global__ void __launch_bounds__(NET_OBS_THREADS) net_obs_kernel(const __grid_c
     }
 }
 
+static int net_wants_ring32(const NetDev& P) {
+    const char* rv = getenv("ORGYM_NET_RING32");
+    return net_jit_uses_stream(P) && net_obs_smem(P) <= 200 * 1024 && !(rv && rv[0] == '0') ? 1 : 0;
+}
+
 static int net_obs_launch(const NetHandle* H, const void* state, float* obs, cudaStream_t s) {
     const int64_t N = H->base.num_envs;
     const int64_t tiles = (N + NET_TILE - 1) / NET_TILE;
+    // (launching the four CTAs of a tile as one thread-block cluster, so that their quarter rows reach DRAM together, was
+    // measured slower: 0.19-0.20 ms against 0.18 ms)
     net_obs_kernel<<<(unsigned)(tiles * (NET_TILE / NET_OBS_ROWS)), NET_OBS_THREADS, net_obs_smem(H->dev), s>>>(H->dev, N, state,
                                                                                                                obs);
     ORGYM_CUDA(cudaGetLastError());
@@ -893,6 +939,9 @@ extern "C" int orgym_netinv_create(const orgym_netinv_config_t* c, int64_t num_e
             cudaFuncSetAttribute(net_sim_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
             cudaFuncSetAttribute(net_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
             H->stream_aot = 0;
+            // large graphs whose observation is assembled by net_obs_kernel keep a float32 copy of the rings in the tile
+            // (ORGYM_NET_RING32=0: off, for comparison)
+            P.ring32 = net_wants_ring32(P);
             // kernel specialised for this topology (NVRTC); any failure falls back to the generic kernel above
             H->jit_threads = 0;
             H->dem_dev = nullptr;
@@ -1097,6 +1146,7 @@ extern "C" int orgym_netinv_codegen(const orgym_netinv_config_t* cfg, int compil
         delete P;
         return rc;
     }
+    P->ring32 = net_wants_ring32(*P);
     std::string src = net_jit_source(*P, 128);
     delete P;
     if (needed) *needed = (int64_t)src.size();

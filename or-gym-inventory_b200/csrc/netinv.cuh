@@ -10,6 +10,7 @@
 
 struct NetDev {
     int T, backlog, J, E, M, obs_dim, sumL;
+    int ring32;  // the state tile carries a float32 copy of the lead-time rings for net_obs_kernel (large graphs)
     const double* disc;  // [T] alpha**t
     double I0[NJ], h[NJ], C[NJ], v[NJ], o[NJ];
     uint8_t is_factory[NJ], is_retail[NJ];
@@ -39,6 +40,7 @@ struct NetHandle {
     int jit_stream;            // STEP kernel is the streaming variant (large graphs)
     int stream_aot;            // large graphs: STEP runs the table-driven ahead-of-time streaming kernel (netinv.cu)
     int jit_obs_split;         // streaming variant without its observation pass: net_obs_kernel (TMA-staged) follows it
+    int jit_onepass;           // streaming variant in its single-pass form (no scratch rows, no action tile)
     AliasDev* dem_dev;  // device copy of dev.dem[] for the specialised kernel
 };
 
@@ -55,6 +57,7 @@ struct NetHandle {
 struct NetState {
     uint64_t* key;
     double *X, *Y, *U, *ring;
+    float* ring32;  // [sumL][NET_TILE] float32 copy of `ring` (P.ring32), after the scratch area
     int32_t* period;
     uint32_t* episode;
     // tile_base = state + (env / NET_TILE) * net_tile_bytes(P); index the fields with [slot * NET_TILE + env % NET_TILE]
@@ -70,11 +73,17 @@ struct NetState {
         period = (int32_t*)p;
         p += 4 * NET_TILE;
         episode = (uint32_t*)p;
+        p += 4 * NET_TILE + 8 * (size_t)(P.E + P.J) * NET_TILE;
+        ring32 = P.ring32 ? (float*)p : nullptr;
     }
 };
-// ... followed by the per-instance scratch area [R_t E][consumed J] float64 used by the streaming STEP kernel
+// ... followed by the per-instance scratch area [R_t E][consumed J] float64 used by the two-pass streaming STEP kernel
+// and, for the large graphs whose observation is assembled by net_obs_kernel, by a float32 copy of the rings: the
+// observation is float32 anyway, the values pass through unchanged, and the kernel that rebuilds 504 window columns
+// per instance every period reads 4 instead of 8 bytes for each.  `ring` stays authoritative (arrivals are float64).
 __host__ __device__ static inline int64_t net_tile_bytes(const NetDev& P) {
-    return (int64_t)NET_TILE * (8 + 8 * (int64_t)(P.J + P.E + P.M + P.sumL) + 8 + 8 * (int64_t)(P.E + P.J));
+    return (int64_t)NET_TILE * (8 + 8 * (int64_t)(P.J + P.E + P.M + P.sumL) + 8 + 8 * (int64_t)(P.E + P.J) +
+                                (P.ring32 ? 4 * (int64_t)P.sumL : 0));
 }
 static inline int64_t net_state_bytes(const NetDev& P, int64_t num_envs) {
     return ((num_envs + NET_TILE - 1) / NET_TILE) * net_tile_bytes(P);
@@ -87,4 +96,5 @@ int net_jit_launch(const NetHandle* H, const struct NetSimArgs& A, cudaStream_t 
 std::string net_jit_source(const NetDev& P, int nthr);
 int net_jit_uses_stream(const NetDev& P);
 size_t net_obs_smem(const NetDev& P);    // netinv.cu: shared memory of the TMA-staged observation kernel
+int net_jit_onepass(const NetDev& P);    // ORGYM_NET_JIT_ONEPASS (default 1) and suppliers follow their purchasers in node order
 int net_jit_obs_split(const NetDev& P);  // ORGYM_NET_OBS_TMA (default 1) and the observation rows fit in shared memory

@@ -54,6 +54,21 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
 int net_jit_obs_split(const NetDev& P) {
     return env_int("ORGYM_NET_OBS_TMA", 1, 0, 1) && net_obs_smem(P) <= 200 * 1024;
 }
+// Single-pass form of the streaming STEP kernel (see emit_step_stream): usable when every inventory-holding supplier comes
+// after its purchasers in main-node order (true of the reference's graphs, which number nodes market -> raw material),
+// so that a purchaser still finds its suppliers' start-of-period inventory in the state tile.
+int net_jit_onepass(const NetDev& P) {
+    if (!env_int("ORGYM_NET_JIT_ONEPASS", 1, 0, 1) || env_int("ORGYM_NET_JIT_LDGSTS", 0, 0, 1)) return 0;
+    for (int j = 0; j < P.J; j++)
+        for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
+            const int s = P.sup[P.pred_idx[z]];
+            if (s >= 0 && s <= j) return 0;
+        }
+    for (int i = 0; i + 1 < P.E; i++)  // a supplier's links must be one contiguous run of the sorted link list
+        for (int k = i + 2; k < P.E; k++)
+            if (P.sup[i] >= 0 && P.sup[k] == P.sup[i] && P.sup[i + 1] != P.sup[i]) return 0;
+    return 1;
+}
 // measured on the 64-node graph: the register-staged pass (0) beats the cp.async one (1) by 6 % -- kept as a knob
 static int stream_async() { return env_int("ORGYM_NET_JIT_ASYNC", 0, 0, 1); }
 static int stream_cw() {
@@ -80,6 +95,9 @@ std::string net_jit_source(const NetDev& P, int nthr) {
     // state tiles (netinv.cuh): NP instances per tile, slot stride NP, so every state access is base + constant
     o("#define NP %d\n#define TILE_BYTES %lldLL", NET_TILE, (long long)net_tile_bytes(P));
     // ---- observation writer (:334-413)
+    o("// order request of one link: round half to even, negative -> 0 (network_management.py:449)");
+    o("__device__ __forceinline__ double net_reqf(float a) { const double q = rint((double)a); return q > 0.0 ? q : 0.0; }");
+    o("__device__ __forceinline__ double net_req(const float* a) { return net_reqf(__ldg(a)); }");
     o("__device__ __forceinline__ void write_obs(const double (&X)[NJ > 0 ? NJ : 1], const double (&U)[NM > 0 ? NM : 1],");
     o("    const double* __restrict__ ring, int el, int t, float* o) {");
     for (int r = 0; r < M; r++) o("  o[%d] = (float)U[%d];", r, r);
@@ -381,6 +399,7 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
     o("  double* ring = s_U + NM * NP;");
     o("  int* s_period = (int*)(ring + NSUML * NP); unsigned int* s_episode = (unsigned int*)(s_period + NP);");
     o("  double* sc_R = (double*)(s_episode + NP); double* sc_C = sc_R + NE * NP;");
+    if (P.ring32) o("  float* const r32 = (float*)(sc_C + NJ * NP);   // float32 copy of the rings, read by net_obs_kernel");
     o("  float* trow = tile + tid * 33;");
     // every warp transposes the 32 rows of its own lanes: the staging tile needs warp-level synchronisation only,
     // so the warps of a CTA drift apart and cover each other's memory latency
@@ -396,6 +415,7 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
     o("        for (int i = 0; i < NE; i++) s_Y[i * NP + el] = 0.0;");
     o("        for (int r = 0; r < NM; r++) s_U[r * NP + el] = 0.0;");
     o("        for (int k = 0; k < NSUML; k++) ring[k * NP + el] = 0.0;");
+    if (P.ring32) o("        for (int k = 0; k < NSUML; k++) r32[k * NP + el] = 0.0f;");
     o("        s_period[el] = 0; s_episode[el] = episode + 1;");
     o("        A.reward[e] = 0.0; A.terminated[e] = 0; A.truncated[e] = 0;");
     o("      } else {");
@@ -431,6 +451,238 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
             for (int j = 0; j < std::min(J, GROUP * (PF - 1)); j++) emit_prefetch_node(j, "    ");
         o("  }");
     }
+    const int ONEPASS = net_jit_onepass(P);
+    o("  // stream_form=%s", ONEPASS ? "onepass" : "twopass");
+    std::vector<int> link_done(E, 0);
+    if (ONEPASS) {
+        // ---- single pass over the main nodes.  The two-pass form below parks every R_t and every supplier's consumption in
+        // scratch rows of the state tile between its passes: with the whole batch resident that is 1 KB per instance
+        // written and read back through DRAM (the scratch of 2^17 instances exceeds the L2).  Here a node recomputes what
+        // it needs instead: the allocation of a supplier is a function of that supplier's start-of-period inventory and
+        // the requests on its own links, so purchaser j re-runs the supplier's allocation chain up to its link (same
+        // operations, same order -> the same float64 R_t), and a supplier runs its whole chain for its sales and
+        // consumption.  Suppliers follow their purchasers in node order, so their X row still holds X[t].  Requests are
+        // read per lane from the row-major action tensor (a lane's row is 4*E bytes, L1-resident between uses).
+        std::vector<int> seg0(J, -1), seg1(J, -1);
+        for (int i = 0; i < E; i++)
+            if (P.sup[i] >= 0) {
+                if (seg0[P.sup[i]] < 0) seg0[P.sup[i]] = i;
+                seg1[P.sup[i]] = i;
+            }
+        o("  const float* const arow = A.actions + ec * NE;");
+        o("#define REQ(i) net_req(arow + (i))");
+        // allocation chain of supplier s from its first link to link i1; f of link i lands in variable <pfx><i>
+        auto emit_chain = [&](int s, int i1, const char* xvar, const char* pfx, const char* ind, bool keep_cons) {
+            o("%sdouble cons_%s = 0.0;", ind, pfx);
+            for (int i = seg0[s]; i <= i1; i++) {
+                o("%sdouble %s%d;", ind, pfx, i);
+                o("%s{ const double req = rq%d; double avail = %s - cons_%s; avail = avail > 0.0 ? avail : 0.0; double oa = avail;",
+                  ind, i, xvar, pfx);
+                if (P.is_factory[s])
+                    o("%s  { double mp = %s * avail; double lim = mp < %s ? mp : %s; oa = lim < oa ? lim : oa; }", ind,
+                      lit(P.v[s]).c_str(), lit(P.C[s]).c_str(), lit(P.C[s]).c_str());
+                o("%s  %s%d = oa < req ? oa : req;", ind, pfx, i);
+                if (i < i1 || keep_cons) {
+                    if (P.v[s] == 1.0)
+                        o("%s  cons_%s += %s%d; }", ind, pfx, pfx, i);
+                    else
+                        o("%s  cons_%s += %s%d / %s; }", ind, pfx, pfx, i, lit(P.v[s]).c_str());
+                } else
+                    o("%s  }", ind);
+            }
+        };
+        auto emit_rt = [&](int i, const char* xvar, const char* ind) {  // declares rt<i>
+            const int s = P.sup[i];
+            char pfx[32];
+            snprintf(pfx, sizeof(pfx), "g%d_", i);
+            if (s == -1)
+                o("%sconst double rt%d = rq%d;", ind, i, i);
+            else if (s < 0)
+                o("%sconst double rt%d = 0.0;", ind, i);
+            else {
+                emit_chain(s, i, xvar, pfx, ind, false);
+                o("%sconst double rt%d = %s%d;", ind, i, pfx, i);
+            }
+            o("%sif (A.info_sales) A.info_sales[NET_IIDX(A, e, NE + NM, %d)] = rt%d;", ind, i, i);
+        };
+        auto req_links = [&](int i) {  // links whose request the R_t of link i depends on
+            std::vector<int> v;
+            const int s = P.sup[i];
+            if (s == -1)
+                v.push_back(i);
+            else if (s >= 0)
+                for (int l = seg0[s]; l <= i; l++) v.push_back(l);
+            return v;
+        };
+        // Loads of a node: float64 state rows (name, address) and the requests (links) it needs.  (Issuing the loads of
+        // node j + 1 as asynchronous global->shared copies -- cp.async, 8- and 4-byte pieces into a two-stage per-lane
+        // landing zone -- before node j is computed was measured at 0.54 ms against 0.42 ms for the step pair: small
+        // cp.async copies are slow, and the 28 KB landing zone per CTA costs the L1 that holds the action rows.)
+        struct NodeLd {
+            std::vector<std::pair<std::string, std::string>> d8;
+            std::vector<int> acts;
+        };
+        std::vector<NodeLd> nld((size_t)J);
+        for (int j = 0; j < J; j++) {
+            NodeLd& n = nld[(size_t)j];
+            char nb[64], ab[96];
+            snprintf(nb, sizeof(nb), "x%d", j);
+            snprintf(ab, sizeof(ab), "s_X + %d * NP + el", j);
+            n.d8.push_back({nb, ab});
+            std::vector<char> need((size_t)E, 0);
+            for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
+                const int i = P.pred_idx[z], L = P.L[i], sp = P.sup[i];
+                if (sp >= 0) {
+                    snprintf(nb, sizeof(nb), "xq%d", i);
+                    snprintf(ab, sizeof(ab), "s_X + %d * NP + el", sp);
+                    n.d8.push_back({nb, ab});
+                }
+                snprintf(nb, sizeof(nb), "y%d", i);
+                snprintf(ab, sizeof(ab), "s_Y + %d * NP + el", i);
+                n.d8.push_back({nb, ab});
+                if (L > 0) {
+                    snprintf(nb, sizeof(nb), "ar%d", i);
+                    snprintf(ab, sizeof(ab), "ring + (%d + t %% %d) * NP + el", P.roff[i], L);
+                    n.d8.push_back({nb, ab});
+                }
+                for (int l : req_links(i)) need[(size_t)l] = 1;
+            }
+            for (int r = 0; r < M; r++)
+                if (P.rt_node[r] == j) {
+                    snprintf(nb, sizeof(nb), "u%d", r);
+                    snprintf(ab, sizeof(ab), "s_U + %d * NP + el", r);
+                    n.d8.push_back({nb, ab});
+                }
+            if (has_seg[j])
+                for (int l = seg0[j]; l <= seg1[j]; l++) need[(size_t)l] = 1;
+            for (int l = 0; l < E; l++)
+                if (need[(size_t)l]) n.acts.push_back(l);
+        }
+        o("  double total = 0.0;");
+        o("  if (do_step) {");
+        {  // reorder links whose purchaser holds no inventory: pipeline bookkeeping only (before any X row changes)
+            std::vector<int> has_pur(E, 0);
+            for (int j = 0; j < J; j++)
+                for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) has_pur[P.pred_idx[z]] = 1;
+            for (int i = 0; i < E; i++) {
+                if (has_pur[i]) continue;
+                link_done[i] = 1;
+                const int s = P.sup[i], L = P.L[i];
+                o("    {");
+                if (s >= 0) o("      const double xq = s_X[%d * NP + el];", s);
+                for (int l : req_links(i)) o("      const double rq%d = REQ(%d);", l, l);
+                emit_rt(i, "xq", "      ");
+                if (L == 0)
+                    o("      const double ar = rt%d;", i);
+                else
+                    o("      double* slot = ring + (%d + t %% %d) * NP + el; const double ar = *slot; *slot = rt%d;%s", P.roff[i], L, i,
+                      P.ring32 ? (std::string(" r32[slot - ring] = (float)rt") + std::to_string(i) + ";").c_str() : "");
+                o("      s_Y[%d * NP + el] = (s_Y[%d * NP + el] - ar) + rt%d; }", i, i, i);
+            }
+        }
+        // ORGYM_NET_JIT_AHEAD = d (default 0, measured no gain): the loads of node j + d are written BEFORE the arithmetic of
+        // node j.  Each node ends in stores and (uniform) branches around the optional info outputs, basic-block boundaries
+        // the compiler does not hoist loads across, so a warp pays one memory round trip per node; but at the 64 registers
+        // that keep the whole batch resident the looked-ahead values are spilled as they arrive, which waits for them all
+        // the same (0.417 / 0.417 / 0.443 ms for d = 0 / 1 / 2).  What did help is ORGYM_NET_JIT_SYNC below.
+        const int AHEAD = env_int("ORGYM_NET_JIT_AHEAD", 0, 0, 4);
+        const int SYNC1 = env_int("ORGYM_NET_JIT_SYNC", 4, 0, 64);  // measured: 0.417 ms without, 0.389-0.393 with (any cadence 1..8)
+        auto emit_loads_outer = [&](int j) {
+            const NodeLd& n = nld[(size_t)j];
+            for (const auto& d : n.d8) o("    const double p_%s = *(%s);", d.first.c_str(), d.second.c_str());
+            for (int l : n.acts) o("    const float pa%d_%d = __ldg(arow + %d);", j, l, l);
+        };
+        for (int j = 0; j < std::min(J, AHEAD); j++) emit_loads_outer(j);
+        for (int j = 0; j < J; j++) {
+            if (AHEAD > 0 && j + AHEAD < J) emit_loads_outer(j + AHEAD);
+            o("    {");
+            const NodeLd& n = nld[(size_t)j];
+            for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
+                const int i = P.pred_idx[z], L = P.L[i];
+                if (L > 0) o("      double* const slot%d = ring + (%d + t %% %d) * NP + el;", i, P.roff[i], L);
+            }
+            if (AHEAD > 0) {
+                for (const auto& d : n.d8) o("      const double %s = p_%s;", d.first.c_str(), d.first.c_str());
+                for (int l : n.acts) o("      const double rq%d = net_reqf(pa%d_%d);", l, j, l);
+            } else {  // loads first (all independent)
+                for (const auto& d : n.d8) o("      const double %s = *(%s);", d.first.c_str(), d.second.c_str());
+                for (int l : n.acts) o("      const double rq%d = REQ(%d);", l, l);
+            }
+            // R_t of the inbound links, own allocation chain
+            for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
+                const int i = P.pred_idx[z];
+                char xv[32];
+                snprintf(xv, sizeof(xv), "xq%d", i);
+                emit_rt(i, xv, "      ");
+                link_done[i] = 1;
+            }
+            if (has_seg[j]) {
+                char xv[32];
+                snprintf(xv, sizeof(xv), "x%d", j);
+                emit_chain(j, seg1[j], xv, "qs", "      ", true);
+            }
+            o("      { double arr = 0.0, PC = 0.0, HCp = 0.0;");
+            for (int z = P.pred_ptr[j]; z < P.pred_ptr[j + 1]; z++) {
+                const int i = P.pred_idx[z], L = P.L[i];
+                if (L == 0)
+                    o("        { const double ar = rt%d;", i);
+                else
+                    o("        { const double ar = ar%d; *slot%d = rt%d;%s", i, i, i,
+                      P.ring32 ? (std::string(" r32[slot") + std::to_string(i) + " - ring] = (float)rt" + std::to_string(i) + ";").c_str() : "");
+                o("          arr += ar; const double yn = (y%d - ar) + rt%d; s_Y[%d * NP + el] = yn;", i, i, i);
+                o("          PC += %s * rt%d; HCp += %s * (yn > 0.0 ? yn : 0.0); }", lit(P.p[i]).c_str(), i, lit(P.g[i]).c_str());
+            }
+            if (has_seg[j])
+                o("        double x = (x%d + arr) - cons_qs;", j);
+            else
+                o("        double x = (x%d + arr) - 0.0;", j);
+            o("        double SR = 0.0, sold = 0.0, UP = 0.0;");
+            for (int r = 0; r < M; r++) {
+                if (P.rt_node[r] != j) continue;
+                o("        double S%d, U%d;", r, r);
+                o("        { double d;");
+                o("          if (A.demand) d = rint(A.demand[e * A.d_se + %d]);", r);
+                o("          else d = (double)sample_fixed(dem[%d], dem[%d].table, key, episode, t, %du);", r, r, r);
+                o("          d = d > 0.0 ? d : 0.0;");
+                o("          const double fill = d + u%d; const double invr = x > 0.0 ? x : 0.0;", r);
+                o("          S%d = invr < fill ? invr : fill; x = x - S%d; const double un = fill - S%d; U%d = %s;", r, r, r, r,
+                  P.backlog ? "un" : "0.0");
+                o("          s_U[%d * NP + el] = U%d;", r, r);
+                o("          if (A.info_demand) A.info_demand[NET_IIDX(A, e, NM, %d)] = d;", r);
+                o("          if (A.info_sales) A.info_sales[NET_IIDX(A, e, NE + NM, %d)] = S%d; }", E + r, r);
+            }
+            o("        s_X[%d * NP + el] = x;", j);
+            for (int z = P.succ_ptr[j]; z < P.succ_ptr[j + 1]; z++) {
+                const int l = P.succ_idx[z];
+                if (l < E)
+                    o("        SR += %s * qs%d; sold += qs%d;", lit(P.p[l]).c_str(), l, l);
+                else {
+                    const int r = l - E;
+                    if (P.is_retail[j]) o("        UP += %s * U%d;", lit(P.rt_b[r]).c_str(), r);
+                    o("        SR += %s * S%d; sold += S%d;", lit(P.rt_p[r]).c_str(), r, r);
+                }
+            }
+            o("        const double xp = x > 0.0 ? x : 0.0; const double HC = %s * xp + HCp; double OC = 0.0;", lit(P.h[j]).c_str());
+            if (P.is_factory[j]) {
+                if (!(P.v[j] > 0.0))
+                    o("        OC = 0.0;");
+                else if (P.v[j] == 1.0)
+                    o("        OC = %s * sold;", lit(P.o[j]).c_str());
+                else
+                    o("        OC = %s * (sold / %s);", lit(P.o[j]).c_str(), lit(P.v[j]).c_str());
+            }
+            o("        (void)sold; const double pj = (((SR - PC) - OC) - HC) - UP; total += pj;");
+            o("        if (A.info_profit) A.info_profit[NET_IIDX(A, e, NJ, %d)] = pj; }", j);
+            o("    }");
+            // ORGYM_NET_JIT_SYNC=k: a CTA-wide barrier after every k-th node keeps the warps of a CTA within the same stretch of
+            // this long straight-line kernel, so an instruction line is fetched once per CTA rather than once per warp
+            if (SYNC1 > 0 && AHEAD == 0 && (j + 1) % SYNC1 == 0 && j + 1 < J) {
+                o("  }");
+                o("  __syncthreads();");
+                o("  if (do_step) {");
+            }
+        }
+    } else {
     // ---- pass A: orders, 32 links per action chunk
     o("  double cons = 0.0;");
     for (int j = 0; j < J; j++)
@@ -486,7 +738,6 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
     }
     o("  double total = 0.0;");
     o("  if (do_step) {");
-    std::vector<int> link_done(E, 0);
     // Nodes are independent of each other in this pass (every link has one purchaser, every market link one retailer;
     // R_t / consumed are read-only here), so they are processed in groups: all loads of a group are issued first
     // (dozens of independent loads in flight), then the group's arithmetic and stores.
@@ -563,7 +814,8 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
                 if (L == 0)
                     o("        { const double ar = rt%d;", i);
                 else
-                    o("        { const double ar = ar%d; *slot%d = rt%d;", i, i, i);
+                    o("        { const double ar = ar%d; *slot%d = rt%d;%s", i, i, i,
+                      P.ring32 ? (std::string(" r32[slot") + std::to_string(i) + " - ring] = (float)rt" + std::to_string(i) + ";").c_str() : "");
                 o("          arr += ar; const double yn = (y%d - ar) + rt%d; s_Y[%d * NP + el] = yn;", i, i, i);
                 o("          PC += %s * rt%d; HCp += %s * (yn > 0.0 ? yn : 0.0); }", lit(P.p[i]).c_str(), i, lit(P.g[i]).c_str());
             }
@@ -616,6 +868,7 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
             o("  if (do_step) {");
         }
     }
+    }
     for (int i = 0; i < E; i++) {  // reorder links whose purchaser holds no inventory: pipeline bookkeeping only
         if (link_done[i]) continue;
         const int L = P.L[i];
@@ -623,7 +876,8 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
         if (L == 0)
             o("      const double ar = rt;");
         else
-            o("      double* slot = ring + (%d + t %% %d) * NP + el; const double ar = *slot; *slot = rt;", P.roff[i], L);
+            o("      double* slot = ring + (%d + t %% %d) * NP + el; const double ar = *slot; *slot = rt;%s", P.roff[i], L,
+              P.ring32 ? " r32[slot - ring] = (float)rt;" : "");
         o("      s_Y[%d * NP + el] = (s_Y[%d * NP + el] - ar) + rt; }", i, i);
     }
     o("    const int tn = t + 1; const bool trunc = tn >= NT;");
@@ -638,6 +892,7 @@ void emit_step_stream(Src& o, const NetDev& P, int min_blocks) {
     o("      for (int i = 0; i < NE; i++) s_Y[i * NP + el] = 0.0;");
     o("      for (int r = 0; r < NM; r++) s_U[r * NP + el] = 0.0;");
     o("      for (int k = 0; k < NSUML; k++) ring[k * NP + el] = 0.0;");
+    if (P.ring32) o("      for (int k = 0; k < NSUML; k++) r32[k * NP + el] = 0.0f;");
     o("      s_period[el] = 0; s_episode[el] = episode + 1;");
     o("    } else s_period[el] = tn;");
     o("  }");
@@ -744,6 +999,7 @@ int net_jit_build(NetHandle* H, std::string* err) {
     std::string src = net_jit_source(P, H->jit_threads);
     H->jit_stream = net_jit_uses_stream(P);
     H->jit_obs_split = H->jit_stream && net_jit_obs_split(P);
+    H->jit_onepass = H->jit_stream && net_jit_onepass(P);
     int rc = orgym_jit_compile(src, "net_jit_step", &H->jit, err);
     if (rc != 0) return rc;
     if (cudaLibraryGetKernel(&H->jit_rollout, H->jit.lib, "net_jit_rollout") != cudaSuccess) {
@@ -775,7 +1031,7 @@ int net_jit_launch(const NetHandle* H, const NetSimArgs& A_in, cudaStream_t s) {
     size_t smem = 16;
     if (!A.rollout && H->jit_stream) {
         A.use_tile = 0;  // the streaming kernel stages through its own tiles
-        smem = net_jit_stream_smem(nthr);
+        smem = H->jit_onepass && H->jit_obs_split ? 16 : net_jit_stream_smem(nthr);  // the single-pass form stages nothing
     } else if (!A.rollout) {
         A.use_tile = tile <= 160 * 1024 ? 1 : 0;
         if (A.use_tile) smem = tile;

@@ -426,6 +426,14 @@ __global__ void nv_export_params_kernel(int64_t N, int64_t npad, int L, const vo
 // The search advances four terms per trip: the partial sums are formed in the same order as a term-by-term loop
 // (identical floating-point values), but only the last one is compared with q -- the CDF is non-decreasing, so the
 // quantile lies in the block iff its last partial sum reaches q.
+// four consecutive table entries from a 32-byte aligned address as ONE 256-bit load (sm_100: LDG.E.256): a lane's block
+// of reciprocals is exactly one L1 sector, fetched with one request instead of two
+struct D4 { double x, y, z, w; };
+__device__ __forceinline__ D4 ld_rcp4(const double* p) {
+    D4 v;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ double poisson_ppf_dev(double q, double mu, const double* __restrict__ rcp) {
     if (!(q > 0.0)) return -1.0;
     if (q >= 1.0) return INFINITY;
@@ -437,39 +445,84 @@ __device__ __forceinline__ double poisson_ppf_dev(double q, double mu, const dou
     // Every lane walks the reciprocal table at its own k, so a warp load is a gather: with four 8-byte loads per block at
     // an arbitrary offset it touched ~20 sectors per load and the L1 data stage bounded the search (ncu, round 2).
     // Up to three single steps first bring k + 1 to a multiple of 4; the block's four reciprocals are then one aligned
-    // 32-byte piece -- two 16-byte loads, one sector per lane.  Term-by-term the arithmetic is unchanged.
-    while (((k + 1) & 3) != 0 && k + 1 <= ORGYM_RCP_N) {
-        const double c = cdf + term;
-        if (c >= q) return (double)k;
-        term *= mu * rcp[k + 1];
-        ++k;
-        if (term == 0.0 && k > kmu) return (double)k;
-        cdf = c;
+    // 32-byte piece -- one 256-bit load, one sector per lane.  Term-by-term the arithmetic is unchanged.
+    // Single exit: the result is carried in (res, done) instead of returning from inside the loops.  With early returns
+    // the lanes of a warp left the alignment steps on different paths and were not reconverged before the block loop,
+    // which then ran once per alignment class (ncu: twice the trips of the warp's slowest lane).
+    double res = 0.0;
+    bool done = false;
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+        if (!done && ((k + 1) & 3) != 0 && k + 1 <= ORGYM_RCP_N) {
+            const double c = cdf + term;
+            if (c >= q) {
+                res = (double)k;
+                done = true;
+            } else {
+                term *= mu * rcp[k + 1];
+                ++k;
+                if (term == 0.0 && k > kmu) {
+                    res = (double)k;
+                    done = true;
+                }
+                cdf = c;
+            }
+        }
     }
-    while (k + 4 <= ORGYM_RCP_N) {
-        const double2 ra = *reinterpret_cast<const double2*>(rcp + k + 1), rb = *reinterpret_cast<const double2*>(rcp + k + 3);
-        const double t0 = term, t1 = t0 * (mu * ra.x), t2 = t1 * (mu * ra.y), t3 = t2 * (mu * rb.x),
-                     t4 = t3 * (mu * rb.y);
+    // Eight terms per trip (two aligned 32-byte pieces of the reciprocal table), then four, with the partial sums formed
+    // in term order.  (cdf, term, k) advance unconditionally -- they are dead once done is set, so no copies of the old
+    // values stay alive across a block.
+    while (!done && k + 8 <= ORGYM_RCP_N) {
+        const D4 ra = ld_rcp4(rcp + k + 1), rb = ld_rcp4(rcp + k + 5);
+        const double t0 = term, t1 = t0 * (mu * ra.x), t2 = t1 * (mu * ra.y), t3 = t2 * (mu * ra.z), t4 = t3 * (mu * ra.w),
+                     t5 = t4 * (mu * rb.x), t6 = t5 * (mu * rb.y), t7 = t6 * (mu * rb.z), t8 = t7 * (mu * rb.w);
+        const double c0 = cdf + t0, c1 = c0 + t1, c2 = c1 + t2, c3 = c2 + t3, c4 = c3 + t4, c5 = c4 + t5, c6 = c5 + t6,
+                     c7 = c6 + t7;
+        if (c7 >= q) {
+            const int j = c3 >= q ? (c0 >= q ? 0 : (c1 >= q ? 1 : (c2 >= q ? 2 : 3)))
+                                  : (c4 >= q ? 4 : (c5 >= q ? 5 : (c6 >= q ? 6 : 7)));
+            res = (double)(k + j);
+            done = true;
+        } else if (t8 == 0.0 && k + 8 > kmu) {  // underflow beyond the mean: q is within rounding of 1
+            const double tt[8] = {t1, t2, t3, t4, t5, t6, t7, t8};
+            int j = 8;
+#pragma unroll
+            for (int i = 7; i >= 1; i--)
+                if (tt[i - 1] == 0.0 && k + i > kmu) j = i;
+            res = (double)(k + j);
+            done = true;
+        }
+        cdf = c7;
+        term = t8;
+        k += 8;
+    }
+    if (!done && k + 4 <= ORGYM_RCP_N) {
+        const D4 ra = ld_rcp4(rcp + k + 1);
+        const double t0 = term, t1 = t0 * (mu * ra.x), t2 = t1 * (mu * ra.y), t3 = t2 * (mu * ra.z),
+                     t4 = t3 * (mu * ra.w);
         const double c0 = cdf + t0, c1 = c0 + t1, c2 = c1 + t2, c3 = c2 + t3;
-        if (c3 >= q) return (double)(k + (c0 >= q ? 0 : (c1 >= q ? 1 : (c2 >= q ? 2 : 3))));
-        if (t4 == 0.0) {  // underflow beyond the mean: q is within rounding of 1
-            if (t1 == 0.0 && k + 1 > kmu) return (double)(k + 1);
-            if (t2 == 0.0 && k + 2 > kmu) return (double)(k + 2);
-            if (t3 == 0.0 && k + 3 > kmu) return (double)(k + 3);
-            if (k + 4 > kmu) return (double)(k + 4);
+        if (c3 >= q) {
+            res = (double)(k + (c0 >= q ? 0 : (c1 >= q ? 1 : (c2 >= q ? 2 : 3))));
+            done = true;
+        } else if (t4 == 0.0 && k + 4 > kmu) {
+            res = (double)(k + ((t1 == 0.0 && k + 1 > kmu) ? 1 : ((t2 == 0.0 && k + 2 > kmu) ? 2 : ((t3 == 0.0 && k + 3 > kmu) ? 3 : 4))));
+            done = true;
         }
         cdf = c3;
         term = t4;
         k += 4;
     }
-    for (;;) {  // beyond the reciprocal table (means in the thousands)
-        cdf += term;
-        if (cdf >= q) break;
-        ++k;
-        term *= mu * (k <= ORGYM_RCP_N ? rcp[k] : __drcp_rn((double)k));
-        if (term == 0.0 && (double)k > mu) break;
+    if (!done) {  // beyond the reciprocal table (means in the thousands)
+        for (;;) {
+            cdf += term;
+            if (cdf >= q) break;
+            ++k;
+            term *= mu * (k <= ORGYM_RCP_N ? rcp[k] : __drcp_rn((double)k));
+            if (term == 0.0 && (double)k > mu) break;
+        }
+        res = (double)k;
     }
-    return (double)k;
+    return res;
 }
 
 // ---- fused rollout ----------------------------------------------------------------------------------------------

@@ -90,6 +90,38 @@ def test_network_kernel_specialiser_compiles_without_gpu(lib, kind):
     assert len(src) == need.value and "net_jit_step" in src and "net_jit_rollout" in src and f"#define NE {len(P.reorder_links)}" in src
 
 
+def test_streaming_step_kernel_form_follows_node_order(lib, monkeypatch):
+    """netinv_jit.cu: the streaming STEP kernel is generated as one pass over the nodes (no scratch rows) when every
+    inventory-holding supplier has a larger node id than its purchasers -- the reference's numbering, market -> raw
+    material -- and as two passes otherwise (the same network with the ids mirrored)."""
+    import networkx as nx
+    monkeypatch.setenv("ORGYM_NET_JIT_STREAM", "1")
+
+    def form(P, compile_check=0):
+        keep = []
+        cfg = P.to_c(keep)
+        need = C.c_int64(0)
+        buf = C.create_string_buffer(8 << 20)
+        rc = lib.orgym_netinv_codegen(C.byref(cfg), compile_check, buf, len(buf), C.byref(need))
+        assert rc == 0, lib.orgym_last_error()
+        src = buf.value.decode()
+        assert "step_kernel_kind=stream" in src
+        return "onepass" if "stream_form=onepass" in src else "twopass", src
+
+    P = pkg.NetInvMgmtParams(default_graph_kind="default")
+    f, src = form(P, 1)
+    assert f == "onepass" and "sc_R[" not in src.split("net_jit_step(")[1].split("net_jit_rollout")[0].split("stream_form")[1].split("const int tn")[0]
+    from or_gym_inventory_b200.network_management import default_graph
+    g = default_graph()
+    n = max(g.nodes)
+    g2 = nx.relabel_nodes(g, {k: n - k for k in g.nodes}, copy=True)
+    P2 = pkg.NetInvMgmtParams(graph=g2)
+    f2, src2 = form(P2, 1)
+    assert f2 == "twopass" and "sc_R[" in src2
+    monkeypatch.setenv("ORGYM_NET_JIT_ONEPASS", "0")
+    assert form(P)[0] == "twopass"
+
+
 @pytest.mark.parametrize("kind", ["default_lost", "default_backlog", "zero_lead", "binomial"])
 def test_serial_rollout_specialiser_compiles_without_gpu(lib, kind):
     """invmgmt_jit.cu: configuration -> straight-line CUDA for the fused rollout -> NVRTC compile check for sm_100a."""

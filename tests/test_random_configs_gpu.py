@@ -101,11 +101,13 @@ def test_newsvendor_random_config(case):
     env.close()
 
 
-def _random_graph(rng):
+def _random_graph(rng, ordered=False):
     import networkx as nx
     g = nx.DiGraph()
     n_mk, n_rt, n_ds, n_fc, n_raw = 2, int(rng.integers(1, 4)), int(rng.integers(1, 3)), int(rng.integers(1, 4)), 2
     ids = list(rng.permutation(n_mk + n_rt + n_ds + n_fc + n_raw) + 10)   # shuffled node ids: sorted order != insertion order
+    if ordered:   # ids ascending market -> raw material, as in the reference's graphs (single-pass streaming kernel)
+        ids = sorted(ids, reverse=True)
     take = lambda k: [int(ids.pop()) for _ in range(k)]  # noqa: E731
     mk, rt, ds, fc, raw = take(n_mk), take(n_rt), take(n_ds), take(n_fc), take(n_raw)
     g.add_nodes_from(mk)
@@ -133,16 +135,17 @@ def _random_graph(rng):
     return g
 
 
-@pytest.mark.parametrize("mode", ["specialised", "stream", "stream_jit", "generic"])
+@pytest.mark.parametrize("mode", ["specialised", "stream", "stream_jit", "stream_jit_twopass", "generic"])
 @pytest.mark.parametrize("case", range(6 * STRESS))
 def test_netinv_random_graph(case, mode, monkeypatch):
     from oracle import oracle
     torch = _torch()
     monkeypatch.setenv("ORGYM_NET_JIT", "0" if mode == "generic" else "2")
     monkeypatch.setenv("ORGYM_NET_JIT_STREAM", "1" if mode.startswith("stream") else "0")
-    monkeypatch.setenv("ORGYM_NET_STREAM_AOT", "0" if mode == "stream_jit" else "1")
+    monkeypatch.setenv("ORGYM_NET_STREAM_AOT", "0" if mode.startswith("stream_jit") else "1")
+    monkeypatch.setenv("ORGYM_NET_JIT_ONEPASS", "0" if mode == "stream_jit_twopass" else "1")
     rng = np.random.default_rng(3000 + case)
-    g = _random_graph(rng)
+    g = _random_graph(rng, ordered=bool(case % 2))
     T = int(rng.integers(4, 26))
     N = 130
     env = pkg.NetInvMgmtMasterEnv(graph=g, num_periods=T, backlog=bool(case % 2), alpha=float(rng.uniform(0.9, 1.0)),
