@@ -434,85 +434,101 @@ __device__ __forceinline__ D4 ld_rcp4(const double* p) {
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
     return v;
 }
-__device__ __forceinline__ double poisson_ppf_dev(double q, double mu, const double* __restrict__ rcp) {
-    if (!(q > 0.0)) return -1.0;
-    if (q >= 1.0) return INFINITY;
+// The search is written as three pieces over one state (a kernel can then interleave the searches of several episodes
+// with exactly the arithmetic of the plain loop: see nv_level_kernel).
+struct PpfState {
+    double q, mu, cdf, term, res;  // term = pmf(k), cdf = P(X < k)
+    int k, kmu;                    // for integer k: k > mu <=> k > floor(mu) = kmu
+    bool done;
+};
+// Every lane walks the reciprocal table at its own k, so a warp load is a gather: with four 8-byte loads per block at
+// an arbitrary offset it touched ~20 sectors per load and the L1 data stage bounded the search (ncu, round 2).
+// Up to three single steps first bring k + 1 to a multiple of 4; the block's four reciprocals are then one aligned
+// 32-byte piece -- one 256-bit load, one sector per lane.  Term-by-term the arithmetic is unchanged.
+// Single exit: the result is carried in (res, done) instead of returning from inside the loops.  With early returns
+// the lanes of a warp left the alignment steps on different paths and were not reconverged before the block loop,
+// which then ran once per alignment class (ncu: twice the trips of the warp's slowest lane).
+__device__ __forceinline__ void ppf_init(PpfState& S, double q, double mu, const double* __restrict__ rcp) {
+    S.q = q; S.mu = mu; S.cdf = 0.0; S.term = 0.0; S.res = 0.0; S.k = 0; S.kmu = 0; S.done = false;
+    if (!(q > 0.0)) { S.res = -1.0; S.done = true; return; }
+    if (q >= 1.0) { S.res = INFINITY; S.done = true; return; }
     double lo = floor(mu - 9.0 * sqrt(mu) - 9.0);
     if (lo < 0.0) lo = 0.0;
-    double term = exp(-mu + lo * log(mu) - lgamma(lo + 1.0)), cdf = 0.0;  // term = pmf(k), cdf = P(X < k)
-    int k = (int)lo;
-    const int kmu = mu < 1e9 ? (int)mu : 1000000000;  // for integer k: k > mu <=> k > floor(mu)
-    // Every lane walks the reciprocal table at its own k, so a warp load is a gather: with four 8-byte loads per block at
-    // an arbitrary offset it touched ~20 sectors per load and the L1 data stage bounded the search (ncu, round 2).
-    // Up to three single steps first bring k + 1 to a multiple of 4; the block's four reciprocals are then one aligned
-    // 32-byte piece -- one 256-bit load, one sector per lane.  Term-by-term the arithmetic is unchanged.
-    // Single exit: the result is carried in (res, done) instead of returning from inside the loops.  With early returns
-    // the lanes of a warp left the alignment steps on different paths and were not reconverged before the block loop,
-    // which then ran once per alignment class (ncu: twice the trips of the warp's slowest lane).
-    double res = 0.0;
-    bool done = false;
+    S.term = exp(-mu + lo * log(mu) - lgamma(lo + 1.0));
+    S.k = (int)lo;
+    S.kmu = mu < 1e9 ? (int)mu : 1000000000;
 #pragma unroll
     for (int s = 0; s < 3; s++) {
-        if (!done && ((k + 1) & 3) != 0 && k + 1 <= ORGYM_RCP_N) {
-            const double c = cdf + term;
+        if (!S.done && ((S.k + 1) & 3) != 0 && S.k + 1 <= ORGYM_RCP_N) {
+            const double c = S.cdf + S.term;
             if (c >= q) {
-                res = (double)k;
-                done = true;
+                S.res = (double)S.k;
+                S.done = true;
             } else {
-                term *= mu * rcp[k + 1];
-                ++k;
-                if (term == 0.0 && k > kmu) {
-                    res = (double)k;
-                    done = true;
+                S.term *= mu * rcp[S.k + 1];
+                ++S.k;
+                if (S.term == 0.0 && S.k > S.kmu) {
+                    S.res = (double)S.k;
+                    S.done = true;
                 }
-                cdf = c;
+                S.cdf = c;
             }
         }
     }
-    // Eight terms per trip (two aligned 32-byte pieces of the reciprocal table), then four, with the partial sums formed
-    // in term order.  (cdf, term, k) advance unconditionally -- they are dead once done is set, so no copies of the old
-    // values stay alive across a block.
-    while (!done && k + 8 <= ORGYM_RCP_N) {
-        const D4 ra = ld_rcp4(rcp + k + 1), rb = ld_rcp4(rcp + k + 5);
-        const double t0 = term, t1 = t0 * (mu * ra.x), t2 = t1 * (mu * ra.y), t3 = t2 * (mu * ra.z), t4 = t3 * (mu * ra.w),
-                     t5 = t4 * (mu * rb.x), t6 = t5 * (mu * rb.y), t7 = t6 * (mu * rb.z), t8 = t7 * (mu * rb.w);
-        const double c0 = cdf + t0, c1 = c0 + t1, c2 = c1 + t2, c3 = c2 + t3, c4 = c3 + t4, c5 = c4 + t5, c6 = c5 + t6,
-                     c7 = c6 + t7;
-        if (c7 >= q) {
-            const int j = c3 >= q ? (c0 >= q ? 0 : (c1 >= q ? 1 : (c2 >= q ? 2 : 3)))
-                                  : (c4 >= q ? 4 : (c5 >= q ? 5 : (c6 >= q ? 6 : 7)));
-            res = (double)(k + j);
-            done = true;
-        } else if (t8 == 0.0 && k + 8 > kmu) {  // underflow beyond the mean: q is within rounding of 1
-            const double tt[8] = {t1, t2, t3, t4, t5, t6, t7, t8};
-            int j = 8;
+}
+// Eight terms (two aligned 32-byte pieces of the reciprocal table) with the partial sums formed in term order; requires
+// !S.done and S.k + 8 <= ORGYM_RCP_N.  (cdf, term, k) advance unconditionally -- they are dead once done is set, so no
+// copies of the old values stay alive across a block.
+__device__ __forceinline__ void ppf_step8(PpfState& S, const double* __restrict__ rcp) {
+    const double q = S.q, mu = S.mu;
+    const int k = S.k, kmu = S.kmu;
+    const D4 ra = ld_rcp4(rcp + k + 1), rb = ld_rcp4(rcp + k + 5);
+    const double t0 = S.term, t1 = t0 * (mu * ra.x), t2 = t1 * (mu * ra.y), t3 = t2 * (mu * ra.z), t4 = t3 * (mu * ra.w),
+                 t5 = t4 * (mu * rb.x), t6 = t5 * (mu * rb.y), t7 = t6 * (mu * rb.z), t8 = t7 * (mu * rb.w);
+    const double c0 = S.cdf + t0, c1 = c0 + t1, c2 = c1 + t2, c3 = c2 + t3, c4 = c3 + t4, c5 = c4 + t5, c6 = c5 + t6,
+                 c7 = c6 + t7;
+    if (c7 >= q) {
+        const int j = c3 >= q ? (c0 >= q ? 0 : (c1 >= q ? 1 : (c2 >= q ? 2 : 3)))
+                              : (c4 >= q ? 4 : (c5 >= q ? 5 : (c6 >= q ? 6 : 7)));
+        S.res = (double)(k + j);
+        S.done = true;
+    } else if (t8 == 0.0 && k + 8 > kmu) {  // underflow beyond the mean: q is within rounding of 1
+        const double tt[8] = {t1, t2, t3, t4, t5, t6, t7, t8};
+        int j = 8;
 #pragma unroll
-            for (int i = 7; i >= 1; i--)
-                if (tt[i - 1] == 0.0 && k + i > kmu) j = i;
-            res = (double)(k + j);
-            done = true;
-        }
-        cdf = c7;
-        term = t8;
-        k += 8;
+        for (int i = 7; i >= 1; i--)
+            if (tt[i - 1] == 0.0 && k + i > kmu) j = i;
+        S.res = (double)(k + j);
+        S.done = true;
     }
-    if (!done && k + 4 <= ORGYM_RCP_N) {
+    S.cdf = c7;
+    S.term = t8;
+    S.k = k + 8;
+}
+// the last block of four inside the table, then term by term beyond it (means in the thousands); requires !S.done
+__device__ __forceinline__ void ppf_tail(PpfState& S, const double* __restrict__ rcp) {
+    const double q = S.q, mu = S.mu;
+    const int kmu = S.kmu;
+    if (S.k + 4 <= ORGYM_RCP_N) {
+        const int k = S.k;
         const D4 ra = ld_rcp4(rcp + k + 1);
-        const double t0 = term, t1 = t0 * (mu * ra.x), t2 = t1 * (mu * ra.y), t3 = t2 * (mu * ra.z),
+        const double t0 = S.term, t1 = t0 * (mu * ra.x), t2 = t1 * (mu * ra.y), t3 = t2 * (mu * ra.z),
                      t4 = t3 * (mu * ra.w);
-        const double c0 = cdf + t0, c1 = c0 + t1, c2 = c1 + t2, c3 = c2 + t3;
+        const double c0 = S.cdf + t0, c1 = c0 + t1, c2 = c1 + t2, c3 = c2 + t3;
         if (c3 >= q) {
-            res = (double)(k + (c0 >= q ? 0 : (c1 >= q ? 1 : (c2 >= q ? 2 : 3))));
-            done = true;
+            S.res = (double)(k + (c0 >= q ? 0 : (c1 >= q ? 1 : (c2 >= q ? 2 : 3))));
+            S.done = true;
         } else if (t4 == 0.0 && k + 4 > kmu) {
-            res = (double)(k + ((t1 == 0.0 && k + 1 > kmu) ? 1 : ((t2 == 0.0 && k + 2 > kmu) ? 2 : ((t3 == 0.0 && k + 3 > kmu) ? 3 : 4))));
-            done = true;
+            S.res = (double)(k + ((t1 == 0.0 && k + 1 > kmu) ? 1 : ((t2 == 0.0 && k + 2 > kmu) ? 2 : ((t3 == 0.0 && k + 3 > kmu) ? 3 : 4))));
+            S.done = true;
         }
-        cdf = c3;
-        term = t4;
-        k += 4;
+        S.cdf = c3;
+        S.term = t4;
+        S.k = k + 4;
     }
-    if (!done) {  // beyond the reciprocal table (means in the thousands)
+    if (!S.done) {
+        int k = S.k;
+        double cdf = S.cdf, term = S.term;
         for (;;) {
             cdf += term;
             if (cdf >= q) break;
@@ -520,9 +536,16 @@ __device__ __forceinline__ double poisson_ppf_dev(double q, double mu, const dou
             term *= mu * (k <= ORGYM_RCP_N ? rcp[k] : __drcp_rn((double)k));
             if (term == 0.0 && (double)k > mu) break;
         }
-        res = (double)k;
+        S.res = (double)k;
+        S.done = true;
     }
-    return res;
+}
+__device__ __forceinline__ double poisson_ppf_dev(double q, double mu, const double* __restrict__ rcp) {
+    PpfState S;
+    ppf_init(S, q, mu, rcp);
+    while (!S.done && S.k + 8 <= ORGYM_RCP_N) ppf_step8(S, rcp);
+    if (!S.done) ppf_tail(S, rcp);
+    return S.res;
 }
 
 // ---- fused rollout ----------------------------------------------------------------------------------------------
@@ -554,24 +577,32 @@ __device__ __forceinline__ bool nv_classic_fallback(float fh, float fk) {
     const float hk = fh + fk;
     return hk <= 1e-6f || fk < 0.0f || fh < 0.0f;
 }
-__device__ __forceinline__ double nv_policy_level(const NvDev& P, int policy, double param0, int L, float fh, float fk, float fmu) {
-    double level = 0.0;
+// the level is poisson_ppf(*q, *mu) passed through nv_level_finish when this returns true, 0 otherwise
+__device__ __forceinline__ bool nv_level_query(int policy, double param0, int L, float fh, float fk, float fmu, double* q,
+                                               double* mu) {
     if (policy == ORGYM_NV_POLICY_CLASSIC) {
-        if (!nv_classic_fallback(fh, fk)) {
-            const float cr = fk / (fh + fk);
-            const float eff = (fmu * (float)(L + 1)) * (float)param0;
-            level = poisson_ppf_dev((double)cr, eff > 1e-6f ? (double)eff : 1e-6, P.rcp);
-        }
-    } else {
-        if (fh + fk > 1e-6f) {
-            float cr = fk / (fh + fk);
-            cr = cr < 0.001f ? 0.001f : (cr > 0.999f ? 0.999f : cr);
-            const float eff = fmu * (float)(L + 1);
-            level = poisson_ppf_dev((double)cr, eff > 1e-6f ? (double)eff : 1e-6, P.rcp);
-        }
-        level = level > 0.0 ? level : 0.0;
+        if (nv_classic_fallback(fh, fk)) return false;
+        const float cr = fk / (fh + fk);
+        const float eff = (fmu * (float)(L + 1)) * (float)param0;
+        *q = (double)cr;
+        *mu = eff > 1e-6f ? (double)eff : 1e-6;
+        return true;
     }
-    return level;
+    if (!(fh + fk > 1e-6f)) return false;
+    float cr = fk / (fh + fk);
+    cr = cr < 0.001f ? 0.001f : (cr > 0.999f ? 0.999f : cr);
+    const float eff = fmu * (float)(L + 1);
+    *q = (double)cr;
+    *mu = eff > 1e-6f ? (double)eff : 1e-6;
+    return true;
+}
+__device__ __forceinline__ double nv_level_finish(int policy, double ppf) {
+    return policy == ORGYM_NV_POLICY_CLASSIC ? ppf : (ppf > 0.0 ? ppf : 0.0);
+}
+__device__ __forceinline__ double nv_policy_level(const NvDev& P, int policy, double param0, int L, float fh, float fk, float fmu) {
+    double q, mu;
+    if (!nv_level_query(policy, param0, L, fh, fk, fmu, &q, &mu)) return 0.0;
+    return nv_level_finish(policy, poisson_ppf_dev(q, mu, P.rcp));
 }
 
 __device__ __forceinline__ float clipf(float q, float hi) { return q < 0.0f ? 0.0f : (q > hi ? hi : q); }
@@ -734,8 +765,8 @@ __global__ void __launch_bounds__(NV_ROLL_THREADS, NV_ROLL_MINB) nv_rollout_kern
 
 // The Poisson quantile behind that level is a serial float64 recurrence of a few hundred terms per episode.  Inside the
 // rollout kernel (96 registers, 5 warps per scheduler) its latency is exposed: 19 % of the instructions but ~40 % of the
-// time of a classic-policy rollout.  As a kernel of its own -- one thread per episode, nothing else live -- it runs at
-// several times the occupancy and hides that latency; the level travels to the rollout kernel through the episode's
+// time of a classic-policy rollout.  As a kernel of its own -- nothing else live -- it runs at several times the
+// occupancy and hides that latency; the level travels to the rollout kernel through the episode's
 // slot of the ep_return output array (written here, read at the start of the rollout, overwritten with the return at
 // its end), so no extra memory is needed.  Same arithmetic, same value.
 struct NvLevelArgs {
@@ -747,6 +778,11 @@ struct NvLevelArgs {
     const double* fixed;
     double* level_out;
 };
+// One thread per episode.  The searches differ in length (a few to ~110 blocks of eight terms, by the episode's demand
+// mean and critical ratio), so 19 of a warp's 32 lanes are active on average.  Measured alternative (round 2, in the
+// history of this file): a warp prepares 256 episodes, parks the search states in shared memory and drains them as a
+// queue, a lane fetching the next state when its own search ends (refills batched, results stored coalesced at the
+// end) -- 23 lanes active, but 44 % more thread-instructions for the queue handling: 0.755 ms against 0.685 ms.
 __global__ void __launch_bounds__(256, 4) nv_level_kernel(const __grid_constant__ NvDev P, const __grid_constant__ NvLevelArgs A) {
     const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (e >= A.N) return;
