@@ -1,10 +1,18 @@
 """small launch sequences for the round-2 ncu captures (one target per invocation):
-    python tools/prof_r02.py inv_lost | inv_backlog | inv_random | inv_wide | inv_step | nv | nv_step | net | net_step | net64"""
+    python tools/prof_r02.py inv_lost | inv_backlog | inv_random | inv_wide | inv_step | nv | nv_step | net | net_step | net64 | report"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import or_gym_inventory_b200 as pkg
 which = sys.argv[1]
+if which == "report":   # the evaluation-report kernels (csrc/report.cu) on one rollout's outputs, twice
+    env = pkg.InvManagementLostSalesEnv(num_envs=1 << 24, device="cuda:0")
+    out = env.rollout("base_stock", seed=5000, safety_factor=1.0, want=("ep_return", "stats32"))
+    rep, scr = pkg.evaluation_report_device(out, 30)
+    rep, scr = pkg.evaluation_report_device(out, 30, report=rep, scratch=scr)
+    torch.cuda.synchronize()
+    print("ok", pkg.report_to_dict(rep)["MedianReward"])
+    sys.exit(0)
 if which.startswith("inv"):
     N = 1 << 24
     cls = pkg.InvManagementBacklogEnv if which == "inv_backlog" else pkg.InvManagementLostSalesEnv
