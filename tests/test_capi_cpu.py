@@ -122,6 +122,23 @@ def test_streaming_step_kernel_form_follows_node_order(lib, monkeypatch):
     assert form(P)[0] == "twopass"
 
 
+def test_large_graph_kernels_compile_without_gpu(lib):
+    """BASELINE config 5's synthetic 64-node network: the generator picks the streaming STEP form on its own (graph
+    size), in its single-pass variant, with the float32 ring copy for the observation kernel; NVRTC accepts the ~5600
+    generated lines for sm_100a."""
+    P = pkg.NetInvMgmtParams(graph=pkg.synthetic_graph(64), num_periods=30, backlog=False)
+    keep = []
+    cfg = P.to_c(keep)
+    need = C.c_int64(0)
+    buf = C.create_string_buffer(8 << 20)
+    rc = lib.orgym_netinv_codegen(C.byref(cfg), 1, buf, len(buf), C.byref(need))
+    assert rc == 0, lib.orgym_last_error()
+    src = buf.value.decode()
+    assert len(src) == need.value and f"#define NE {len(P.reorder_links)}" in src and len(P.reorder_links) == 88
+    assert "step_kernel_kind=stream" in src and "stream_form=onepass" in src
+    assert "float* const r32" in src and "__syncthreads();" in src.split("stream_form=onepass")[1].split("net_jit_rollout")[0]
+
+
 @pytest.mark.parametrize("kind", ["default_lost", "default_backlog", "zero_lead", "binomial"])
 def test_serial_rollout_specialiser_compiles_without_gpu(lib, kind):
     """invmgmt_jit.cu: configuration -> straight-line CUDA for the fused rollout -> NVRTC compile check for sm_100a."""
